@@ -1,0 +1,185 @@
+/* liburir -- C-ABI of the B200-native unet-rir hot path (sm_100a only).
+ *
+ * The reference (igmsalinas/unet-rir) is pure Python/TensorFlow and has no FFI of its own
+ * (SURVEY.md 8b); every device op it triggers is a TF/cuDNN/librosa library call. This header is
+ * therefore the boundary a maintainer of the reference would bind (ctypes stub shown in
+ * INTEGRATION.md) to replace those calls one for one. Each entry point cites the reference
+ * call site(s) it stands in for (paths relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, < 0 on error (URIR_ERR_*); urir_last_error() gives the thread-local
+ *     message. Shapes that the library does not support fail loudly; there is no CPU fallback.
+ *   - never allocate, never synchronise, never own memory; all pointers are DEVICE pointers
+ *     unless the argument name ends in _host; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so calls are CUDA-graph capturable.
+ *   - activations are NHWC. A tensor may live inside a wider buffer (skip-concat slices):
+ *     `*_ld` is the number of elements per pixel of the holding buffer, `*_coff` the channel
+ *     offset of the tensor inside it.
+ *   - conv weights are passed in two bf16 layouts produced by urir_weight_prep():
+ *       w_ck : [R*S][C][K]  (== Keras HWIO, and == Keras Conv2DTranspose HWOI of the
+ *                             transposed layer)
+ *       w_kc : [R*S][K][C]
+ */
+#ifndef URIR_H_
+#define URIR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URIR_VERSION 100
+
+#define URIR_OK           0
+#define URIR_ERR_ARG     -1   /* bad / unsupported shape or argument           */
+#define URIR_ERR_CUDA    -2   /* CUDA runtime / driver error                   */
+#define URIR_ERR_UNSUP   -3   /* requested implementation cannot run the shape */
+
+#define URIR_F32   0
+#define URIR_BF16  1
+
+#define URIR_IMPL_AUTO   0    /* tcgen05 implicit GEMM when the shape qualifies, else SIMT */
+#define URIR_IMPL_SIMT   1    /* CUDA-core direct convolution                              */
+#define URIR_IMPL_TC     2    /* tcgen05 implicit GEMM or URIR_ERR_UNSUP                   */
+
+#define URIR_ACT_NONE    0
+#define URIR_ACT_SIGMOID 1
+
+/* One strided convolution y[N,P,Q,K] = conv(x[N,H,W,C], w[R,S,C,K]) (+bias), TF "SAME"
+ * geometry given explicitly. Conv2DTranspose layers are described by the strided conv they are
+ * the input-gradient of (x = the LARGE tensor). */
+typedef struct urir_conv_desc {
+    int32_t N, H, W, C;         /* x dims                                             */
+    int32_t K, R, S;            /* filter count and window                            */
+    int32_t stride;             /* 1 or 2, both axes                                  */
+    int32_t pad_top, pad_left;  /* leading pads; trailing pads are implied by P, Q    */
+    int32_t P, Q;               /* y spatial dims                                     */
+    int32_t x_ld, x_coff;       /* x buffer: elements per pixel, channel offset       */
+    int32_t y_ld, y_coff;       /* y buffer: elements per pixel, channel offset       */
+    int32_t x_dtype, y_dtype;   /* URIR_F32 | URIR_BF16                               */
+    int32_t impl;               /* URIR_IMPL_*                                        */
+    int32_t act;                /* fprop only: URIR_ACT_* applied after bias          */
+    int32_t accumulate;         /* fprop/dgrad: out += result instead of out = result */
+} urir_conv_desc;
+
+typedef struct urir_stft_desc {
+    int32_t n_fft, win_length, hop_length;  /* dataset.py:62-64 : 256, 128, 64          */
+    int32_t n_samples;                      /* 9600 = 0.2 s x 48 kHz (dataset.py:66-67)  */
+    int32_t n_bins, n_frames;               /* 129, 151 (postprocess.py:54)              */
+    int32_t H_pad, W_pad;                   /* 144, 160 (dataset.py:70)                  */
+    int32_t pad_mode;                       /* 0 = constant (librosa>=0.10), 1 = reflect */
+    int32_t remove_mean;                    /* Loader.load mean removal preprocess.py:56 */
+    int32_t normalized;                     /* 1: spec holds Normalizer-normalised amp/phase
+                                               (preprocess.py:26-41); 0: raw |S| and angle(S)  */
+} urir_stft_desc;
+
+/* ---- library state ------------------------------------------------------------------- */
+int         urir_version(void);
+const char* urir_last_error(void);
+/* number of kernels launched by this library since load; kind 0 = all, 1 = tcgen05 only */
+long long   urir_launch_count(int kind);
+
+/* ---- convolutions: replace tf.keras Conv2D / Conv2DTranspose and their autodiff ------- */
+/* Conv2D forward (dl_models/u_net.py:269-276, 366, 248, 262). Also Conv2DTranspose's
+ * input-gradient. `stats` (optional, fp32[2*K], caller-zeroed) receives per-channel sum and
+ * sum of squares of the output for the BatchNormalization that follows (u_net.py:367-368). */
+int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, const void* w_kc,
+                      const float* bias, void* y, float* stats, void* stream);
+/* Conv2D input-gradient (tape.gradient, amp_phase_trainer.py:138) and Conv2DTranspose forward
+ * (dl_models/u_net.py:297-304): dx[N,H,W,C] = sum dy[N,P,Q,K] * w (+bias).
+ * `stats` (optional, fp32[2*C], caller-zeroed): per-channel sum / sum of squares of dx -- the
+ * sum is the bias gradient of the layer that produced x. */
+int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck, const void* w_kc,
+                      const float* bias, void* dx, float* stats, void* stream);
+/* Conv2D / Conv2DTranspose weight gradient: dw[R,S,C,K] fp32 (HWIO) = sum x * dy; overwritten.
+ * For a Conv2DTranspose layer pass x = gradient of its output, dy = its input. */
+int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw,
+                      void* stream);
+/* fp32 HWIO master weights -> the two bf16 operand layouts. */
+int urir_weight_prep(const float* w_hwio, void* w_ck, void* w_kc, int taps, int C, int K,
+                     void* stream);
+/* per-channel sum over pixels (bias gradients): out[c] = sum_p x[p*ld + coff + c]; overwritten. */
+int urir_channel_sum(const void* x, int dtype, long long npix, int C, int ld, int coff,
+                     float* out, void* stream);
+
+/* ---- BatchNormalization + ReLU (u_net.py:367-369; Keras eps 1e-3, momentum .99) -------- */
+/* training: stats = [sum, sumsq] over `count` pixels -> scale_shift[2C], mean_rstd[2C], and
+ * moving stats update; inference (stats == NULL): scale/shift from the moving statistics. */
+int urir_bn_finalize(const float* stats, double count, const float* gamma, const float* beta,
+                     float* moving_mean, float* moving_var, float momentum, float eps,
+                     int unbiased_moving_var, float* scale_shift, float* mean_rstd, int C,
+                     void* stream);
+/* y = relu(x*scale + shift); x, y bf16 (y may be a concat slice, or alias x). relu != 0. */
+int urir_bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* scale_shift,
+                     void* y, int y_ld, int y_coff, long long npix, int C, int relu, void* stream);
+/* sums[2C] (overwritten) = [sum g, sum g*xhat], g = dy * (x*scale+shift > 0). */
+int urir_bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld,
+                            int x_coff, const float* scale_shift, const float* mean_rstd,
+                            float* sums, long long npix, int C, void* stream);
+/* dx = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n) (bf16); dgamma = sum_gx; dbeta = sum_g;
+ * dbias (optional) = sum over pixels of dx = gradient of the preceding conv's bias. */
+int urir_bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld,
+                           int x_coff, const float* scale_shift, const float* mean_rstd,
+                           const float* gamma, const float* sums, void* dx, int dx_ld,
+                           int dx_coff, float* dgamma, float* dbeta, float* dbias, long long npix,
+                           int C, void* stream);
+
+/* ---- vector block (u_net.py:253-263) --------------------------------------------------- */
+/* Embedding(2000,256) + Flatten: out bf16 [B, T*D] */
+int urir_embedding_fwd(const int32_t* idx, const float* table, void* out, int B, int T, int D,
+                       int vocab, void* stream);
+/* dtable fp32 [vocab, D] (overwritten) += scatter of dx fp32 [B, T*D] */
+int urir_embedding_bwd(const int32_t* idx, const float* dx, float* dtable, int B, int T, int D,
+                       int vocab, void* stream);
+/* Dense + Dropout: out bf16 [B,N] = (x bf16 [B,Kd] @ w bf16 [Kd,N] + bias) * mask (mask may be
+ * NULL); ws = caller-provided fp32 [B,N] split-K scratch (zeroed by the call). */
+int urir_dense_fwd(const void* x, const void* w, const float* bias, const float* mask, void* out,
+                   float* ws, int B, int Kd, int N, void* stream);
+/* dy_eff = dy (bf16 [B,N]) * mask;  dw fp32 [Kd,N] = x^T dy_eff;  db fp32 [N];
+ * dx fp32 [B,Kd] = dy_eff @ w^T.  All outputs overwritten. */
+int urir_dense_bwd(const void* x, const void* w, const void* dy, const float* mask, float* dw,
+                   float* db, float* dx, int B, int Kd, int N, void* stream);
+/* inverted-dropout mask {0, 1/(1-rate)} from a counter-based generator; the stream position is
+ * (seed, *step_dev) so CUDA-graph replays draw fresh masks. */
+int urir_dropout_mask(float* mask, long long n, float rate, uint64_t seed,
+                      const int32_t* step_dev, void* stream);
+
+/* ---- loss (amp_phase_trainer.py:143-168 and main_training.py:203-235) ------------------ */
+/* y_true, y_pred fp32 [npix, 2] (amp, phase). losses[4] (overwritten) =
+ *   [w_amp*SSE + w_ph*sum(1-cos), mean(1-cos), mean sq err, 0];
+ * grad (optional, fp32 [npix,2]) = dL/dy_pred, times y(1-y) when sigmoid_bwd != 0 (the head's
+ * "sigmoid_layer", u_net.py:249). */
+int urir_ampphase_loss(const float* y_true, const float* y_pred, long long npix, float w_amp,
+                       float w_ph, int sigmoid_bwd, float* losses, float* grad, void* stream);
+
+/* ---- optimiser (amp_phase_trainer.py:30-35,139 ; Keras conventions) ------ */
+/* flat Adam over n contiguous fp32 elements; lr and step (0-based count of completed steps)
+ * are read from device memory so a captured graph follows the LR schedule. */
+int urir_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev,
+              const int32_t* step_dev, float beta1, float beta2, float eps, void* stream);
+int urir_sgd(float* p, const float* g, long long n, const float* lr_dev, void* stream);
+int urir_step_increment(int32_t* step_dev, void* stream);
+/* y += a*x (fp32) -- L2 kernel-regulariser gradient of the DP loss (main_training.py:232-233) */
+int urir_axpy(float* y, const float* x, float a, long long n, void* stream);
+/* out[0] (+)= scale * sum(x^2) */
+int urir_sumsq(const float* x, long long n, float scale, float* out, int accumulate, void* stream);
+/* elementwise helpers for the alternate block modes (u_net.py:337,359) and casts */
+int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+int urir_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+
+/* ---- signal path (preprocess.py:13-113, postprocess.py:78-133) ------------------------- */
+/* Loader mean removal + FeatureExtractor.extract + Normalizer.normalize + TensorPadder:
+ * wav fp32 [B, n_samples] -> spec fp32 [B, H_pad, W_pad, 2] */
+int urir_stft_ampphase(const float* wav, int B, const urir_stft_desc* d, float* spec,
+                       void* stream);
+/* PostProcess.post_process, algorithm 'ph': spec fp32 [B,H_pad,W_pad,2] -> wav fp32
+ * [B, n_samples] */
+int urir_istft_from_ampphase(const float* spec, int B, const urir_stft_desc* d, float* wav,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URIR_H_ */

@@ -1,0 +1,140 @@
+"""GPU parity: conv fprop / dgrad / wgrad through the C-ABI (both the tcgen05 implicit-GEMM path and
+the CUDA-core path) against the CPU oracle's TF-SAME convolutions on the same seeded bf16-rounded
+inputs. Tolerances: bf16 outputs rel-L2 <= 4e-3 (one bf16 rounding of an fp32-accumulated result);
+fp32 outputs (wgrad, stats) rel-L2 <= 2e-4 (summation order only)."""
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+import urir_testutil as U
+from unet_rir_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 4e-3
+F32_TOL = 2e-4
+
+# (N, H, W, C, K, k, stride): every (k, stride, Cin, Cout) class of the canonical U-Net
+# at reduced spatial size, plus the kernels=6 default and ragged tiles.
+CONV_CASES = [
+    (2, 16, 32, 32, 32, 3, 1),      # E1b / D5b class (BLOCK_K=32 swizzle-64 path)
+    (2, 16, 32, 64, 32, 3, 1),      # D5a class
+    (3, 12, 20, 64, 64, 3, 1),      # ragged box, batch 3
+    (2, 12, 20, 128, 64, 3, 1),     # D4a class
+    (2, 18, 20, 128, 128, 3, 1),    # E3b class
+    (2, 9, 10, 256, 128, 3, 1),     # D3a class, tile spanning images
+    (4, 9, 10, 512, 512, 3, 1),     # E5b class
+    (2, 16, 32, 32, 64, 3, 2),      # E2a class (stride 2, Cin 32)
+    (2, 24, 40, 64, 128, 3, 2),     # E3a class
+    (2, 18, 20, 256, 512, 3, 2),    # E5a class
+    (2, 16, 16, 64, 64, 6, 1),      # kernels=6, stride 1 (pad 2,3)
+    (2, 16, 16, 64, 128, 6, 2),     # kernels=6, stride 2 (pad 2,2)
+]
+
+
+def _inputs(N, H, W, Cc, K, k, stride, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    P, _ = L.same_pad(H, k, stride)
+    Q, _ = L.same_pad(W, k, stride)
+    x = U.bf16_round(torch.randn(N, H, W, Cc, generator=g))
+    w = U.bf16_round(torch.randn(k, k, Cc, K, generator=g) / (k * (Cc ** 0.5)))
+    bias = torch.randn(K, generator=g)
+    dy = U.bf16_round(torch.randn(N, P, Q, K, generator=g))
+    return x, w, bias, dy, P, Q
+
+
+def _oracle_fprop(x, w, bias, stride):
+    return O.conv2d_same(x.permute(0, 3, 1, 2), w, bias, stride).permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("impl", [L.IMPL_SIMT, L.IMPL_TC], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+def test_fprop_dgrad_wgrad(case, impl):
+    N, H, W, Cc, K, k, stride = case
+    x, w, bias, dy, P, Q = _inputs(*case)
+    xg, dyg = x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16)
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    bg = bias.cuda()
+    d = U.conv_desc(N, H, W, Cc, K, k, stride, impl=impl)
+
+    # ---- fprop (+ fused per-channel statistics)
+    y = torch.empty(N, P, Q, K, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2 * K, device="cuda")
+    U.run_fprop(d, xg, w_ck, w_kc, bg, y, stats)
+    ref = _oracle_fprop(x, w, bias, stride)
+    assert U.rel_l2(y.float(), ref) < BF16_TOL
+    assert U.rel_l2(stats[:K], ref.sum(dim=(0, 1, 2))) < 5e-3 or U.max_abs(stats[:K], ref.sum(dim=(0, 1, 2))) < 1e-2
+    assert U.rel_l2(stats[K:], (ref ** 2).sum(dim=(0, 1, 2))) < F32_TOL * 10
+
+    # ---- dgrad (the oracle's autograd of the same conv) with bias (= Conv2DTranspose forward)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = _oracle_fprop(xr, wr, None, stride)
+    gx, gw = torch.autograd.grad(yr, [xr, wr], dy)
+    cbias = torch.randn(Cc, generator=torch.Generator().manual_seed(7))
+    dx = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    dstats = torch.zeros(2 * Cc, device="cuda")
+    U.run_dgrad(d, dyg, w_ck, w_kc, cbias.cuda(), dx, dstats)
+    refdx = gx + cbias
+    assert U.rel_l2(dx.float(), refdx) < BF16_TOL
+    assert U.max_abs(dstats[:Cc], refdx.sum(dim=(0, 1, 2))) < 2e-3 * float(refdx.abs().sum(dim=(0, 1, 2)).max())
+
+    # ---- dgrad with accumulate
+    base = U.bf16_round(torch.randn(N, H, W, Cc, generator=torch.Generator().manual_seed(9)))
+    dx2 = base.cuda().to(torch.bfloat16)
+    d.accumulate = 1
+    U.run_dgrad(d, dyg, w_ck, w_kc, None, dx2, None)
+    d.accumulate = 0
+    assert U.rel_l2(dx2.float(), gx + base) < BF16_TOL
+
+    # ---- wgrad
+    dw = torch.full((k, k, Cc, K), 3.0, device="cuda")      # must be overwritten, not accumulated
+    U.run_wgrad(d, xg, dyg, dw)
+    assert U.rel_l2(dw, gw) < F32_TOL
+
+
+def test_conv_transpose_matches_oracle():
+    """Conv2DTranspose(k, s=2, SAME) forward == urir_conv2d_dgrad of the strided conv, written into
+    the right half of a concat buffer (u_net.py:297-308)."""
+    for k in (3, 6):
+        g = torch.Generator().manual_seed(k)
+        N, Hs, Ws, Cin, Cout = 2, 9, 10, 64, 32
+        x = U.bf16_round(torch.randn(N, Hs, Ws, Cin, generator=g))
+        w = U.bf16_round(torch.randn(k, k, Cout, Cin, generator=g) / (k * 8))     # Keras (kh,kw,out,in)
+        bias = torch.randn(Cout, generator=g)
+        ref = O.conv2d_transpose_same(x.permute(0, 3, 1, 2), w, bias, 2).permute(0, 2, 3, 1)
+        for impl in (L.IMPL_SIMT, L.IMPL_TC):
+            cat = torch.zeros(N, 2 * Hs, 2 * Ws, 2 * Cout, dtype=torch.bfloat16, device="cuda")
+            w_ck, w_kc = U.prep_weights(w.cuda())
+            d = U.conv_desc(N, 2 * Hs, 2 * Ws, Cout, Cin, k, 2, x_ld=2 * Cout, x_coff=Cout, impl=impl)
+            U.run_dgrad(d, x.cuda().to(torch.bfloat16), w_ck, w_kc, bias.cuda(), cat, None)
+            assert U.rel_l2(cat[..., Cout:].float(), ref) < BF16_TOL, (k, impl)
+            assert float(cat[..., :Cout].float().abs().max()) == 0.0      # left half untouched
+
+
+def test_stem_and_head_shapes():
+    """The two bandwidth-bound layers that run on CUDA cores by design: fp32 2-channel stem and the
+    6x6 32->2 sigmoid head (u_net.py:269-276 with Cin=2; u_net.py:248-249)."""
+    g = torch.Generator().manual_seed(3)
+    N, H, W = 2, 16, 32
+    x = torch.rand(N, H, W, 2, generator=g)
+    w = U.bf16_round(torch.randn(3, 3, 2, 32, generator=g) * 0.2)
+    b = torch.randn(32, generator=g) * 0.1
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    y = torch.empty(N, H, W, 32, dtype=torch.bfloat16, device="cuda")
+    d = U.conv_desc(N, H, W, 2, 32, 3, 1, x_dtype=L.F32)
+    U.run_fprop(d, x.cuda(), w_ck, w_kc, b.cuda(), y)
+    assert U.rel_l2(y.float(), _oracle_fprop(x, w, b, 1)) < BF16_TOL
+    with pytest.raises(L.UrirError):
+        d.impl = L.IMPL_TC
+        U.run_fprop(d, x.cuda(), w_ck, w_kc, b.cuda(), y)
+
+    xh = U.bf16_round(torch.randn(N, H, W, 32, generator=g))
+    wh = U.bf16_round(torch.randn(6, 6, 32, 2, generator=g) * 0.05)
+    bh = torch.randn(2, generator=g) * 0.1
+    w_ck, w_kc = U.prep_weights(wh.cuda())
+    out = torch.empty(N, H, W, 2, device="cuda")
+    dh = U.conv_desc(N, H, W, 32, 2, 6, 1, y_dtype=L.F32, act=L.ACT_SIGMOID)
+    U.run_fprop(dh, xh.cuda().to(torch.bfloat16), w_ck, w_kc, bh.cuda(), out)
+    ref = torch.sigmoid(_oracle_fprop(xh, wh, bh, 1))
+    assert U.max_abs(out, ref) < 1e-5

@@ -1,0 +1,118 @@
+"""GPU parity of the whole U-Net path: engine forward / backward / train step (bf16 tcgen05 path and
+the CUDA-core cross-check) against the fp32 CPU oracle on identical weights, inputs and dropout mask.
+
+Tolerances (bf16 activations and GEMM operands vs the oracle's fp32; TF itself would run these convs
+in TF32): per-layer activations rel-L2 <= 1.5e-2, sigmoid output abs <= 1e-2 and rel-L2
+<= 5e-3, losses rel 2e-3, gradients rel-L2 <= 5e-2 per tensor (biases of BN-followed convs, whose true
+gradient is analytically zero, are checked in absolute terms). tcgen05 vs CUDA-core engine runs, which
+share the arithmetic contract, must agree to 3e-3."""
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+import urir_testutil as U
+from unet_rir_b200 import _lib as L
+from unet_rir_b200.engine import UNetEngine
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B=2, kernels=3, seed=0, shape=(144, 160, 2)):
+    g = torch.Generator().manual_seed(seed)
+    om = O.UNetOracle(input_shape=shape, kernels=kernels)
+    params = O.init_params(om.plan, seed=500)
+    # make BN affine / biases non-trivial so their gradients are exercised
+    for n, _, kind in om.plan:
+        if kind in ("gamma",):
+            params[n] = 1 + 0.2 * torch.randn(params[n].shape, generator=g)
+        elif kind in ("beta", "bias"):
+            params[n] = 0.1 * torch.randn(params[n].shape, generator=g)
+    x = torch.rand(B, *shape, generator=g)
+    y = torch.rand(B, *shape, generator=g)
+    x[:, 129:], x[:, :, 151:], y[:, 129:], y[:, :, 151:] = 0, 0, 0, 0     # TensorPadder zeros
+    emb = torch.randint(0, 2000, (B, 2, 16), generator=g, dtype=torch.int32)
+    dim = (shape[0] // 16) * (shape[1] // 16) * 16
+    mask = (torch.rand(B, dim, generator=g) > 0.3).float() / 0.7
+    return om, params, x, y, emb, mask
+
+
+@pytest.mark.parametrize("kernels", [3, 6])
+def test_forward_eval_matches_oracle(kernels):
+    om, params, x, y, emb, mask = _setup(B=2, kernels=kernels)
+    eng = UNetEngine(kernels=kernels)
+    eng.load_state_dict(params)
+    out = eng.forward(x.cuda(), emb.cuda(), training=False).float().cpu()
+    ref = om.forward(params, x, emb, training=False)
+    assert U.max_abs(out, ref) < 1e-2 and U.rel_l2(out, ref) < 5e-3
+
+
+def test_train_forward_backward_matches_oracle():
+    om, params, x, y, emb, mask = _setup(B=2, kernels=3)
+    om.taps = {}
+    st = O.new_opt_state(params, om.plan)
+    (loss, lp, ls), grads, ref_out = O.train_step(om, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    taps = {k: v.detach() for k, v in om.taps.items()}
+
+    results = {}
+    for impl in (L.IMPL_SIMT, L.IMPL_AUTO):
+        eng = UNetEngine(kernels=3, impl=impl)
+        eng.load_state_dict(params)
+        out = eng.forward(x.cuda(), emb.cuda(), training=True, dropout_mask=mask.cuda())
+        dbg = eng.debug_tensors()
+        for name, t in dbg.items():
+            if name in taps:
+                assert U.rel_l2(t, taps[name]) < 1.5e-2, (impl, name, U.rel_l2(t, taps[name]))
+        assert U.max_abs(out.float(), ref_out) < 1e-2 and U.rel_l2(out.float(), ref_out) < 5e-3
+        n = 2 * 144 * 160
+        losses = eng.loss_and_grad(y.cuda(), 1.0 / n, 1.0 / n)
+        assert abs(float(losses[0]) - float(loss)) < 2e-3 * float(loss)
+        assert abs(float(losses[1]) - float(lp)) < 2e-3 * float(lp)
+        assert abs(float(losses[2]) - float(ls)) < 2e-3 * float(ls)
+        eng.backward(eng._buffers(2)["g_out"])
+        torch.cuda.synchronize()
+        bad = []
+        for name in eng.trainable_names():
+            got, ref = eng.grad[name].cpu(), grads[name]
+            scale = float(ref.abs().max())
+            is_dead_bias = name.endswith(".b") and (".blk." in name or ".fuse" in name)
+            if is_dead_bias:      # true gradient is 0 (BatchNorm removes the mean); only rounding noise
+                ok = U.max_abs(got, ref) < 2e-3
+            else:
+                ok = U.rel_l2(got, ref) < 5e-2 or U.max_abs(got, ref) < 1e-6 + 1e-3 * scale
+            if not ok:
+                bad.append((name, U.rel_l2(got, ref), U.max_abs(got, ref), scale))
+        assert not bad, (impl, bad)
+        results[impl] = {k: v.clone() for k, v in eng.grad.items()}
+        # moving statistics followed Keras momentum .99
+        new_stats = {}
+        om.forward(params, x, emb, training=True, dropout_mask=mask, new_stats=new_stats)
+        for k, v in new_stats.items():
+            assert U.rel_l2(eng.state[k].cpu(), v) < 2e-2 or U.max_abs(eng.state[k].cpu(), v) < 1e-3, k
+    # the two device paths share the arithmetic contract
+    for name in results[L.IMPL_SIMT]:
+        a, b = results[L.IMPL_SIMT][name], results[L.IMPL_AUTO][name]
+        assert U.rel_l2(a, b) < 2e-2 or U.max_abs(a, b) < 2e-3, name
+
+
+def test_adam_step_moves_parameters_like_oracle():
+    om, params, x, y, emb, mask = _setup(B=2, kernels=3, seed=1)
+    eng = UNetEngine(kernels=3)
+    eng.load_state_dict(params)
+    st = O.new_opt_state(params, om.plan)
+    p0 = {k: v.clone() for k, v in params.items()}
+    lr = 1e-3
+    O.train_step(om, params, st, x, y, emb, lr, dropout_mask=mask, apply=True)
+    eng.set_lr(lr)
+    eng.forward(x.cuda(), emb.cuda(), training=True, dropout_mask=mask.cuda())
+    n = 2 * 144 * 160
+    eng.loss_and_grad(y.cuda(), 1.0 / n, 1.0 / n)
+    eng.backward(eng._buffers(2)["g_out"])
+    eng.adam_step()
+    assert int(eng.step_dev) == 1
+    # first Adam step moves every weight by ~lr*sign(g): compare the update direction and size
+    for name in ("enc3.blk.c1.w", "dec2.fuse.w", "dec5.up.w", "vec.dense.w", "head.w", "enc1.down.w"):
+        du_ref = params[name] - p0[name]
+        du = eng.param[name].cpu() - p0[name]
+        agree = float((torch.sign(du) == torch.sign(du_ref)).float().mean())
+        assert agree > 0.97, (name, agree)
+        assert abs(float(du.abs().mean()) - float(du_ref.abs().mean())) < 0.05 * float(du_ref.abs().mean()), name

@@ -1,0 +1,201 @@
+"""GPU parity of the bandwidth-bound kernels through the C-ABI against CPU restatements:
+BatchNorm+ReLU fwd/bwd, amp/phase loss, Adam, the vector block, STFT / iSTFT."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import signal_oracle as SO
+from oracle import unet_oracle as O
+import urir_testutil as U
+from unet_rir_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bn_relu_forward_backward():
+    g = torch.Generator().manual_seed(0)
+    N, H, W, Cc = 3, 10, 12, 64
+    ld, coff = 128, 64                       # live inside a concat buffer
+    x = U.bf16_round(torch.randn(N, H, W, Cc, generator=g) * 2 + 0.5)
+    gamma = torch.rand(Cc, generator=g) + 0.5
+    beta = torch.randn(Cc, generator=g) * 0.3
+    dy = U.bf16_round(torch.randn(N, H, W, Cc, generator=g))
+    npix = N * H * W
+    # oracle (training-mode BN with biased variance, eps 1e-3) + autograd
+    xr = x.clone().requires_grad_(True); gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
+    mean = xr.mean(dim=(0, 1, 2)); var = xr.var(dim=(0, 1, 2), unbiased=False)
+    yr = torch.relu((xr - mean) * torch.rsqrt(var + O.BN_EPS) * gr + br)
+    gx, gg, gb = torch.autograd.grad(yr, [xr, gr, br], dy)
+
+    xg = x.cuda().to(torch.bfloat16)
+    stats = torch.stack([x.sum(dim=(0, 1, 2)), (x * x).sum(dim=(0, 1, 2))]).flatten().cuda()
+    mm, mv = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    ss, mr = torch.empty(2 * Cc, device="cuda"), torch.empty(2 * Cc, device="cuda")
+    L.call("bn_finalize", stats.data_ptr(), float(npix), gamma.cuda().data_ptr(), beta.cuda().data_ptr(),
+           mm.data_ptr(), mv.data_ptr(), 0.99, 1e-3, 0, ss.data_ptr(), mr.data_ptr(), Cc)
+    assert U.rel_l2(mm, 0.01 * mean.detach()) < 1e-4
+    assert U.rel_l2(mv, 0.99 + 0.01 * var.detach()) < 1e-5
+    ybuf = torch.zeros(N, H, W, ld, dtype=torch.bfloat16, device="cuda")
+    L.call("bn_relu_fwd", xg.data_ptr(), Cc, 0, ss.data_ptr(), ybuf.data_ptr(), ld, coff, npix, Cc, 1)
+    assert U.rel_l2(ybuf[..., coff:].float(), yr.detach()) < 4e-3
+    assert float(ybuf[..., :coff].float().abs().max()) == 0.0
+
+    dybuf = torch.zeros(N, H, W, ld, dtype=torch.bfloat16, device="cuda")
+    dybuf[..., coff:] = dy.cuda().to(torch.bfloat16)
+    sums = torch.empty(2 * Cc, device="cuda")
+    L.call("bn_relu_bwd_reduce", dybuf.data_ptr(), ld, coff, xg.data_ptr(), Cc, 0, ss.data_ptr(), mr.data_ptr(),
+           sums.data_ptr(), npix, Cc)
+    dx = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    dgamma, dbeta, dbias = (torch.empty(Cc, device="cuda") for _ in range(3))
+    L.call("bn_relu_bwd_apply", dybuf.data_ptr(), ld, coff, xg.data_ptr(), Cc, 0, ss.data_ptr(), mr.data_ptr(),
+           gamma.cuda().data_ptr(), sums.data_ptr(), dx.data_ptr(), Cc, 0, dgamma.data_ptr(), dbeta.data_ptr(),
+           dbias.data_ptr(), npix, Cc)
+    assert U.rel_l2(dx.float(), gx) < 6e-3
+    assert U.rel_l2(dgamma, gg) < 1e-4
+    assert U.rel_l2(dbeta, gb) < 1e-4
+    assert U.max_abs(dbias, gx.sum(dim=(0, 1, 2))) < 0.05       # analytically zero; bf16 rounding noise
+
+    # inference mode: scale/shift from the moving statistics
+    L.call("bn_finalize", None, 0.0, gamma.cuda().data_ptr(), beta.cuda().data_ptr(), mm.data_ptr(), mv.data_ptr(),
+           0.99, 1e-3, 0, ss.data_ptr(), mr.data_ptr(), Cc)
+    rs = torch.rsqrt(mv.cpu() + 1e-3) * gamma
+    assert U.rel_l2(ss[:Cc], rs) < 1e-5
+    assert U.max_abs(ss[Cc:], beta - mm.cpu() * rs) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["amp_phase", "dp"])
+def test_ampphase_loss_and_grad(kind):
+    g = torch.Generator().manual_seed(1)
+    B, H, W = 3, 16, 20
+    yt = torch.rand(B, H, W, 2, generator=g)
+    z = torch.randn(B, H, W, 2, generator=g, requires_grad=True)
+    yp = torch.sigmoid(z)
+    if kind == "amp_phase":           # amp_phase_trainer.py:143-168
+        loss, lp, ls = O.amp_phase_loss(yt, yp)
+        w_amp = w_ph = 1.0 / (B * H * W)
+    else:                             # main_training.py:203-235, alpha .9, global batch 2B
+        alpha, gb = 0.9, 2 * B
+        loss = O.dp_loss(yt, yp, alpha, gb)
+        _, lp, ls = O.amp_phase_loss(yt, yp)
+        w_amp, w_ph = alpha / (H * W * 2 * gb), (1 - alpha) / (H * W * 2 * gb)
+    gz, = torch.autograd.grad(loss, z)
+    losses = torch.empty(4, device="cuda"); grad = torch.empty(B, H, W, 2, device="cuda")
+    L.call("ampphase_loss", yt.cuda().data_ptr(), yp.detach().cuda().data_ptr(), B * H * W, w_amp, w_ph, 1,
+           losses.data_ptr(), grad.data_ptr())
+    assert abs(float(losses[0]) - float(loss)) < 1e-5 * max(1.0, abs(float(loss)))
+    assert abs(float(losses[1]) - float(lp)) < 1e-5 and abs(float(losses[2]) - float(ls)) < 1e-6
+    assert U.rel_l2(grad, gz) < 1e-5
+
+
+def test_adam_matches_keras_convention():
+    g = torch.Generator().manual_seed(2)
+    n = 10007
+    p = torch.randn(n, generator=g); p0 = p.clone()
+    m, v = torch.zeros(n), torch.zeros(n)
+    pc, mc, vc = p.cuda(), m.cuda(), v.cuda()
+    lr = torch.tensor([1e-3], device="cuda"); step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    params, ms, vs = {"w": p}, {"w": m}, {"w": v}
+    for t in range(1, 4):
+        gr = torch.randn(n, generator=g) * (10.0 ** (t - 2))
+        O.keras_adam_step(params, {"w": gr}, ms, vs, t, 1e-3)
+        L.call("adam", pc.data_ptr(), gr.cuda().data_ptr(), mc.data_ptr(), vc.data_ptr(), n, lr.data_ptr(),
+               step.data_ptr(), 0.9, 0.999, 1e-7)
+        L.call("step_increment", step.data_ptr())
+    assert int(step) == 3
+    assert U.rel_l2(pc - p0.cuda(), p - p0) < 1e-5
+    assert U.rel_l2(vc, v) < 1e-5
+
+
+def test_vector_block_dense_embedding():
+    g = torch.Generator().manual_seed(4)
+    B, T, D, Nn = 5, 32, 256, 1440
+    idx = torch.randint(0, 2000, (B, T), generator=g, dtype=torch.int32)
+    table = (torch.rand(2000, D, generator=g) - 0.5) * 0.1
+    w = U.bf16_round((torch.rand(T * D, Nn, generator=g) - 0.5) * 0.05)
+    bias = torch.randn(Nn, generator=g) * 0.1
+    mask = (torch.rand(B, Nn, generator=g) > 0.3).float() / 0.7
+    x = U.bf16_round(table[idx.long()].reshape(B, -1))
+    ref = (x @ w + bias) * mask
+    xg = torch.empty(B, T * D, dtype=torch.bfloat16, device="cuda")
+    L.call("embedding_fwd", idx.cuda().data_ptr(), table.cuda().data_ptr(), xg.data_ptr(), B, T, D, 2000)
+    assert U.max_abs(xg.float(), x) == 0.0
+    wg = w.cuda().to(torch.bfloat16)
+    out = torch.empty(B, Nn, dtype=torch.bfloat16, device="cuda"); ws = torch.empty(B, Nn, device="cuda")
+    L.call("dense_fwd", xg.data_ptr(), wg.data_ptr(), bias.cuda().data_ptr(), mask.cuda().data_ptr(), out.data_ptr(),
+           ws.data_ptr(), B, T * D, Nn)
+    assert U.rel_l2(out.float(), ref) < 4e-3
+    dy = U.bf16_round(torch.randn(B, Nn, generator=g))
+    ge = dy * mask
+    dw = torch.empty(T * D, Nn, device="cuda"); db = torch.empty(Nn, device="cuda"); dx = torch.empty(B, T * D, device="cuda")
+    L.call("dense_bwd", xg.data_ptr(), wg.data_ptr(), dy.cuda().to(torch.bfloat16).data_ptr(), mask.cuda().data_ptr(),
+           dw.data_ptr(), db.data_ptr(), dx.data_ptr(), B, T * D, Nn)
+    assert U.rel_l2(dw, x.t() @ ge) < 1e-4
+    assert U.rel_l2(db, ge.sum(0)) < 1e-4
+    assert U.rel_l2(dx, ge @ w.t()) < 1e-4
+    dtab = torch.empty(2000, D, device="cuda")
+    L.call("embedding_bwd", idx.cuda().data_ptr(), dx.data_ptr(), dtab.data_ptr(), B, T, D, 2000)
+    ref_t = torch.zeros(2000, D).index_add_(0, idx.long().flatten(), dx.cpu().reshape(B * T, D))
+    assert U.rel_l2(dtab, ref_t) < 1e-5
+    # dropout mask: right keep-rate, right scale, new mask per step
+    m1 = torch.empty(B, Nn, device="cuda"); m2 = torch.empty(B, Nn, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("dropout_mask", m1.data_ptr(), B * Nn, 0.3, 500, step.data_ptr())
+    step += 1
+    L.call("dropout_mask", m2.data_ptr(), B * Nn, 0.3, 500, step.data_ptr())
+    assert set(np.unique(m1.cpu().numpy()).round(5)) <= {0.0, round(1 / 0.7, 5)}
+    assert abs(float((m1 > 0).float().mean()) - 0.7) < 0.03 and not torch.equal(m1, m2)
+
+
+def _stft_desc(pad_mode=0, normalized=1, remove_mean=1):
+    return L.StftDesc(256, 128, 64, 9600, 129, 151, 144, 160, pad_mode, remove_mean, normalized)
+
+
+@pytest.mark.parametrize("pad_mode", [0, 1], ids=["constant", "reflect"])
+def test_stft_ampphase_and_inverse(pad_mode):
+    rng = np.random.default_rng(0)
+    B = 5
+    wav = SO.synthetic_rir(B, rng) + 0.01            # non-zero mean, removed on device
+    d = _stft_desc(pad_mode)
+    spec = torch.empty(B, 144, 160, 2, device="cuda")
+    L.call("stft_ampphase", torch.from_numpy(wav).cuda().data_ptr(), B, C.byref(d), spec.data_ptr())
+    spec = spec.cpu().numpy()
+    mode = "constant" if pad_mode == 0 else "reflect"
+    for i in range(B):
+        ref = SO.preprocess(wav[i], pad_mode=mode)
+        assert np.abs(spec[i, :, :, 0] - ref[:, :, 0]).max() < 2e-4          # normalised log-amplitude
+        # phase is ill-conditioned where |S| ~ 0 and wraps at +-pi: compare as unit phasors where loud
+        loud = ref[:129, :151, 0] > 0.35
+        dphi = 2 * math.pi * (spec[i, :129, :151, 1] - ref[:129, :151, 1])
+        assert np.abs(np.sin(dphi / 2))[loud].max() < 2e-3
+        assert spec[i, 129:, :, :].max() == 0.0 and spec[i, :, 151:, :].max() == 0.0   # TensorPadder zeros
+    # inverse on the oracle's spectrogram: PostProcess.post_process
+    feat = np.stack([SO.preprocess(w, pad_mode="constant") for w in wav])
+    out = torch.empty(B, 9600, device="cuda")
+    L.call("istft_from_ampphase", torch.from_numpy(feat).cuda().data_ptr(), B, C.byref(_stft_desc()), out.data_ptr())
+    out = out.cpu().numpy()
+    for i in range(B):
+        ref = SO.post_process(feat[i])
+        missa = 20 * math.log10(np.linalg.norm(out[i] - ref) / np.linalg.norm(ref))
+        assert missa < -60.0, missa                                          # SURVEY 8c tolerance
+    # round trip wav -> GPU stft -> GPU istft (preprocess.py:201-205 prints this misalignment)
+    spec_g = torch.empty(B, 144, 160, 2, device="cuda")
+    L.call("stft_ampphase", torch.from_numpy(wav).cuda().data_ptr(), B, C.byref(_stft_desc()), spec_g.data_ptr())
+    back = torch.empty(B, 9600, device="cuda")
+    L.call("istft_from_ampphase", spec_g.data_ptr(), B, C.byref(_stft_desc()), back.data_ptr())
+    back = back.cpu().numpy()
+    for i in range(B):
+        x0 = SO.remove_mean(wav[i])
+        inner = slice(256, 9600 - 256)
+        assert 20 * math.log10(np.linalg.norm(back[i][inner] - x0[inner]) / np.linalg.norm(x0[inner])) < -60.0
+
+
+def test_unsupported_shapes_fail_loudly():
+    d = L.StftDesc(512, 128, 64, 9600, 257, 151, 272, 160, 0, 1, 1)
+    spec = torch.empty(1, 272, 160, 2, device="cuda"); wav = torch.zeros(1, 9600, device="cuda")
+    with pytest.raises(L.UrirError):
+        L.call("stft_ampphase", wav.data_ptr(), 1, C.byref(d), spec.data_ptr())
+    with pytest.raises(L.UrirError):
+        L.call("ampphase_loss", wav.data_ptr(), wav.data_ptr(), 3, 1.0, 1.0, 0, wav.data_ptr(), None)

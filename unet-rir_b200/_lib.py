@@ -1,0 +1,131 @@
+"""ctypes binding of liburir.so (the C-ABI declared in include/urir.h).
+
+The product path has no CPU fallback: if the library is missing, or a call fails, this raises.
+PyTorch is used only for device memory and streams; every `urir_*` call is enqueued on
+`torch.cuda.current_stream()` so the calls are CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liburir.so")
+
+F32, BF16 = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+ACT_NONE, ACT_SIGMOID = 0, 1
+
+
+class UrirError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "N", "H", "W", "C", "K", "R", "S", "stride", "pad_top", "pad_left", "P", "Q",
+        "x_ld", "x_coff", "y_ld", "y_coff", "x_dtype", "y_dtype", "impl", "act", "accumulate")]
+
+
+class StftDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_fft", "win_length", "hop_length", "n_samples", "n_bins", "n_frames", "H_pad", "W_pad",
+        "pad_mode", "remove_mean", "normalized")]
+
+
+_vp, _i, _ll, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_uint64
+_PROTOS = {
+    "urir_version": (C.c_int, []),
+    "urir_last_error": (C.c_char_p, []),
+    "urir_launch_count": (C.c_longlong, [_i]),
+    "urir_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "urir_conv2d_dgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "urir_conv2d_wgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "urir_weight_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "urir_channel_sum": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp]),
+    "urir_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _i, _vp]),
+    "urir_bn_relu_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _ll, _i, _i, _vp]),
+    "urir_bn_relu_bwd_reduce": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _ll, _i, _vp]),
+    "urir_bn_relu_bwd_apply": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
+                                    _vp, _ll, _i, _vp]),
+    "urir_embedding_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "urir_embedding_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "urir_dense_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "urir_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "urir_dropout_mask": (_i, [_vp, _ll, _f, _u64, _vp, _vp]),
+    "urir_ampphase_loss": (_i, [_vp, _vp, _ll, _f, _f, _i, _vp, _vp, _vp]),
+    "urir_adam": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _f, _f, _vp]),
+    "urir_sgd": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "urir_step_increment": (_i, [_vp, _vp]),
+    "urir_axpy": (_i, [_vp, _vp, _f, _ll, _vp]),
+    "urir_sumsq": (_i, [_vp, _ll, _f, _vp, _i, _vp]),
+    "urir_add_bf16": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "urir_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "urir_stft_ampphase": (_i, [_vp, _i, C.POINTER(StftDesc), _vp, _vp]),
+    "urir_istft_from_ampphase": (_i, [_vp, _i, C.POINTER(StftDesc), _vp, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib = None
+
+
+def load():
+    """Loads liburir.so; raises UrirError (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UrirError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                "(or unet-rir_b200/csrc/build.sh). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().urir_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise UrirError(f"{what or 'urir call'} failed (rc={rc}): {last_error()}")
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int | None:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def launch_count(kind: int = 0) -> int:
+    return int(load().urir_launch_count(kind))
+
+
+def call(name: str, *args):
+    """Calls `urir_<name>`; the last argument (stream) is appended automatically."""
+    fn = getattr(load(), "urir_" + name)
+    check(fn(*args, stream()), name)
+
+
+def same_pad(in_size: int, k: int, s: int):
+    """TF SAME geometry: out = ceil(in/s), total = max((out-1)s + k - in, 0), before = total//2."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return out, total // 2
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise UrirError(f"unsupported dtype {t.dtype}")

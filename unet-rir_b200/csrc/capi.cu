@@ -1,0 +1,220 @@
+// extern "C" surface of liburir (declared in include/urir.h): argument validation, path selection
+// (tcgen05 implicit GEMM vs CUDA-core direct conv), error strings, launch accounting.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <atomic>
+
+#include "urir_common.cuh"
+
+namespace urir {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches_all{0}, g_launches_tc{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+void count_launch(int kind) { g_launches_all++; if (kind == 1) g_launches_tc++; }
+
+// implemented in the other translation units
+int conv_fprop_simt_dispatch(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
+int conv_dgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
+int conv_wgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
+int weight_prep(const float*, void*, void*, int, int, int, cudaStream_t);
+bool igemm_fprop_supported(const urir_conv_desc*);
+bool igemm_dgrad_supported(const urir_conv_desc*);
+int conv_fprop_igemm(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
+int conv_dgrad_igemm(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
+bool wgrad_tc_supported(const urir_conv_desc*);
+int conv_wgrad_tc(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
+int bn_finalize(const float*, double, const float*, const float*, float*, float*, float, float, int, float*, float*, int, cudaStream_t);
+int bn_relu_fwd(const void*, int, int, const float*, void*, int, int, long long, int, int, cudaStream_t);
+int bn_relu_bwd_reduce(const void*, int, int, const void*, int, int, const float*, const float*, float*, long long, int, cudaStream_t);
+int bn_relu_bwd_apply(const void*, int, int, const void*, int, int, const float*, const float*, const float*, const float*,
+                      void*, int, int, float*, float*, float*, long long, int, cudaStream_t);
+int channel_sum(const void*, int, long long, int, int, int, float*, cudaStream_t);
+int ampphase_loss(const float*, const float*, long long, float, float, int, float*, float*, cudaStream_t);
+int adam(float*, const float*, float*, float*, long long, const float*, const int*, float, float, float, cudaStream_t);
+int sgd(float*, const float*, long long, const float*, cudaStream_t);
+int step_increment(int*, cudaStream_t);
+int axpy(float*, const float*, float, long long, cudaStream_t);
+int sumsq(const float*, long long, float, float*, int, cudaStream_t);
+int add_bf16(const void*, const void*, void*, long long, cudaStream_t);
+int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
+int embedding_fwd(const int*, const float*, void*, int, int, int, int, cudaStream_t);
+int embedding_bwd(const int*, const float*, float*, int, int, int, int, cudaStream_t);
+int dense_fwd(const void*, const void*, const float*, const float*, void*, float*, int, int, int, cudaStream_t);
+int dense_bwd(const void*, const void*, const void*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
+int dropout_mask(float*, long long, float, uint64_t, const int*, cudaStream_t);
+int stft_ampphase(const float*, int, const urir_stft_desc*, float*, cudaStream_t);
+int istft_from_ampphase(const float*, int, const urir_stft_desc*, float*, cudaStream_t);
+
+static int check_conv(const urir_conv_desc* d, const char* who) {
+    URIR_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
+    URIR_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0 && d->P > 0 && d->Q > 0,
+                   "%s: non-positive dimension", who);
+    URIR_CHECK_ARG(d->stride >= 1 && d->stride <= 2, "%s: stride %d unsupported (1 or 2)", who, d->stride);
+    URIR_CHECK_ARG(d->pad_top >= 0 && d->pad_left >= 0 && d->pad_top < d->R && d->pad_left < d->S, "%s: bad padding", who);
+    URIR_CHECK_ARG((d->P - 1) * d->stride - d->pad_top < d->H && (d->Q - 1) * d->stride - d->pad_left < d->W,
+                   "%s: output grid (%d,%d) reaches past the input", who, d->P, d->Q);
+    URIR_CHECK_ARG(d->x_ld >= d->x_coff + d->C && d->y_ld >= d->y_coff + d->K && d->x_coff >= 0 && d->y_coff >= 0,
+                   "%s: channel slice exceeds the buffer pitch", who);
+    URIR_CHECK_ARG((d->x_dtype == URIR_F32 || d->x_dtype == URIR_BF16) && (d->y_dtype == URIR_F32 || d->y_dtype == URIR_BF16),
+                   "%s: bad dtype", who);
+    return URIR_OK;
+}
+
+static int env_force_simt() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("URIR_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+
+}  // namespace urir
+
+using namespace urir;
+
+extern "C" {
+
+int urir_version(void) { return URIR_VERSION; }
+const char* urir_last_error(void) { return g_err; }
+long long urir_launch_count(int kind) { return kind == 1 ? g_launches_tc.load() : g_launches_all.load(); }
+
+int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, const void* w_kc, const float* bias,
+                      void* y, float* stats, void* stream) {
+    int rc = check_conv(d, "conv2d_fprop"); if (rc) return rc;
+    URIR_CHECK_ARG(x && y, "conv2d_fprop: null tensor");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc_ok = igemm_fprop_supported(d) && w_kc != nullptr;
+    if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the tcgen05 path");
+    const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
+    return use_tc ? conv_fprop_igemm(d, x, w_kc, bias, y, stats, st) : conv_fprop_simt_dispatch(d, x, w_ck, bias, y, stats, st);
+}
+
+int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck, const void* w_kc, const float* bias,
+                      void* dx, float* stats, void* stream) {
+    int rc = check_conv(d, "conv2d_dgrad"); if (rc) return rc;
+    URIR_CHECK_ARG(dy && dx, "conv2d_dgrad: null tensor");
+    URIR_CHECK_ARG(d->act == URIR_ACT_NONE, "conv2d_dgrad: activation not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc_ok = igemm_dgrad_supported(d) && w_ck != nullptr;
+    if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the tcgen05 path");
+    const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
+    return use_tc ? conv_dgrad_igemm(d, dy, w_ck, bias, dx, stats, st) : conv_dgrad_simt_dispatch(d, dy, w_kc, bias, dx, stats, st);
+}
+
+int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+    int rc = check_conv(d, "conv2d_wgrad"); if (rc) return rc;
+    URIR_CHECK_ARG(x && dy && dw, "conv2d_wgrad: null tensor");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc_ok = wgrad_tc_supported(d);
+    if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_wgrad: shape not supported by the tcgen05 path");
+    const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
+    return use_tc ? conv_wgrad_tc(d, x, dy, dw, st) : conv_wgrad_simt_dispatch(d, x, dy, dw, st);
+}
+
+int urir_weight_prep(const float* w, void* w_ck, void* w_kc, int taps, int C, int K, void* stream) {
+    URIR_CHECK_ARG(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, "weight_prep: bad args");
+    return weight_prep(w, w_ck, w_kc, taps, C, K, (cudaStream_t)stream);
+}
+
+int urir_channel_sum(const void* x, int dtype, long long npix, int C, int ld, int coff, float* out, void* stream) {
+    URIR_CHECK_ARG(x && out, "channel_sum: null tensor");
+    return channel_sum(x, dtype, npix, C, ld, coff, out, (cudaStream_t)stream);
+}
+
+int urir_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* mm, float* mv,
+                     float momentum, float eps, int unbiased, float* scale_shift, float* mean_rstd, int C, void* stream) {
+    return bn_finalize(stats, count, gamma, beta, mm, mv, momentum, eps, unbiased, scale_shift, mean_rstd, C, (cudaStream_t)stream);
+}
+int urir_bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* ss, void* y, int y_ld, int y_coff, long long npix,
+                     int C, int relu, void* stream) {
+    URIR_CHECK_ARG(x && y && ss && npix > 0, "bn_relu_fwd: bad args");
+    return bn_relu_fwd(x, x_ld, x_coff, ss, y, y_ld, y_coff, npix, C, relu, (cudaStream_t)stream);
+}
+int urir_bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
+                            const float* mr, float* sums, long long npix, int C, void* stream) {
+    URIR_CHECK_ARG(dy && x && ss && mr && sums && npix > 0, "bn_relu_bwd_reduce: bad args");
+    return bn_relu_bwd_reduce(dy, dy_ld, dy_coff, x, x_ld, x_coff, ss, mr, sums, npix, C, (cudaStream_t)stream);
+}
+int urir_bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
+                           const float* mr, const float* gamma, const float* sums, void* dx, int dx_ld, int dx_coff,
+                           float* dgamma, float* dbeta, float* dbias, long long npix, int C, void* stream) {
+    URIR_CHECK_ARG(dy && x && ss && mr && sums && dx && npix > 0, "bn_relu_bwd_apply: bad args");
+    return bn_relu_bwd_apply(dy, dy_ld, dy_coff, x, x_ld, x_coff, ss, mr, gamma, sums, dx, dx_ld, dx_coff, dgamma, dbeta,
+                             dbias, npix, C, (cudaStream_t)stream);
+}
+
+int urir_embedding_fwd(const int32_t* idx, const float* table, void* out, int B, int T, int D, int vocab, void* stream) {
+    URIR_CHECK_ARG(idx && table && out && B > 0 && T > 0, "embedding_fwd: bad args");
+    return embedding_fwd(idx, table, out, B, T, D, vocab, (cudaStream_t)stream);
+}
+int urir_embedding_bwd(const int32_t* idx, const float* dx, float* dtable, int B, int T, int D, int vocab, void* stream) {
+    URIR_CHECK_ARG(idx && dx && dtable && B > 0 && T > 0, "embedding_bwd: bad args");
+    return embedding_bwd(idx, dx, dtable, B, T, D, vocab, (cudaStream_t)stream);
+}
+int urir_dense_fwd(const void* x, const void* w, const float* bias, const float* mask, void* out, float* ws, int B,
+                   int Kd, int N, void* stream) {
+    URIR_CHECK_ARG(x && w && out && B > 0 && Kd > 0 && N > 0, "dense_fwd: bad args");
+    return dense_fwd(x, w, bias, mask, out, ws, B, Kd, N, (cudaStream_t)stream);
+}
+int urir_dense_bwd(const void* x, const void* w, const void* dy, const float* mask, float* dw, float* db, float* dx,
+                   int B, int Kd, int N, void* stream) {
+    URIR_CHECK_ARG(x && w && dy && B > 0 && Kd > 0 && N > 0, "dense_bwd: bad args");
+    return dense_bwd(x, w, dy, mask, dw, db, dx, B, Kd, N, (cudaStream_t)stream);
+}
+int urir_dropout_mask(float* mask, long long n, float rate, uint64_t seed, const int32_t* step_dev, void* stream) {
+    URIR_CHECK_ARG(mask && n > 0, "dropout_mask: bad args");
+    return dropout_mask(mask, n, rate, seed, step_dev, (cudaStream_t)stream);
+}
+
+int urir_ampphase_loss(const float* y_true, const float* y_pred, long long npix, float w_amp, float w_ph,
+                       int sigmoid_bwd, float* losses, float* grad, void* stream) {
+    URIR_CHECK_ARG(y_true && y_pred && losses, "ampphase_loss: null tensor");
+    return ampphase_loss(y_true, y_pred, npix, w_amp, w_ph, sigmoid_bwd, losses, grad, (cudaStream_t)stream);
+}
+
+int urir_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, const int32_t* step_dev,
+              float beta1, float beta2, float eps, void* stream) {
+    URIR_CHECK_ARG(p && g && m && v && lr_dev && step_dev, "adam: null tensor");
+    return adam(p, g, m, v, n, lr_dev, step_dev, beta1, beta2, eps, (cudaStream_t)stream);
+}
+int urir_sgd(float* p, const float* g, long long n, const float* lr_dev, void* stream) {
+    URIR_CHECK_ARG(p && g && lr_dev && n > 0, "sgd: bad args");
+    return sgd(p, g, n, lr_dev, (cudaStream_t)stream);
+}
+int urir_step_increment(int32_t* step_dev, void* stream) {
+    URIR_CHECK_ARG(step_dev, "step_increment: null");
+    return step_increment(step_dev, (cudaStream_t)stream);
+}
+int urir_axpy(float* y, const float* x, float a, long long n, void* stream) {
+    URIR_CHECK_ARG(y && x && n > 0, "axpy: bad args");
+    return axpy(y, x, a, n, (cudaStream_t)stream);
+}
+int urir_sumsq(const float* x, long long n, float scale, float* out, int accumulate, void* stream) {
+    URIR_CHECK_ARG(x && out && n > 0, "sumsq: bad args");
+    return sumsq(x, n, scale, out, accumulate, (cudaStream_t)stream);
+}
+int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+    URIR_CHECK_ARG(a && b && out && n > 0, "add_bf16: bad args");
+    return add_bf16(a, b, out, n, (cudaStream_t)stream);
+}
+int urir_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
+    URIR_CHECK_ARG(x && y && n > 0, "cast: bad args");
+    return cast_f32_to_bf16(x, y, n, (cudaStream_t)stream);
+}
+
+int urir_stft_ampphase(const float* wav, int B, const urir_stft_desc* d, float* spec, void* stream) {
+    URIR_CHECK_ARG(wav && spec, "stft: null tensor");
+    return stft_ampphase(wav, B, d, spec, (cudaStream_t)stream);
+}
+int urir_istft_from_ampphase(const float* spec, int B, const urir_stft_desc* d, float* wav, void* stream) {
+    URIR_CHECK_ARG(wav && spec, "istft: null tensor");
+    return istft_from_ampphase(spec, B, d, wav, (cudaStream_t)stream);
+}
+
+}  // extern "C"

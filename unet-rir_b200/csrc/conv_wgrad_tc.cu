@@ -1,0 +1,284 @@
+// tcgen05 weight-gradient kernel for sm_100a:
+//   dw[tap][c][k] (fp32, HWIO) = sum over output pixels  x[pixel + tap][c] * dy[pixel][k]
+// (Conv2D / Conv2DTranspose kernels' gradients under tape.gradient, amp_phase_trainer.py:138).
+//
+// GEMM view per tap: D[c (M = 128), k (N)] += A[c, pixels] * B[pixels, k], the reduction (GEMM-K)
+// runs over pixels. Both operands are the NHWC tensors exactly as they sit in HBM: a TMA box
+// {64 channels, bw x bh x bn pixels} lands as `KP` rows of 128 B, which is the canonical
+// MN-major (channel-contiguous) swizzled UMMA operand, so no transpose is ever materialised.
+// The same tap table / parity-view trick as conv_igemm.cu provides the shifted (and, for stride 2,
+// parity-strided) x tiles; TMA zero-fill supplies the SAME padding.
+// A CTA owns (tap group of T taps, 128-channel c tile, BLOCK_N k tile) and a contiguous range of
+// pixel tiles (split-K); T accumulators of BLOCK_N columns live in TMEM; the epilogue adds them
+// into dw with vectorised global reductions.
+#include "urir_common.cuh"
+#include "urir_tc.cuh"
+
+namespace urir {
+
+using namespace tc;
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int swizzle_bytes);
+
+struct WgradTap { short dh, dw; short map; short wtap; };
+
+struct WgradParams {
+    int bw, bh, bn, kp;             // pixel box, kp = bw*bh*bn (multiple of 16, <= 64)
+    int tiles_w, tiles_h, tiles_n;  // pixel tiles over (Q, P, N)
+    int tiles_per_cta, total_tiles;
+    int C, K;                       // channels of x and dy
+    int a_atom, b_atom;             // channels per TMA box / swizzle atom: 64 (128B) or 32 (64B)
+    int a_atoms, b_atoms;           // valid atoms per operand tile (<= 2 for A, BLOCK_N/b_atom for B)
+    int ntaps, n_mtiles;
+    float* dw;
+    WgradTap taps[36];
+};
+
+struct WgradMaps { CUtensorMap a[4]; CUtensorMap b; };
+
+constexpr int WG_KP = 64;                    // max pixels per stage
+constexpr int WG_A_BYTES = WG_KP * 256;      // 128 channels x 64 pixels x 2 B
+template <int BLOCK_N, int T, int STAGES>
+struct WgradSmem {
+    static constexpr int B_BYTES = WG_KP * BLOCK_N * 2;
+    static constexpr int STAGE_BYTES = T * WG_A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BLOCK_N, int T, int STAGES>
+__global__ void __launch_bounds__(192)
+conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ WgradParams p) {
+    using L = WgradSmem<BLOCK_N, T, STAGES>;
+    constexpr uint32_t TMEM_COLS = (T * BLOCK_N <= 32) ? 32 : (T * BLOCK_N <= 64) ? 64 : (T * BLOCK_N <= 128) ? 128
+                                 : (T * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(T * BLOCK_N <= 512, "accumulators exceed TMEM");
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N, 1, 1);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.y % p.n_mtiles, n_tile = blockIdx.y / p.n_mtiles;
+    const int tap0 = blockIdx.z * T;
+    const int tile_begin = blockIdx.x * p.tiles_per_cta;
+    int tile_end = tile_begin + p.tiles_per_cta; if (tile_end > p.total_tiles) tile_end = p.total_tiles;
+    const int n_iters = tile_end > tile_begin ? tile_end - tile_begin : 0;
+
+    const uint32_t a_row = p.a_atom * 2, b_row = p.b_atom * 2;         // bytes per smem row
+    const uint32_t a_swz = p.a_atom == 64 ? SWZ_128B : SWZ_64B, b_swz = p.b_atom == 64 ? SWZ_128B : SWZ_64B;
+    const uint32_t a_atom_bytes = p.kp * a_row, b_atom_bytes = p.kp * b_row;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 4 && lane == 0) { prefetch_tmap(&maps.b); prefetch_tmap(&maps.a[0]); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)T * p.a_atoms * a_atom_bytes + (uint32_t)p.b_atoms * b_atom_bytes;
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                int t = tile_begin + it;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = t * p.bn;
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                uint8_t* st_base = smem + stage * L::STAGE_BYTES;
+                mbar_expect_tx(full_bar + stage, bytes);
+#pragma unroll
+                for (int ti = 0; ti < T; ++ti) {
+                    const WgradTap tp = p.taps[tap0 + ti];
+                    for (int a = 0; a < p.a_atoms; ++a)
+                        tma_load_4d(&maps.a[tp.map], full_bar + stage, st_base + ti * WG_A_BYTES + a * a_atom_bytes,
+                                    m_tile * 128 + a * p.a_atom, w0 + tp.dw, h0 + tp.dh, n0);
+                }
+                for (int b = 0; b < p.b_atoms; ++b)
+                    tma_load_4d(&maps.b, full_bar + stage, st_base + T * WG_A_BYTES + b * b_atom_bytes,
+                                n_tile * BLOCK_N + b * p.b_atom, w0, h0, n0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        const uint32_t a_lbo = p.a_atoms > 1 ? a_atom_bytes : 0;     // single valid atom: alias it (rows >= C are discarded)
+        const uint32_t b_lbo = b_atom_bytes;
+        const int ksteps = p.kp / 16;
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0; it < n_iters; ++it) {
+            mbar_wait(full_bar + stage, phase);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t s_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                const uint32_t b_addr = s_addr + T * WG_A_BYTES;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t bd = make_smem_desc(b_addr + k * 16 * b_row, b_lbo, 8 * b_row, b_swz);
+#pragma unroll
+                    for (int ti = 0; ti < T; ++ti) {
+                        const uint64_t ad = make_smem_desc(s_addr + ti * WG_A_BYTES + k * 16 * a_row, a_lbo, 8 * a_row, a_swz);
+                        umma_bf16(tmem_base + ti * BLOCK_N, ad, bd, IDESC, (it | k) != 0);
+                    }
+                }
+                umma_commit(empty_bar + stage);
+                if (it == n_iters - 1) umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue: TMEM -> red.global.add into dw =====================
+        if (n_iters > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            fence_after_sync();
+            const int c = m_tile * 128 + warp * 32 + lane;
+            const bool valid = c < p.C;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int ti = 0; ti < T; ++ti) {
+                const int wtap = p.taps[tap0 + ti].wtap;
+                float* drow = p.dw + ((size_t)wtap * p.C + (valid ? c : 0)) * p.K + n_tile * BLOCK_N;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(lane_addr + ti * BLOCK_N + c0, r);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
+                }
+            }
+            fence_before_sync();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+// pixel box with product in {16,32,48,64}: every staged row must be a real (or zero-filled) pixel
+static void choose_kbox(int OW, int OH, int NB, int* bw, int* bh, int* bn) {
+    double best = -1; int bbw = 1, bbh = 1, bbn = 16;
+    for (int w = 1; w <= OW && w <= WG_KP; ++w)
+        for (int h = 1; h <= OH && w * h <= WG_KP; ++h)
+            for (int n = 1; w * h * n <= WG_KP; ++n) {
+                const int kp = w * h * n;
+                if (kp % 16) continue;
+                const double tiles = (double)((OW + w - 1) / w) * ((OH + h - 1) / h) * ((NB + n - 1) / n);
+                const double eff = ((double)OW * OH * NB) / (tiles * kp);
+                const double score = eff + 1e-3 * kp / WG_KP + 1e-6 * w;   // prefer full-depth stages, wide boxes
+                if (score > best) { best = score; bbw = w; bbh = h; bbn = n; }
+            }
+    *bw = bbw; *bh = bbh; *bn = bbn;
+}
+
+template <int BLOCK_N, int T, int STAGES>
+static int launch_wg(const WgradMaps& maps, const WgradParams& p, dim3 grid, cudaStream_t st) {
+    using L = WgradSmem<BLOCK_N, T, STAGES>;
+    static bool attr_set = false;
+    auto kern = conv_wgrad_tc_kernel<BLOCK_N, T, STAGES>;
+    if (!attr_set) {
+        URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    kern<<<grid, 192, L::TOTAL, st>>>(maps, p);
+    URIR_LAUNCH_OK(1);
+    return URIR_OK;
+}
+
+static int pick_n(int k) { return (k % 128 == 0) ? 128 : (k % 64 == 0) ? 64 : (k % 32 == 0) ? 32 : 0; }
+
+bool wgrad_tc_supported(const urir_conv_desc* d) {
+    return d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16 && d->C % 32 == 0 && (d->C <= 64 || d->C % 128 == 0) &&
+           pick_n(d->K) != 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 &&
+           (d->stride == 1 || d->stride == 2) && d->R * d->S <= 36;
+}
+
+int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    WgradMaps maps; WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = pick_n(d->K);
+    const int ntaps = d->R * d->S;
+    const int T = (ntaps % 3 == 0) ? 3 : 1;
+    choose_kbox(d->Q, d->P, d->N, &p.bw, &p.bh, &p.bn);
+    p.kp = p.bw * p.bh * p.bn;
+    p.tiles_w = cdiv(d->Q, p.bw); p.tiles_h = cdiv(d->P, p.bh); p.tiles_n = cdiv(d->N, p.bn);
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.C = d->C; p.K = d->K; p.ntaps = ntaps; p.dw = dw;
+    p.a_atom = (d->C % 64 == 0) ? 64 : 32; p.b_atom = (d->K % 64 == 0) ? 64 : 32;
+    const int m_valid = d->C < 128 ? d->C : 128;
+    p.a_atoms = m_valid / p.a_atom; p.b_atoms = BN / p.b_atom;
+    p.n_mtiles = cdiv(d->C, 128);
+    const int n_ntiles = d->K / BN, tap_groups = ntaps / T;
+    const int units = p.n_mtiles * n_ntiles * tap_groups;
+    int splits = (148 * 2 + units - 1) / units;
+    if (splits > p.total_tiles) splits = p.total_tiles;
+    if (splits < 1) splits = 1;
+    p.tiles_per_cta = cdiv(p.total_tiles, splits);
+    splits = cdiv(p.total_tiles, p.tiles_per_cta);
+
+    const int s = d->stride;
+    int nt = 0;
+    bool used[4] = {false, false, false, false};
+    for (int r = 0; r < d->R; ++r)
+        for (int q = 0; q < d->S; ++q) {
+            const int th = r - d->pad_top, tw = q - d->pad_left;
+            const int ph = posmod(th, s), pw = posmod(tw, s);
+            WgradTap& tp = p.taps[nt++];
+            tp.dh = (short)floordiv(th, s); tp.dw = (short)floordiv(tw, s);
+            tp.map = (short)(ph * s + pw); tp.wtap = (short)(r * d->S + q);
+            used[tp.map] = true;
+        }
+    const uint32_t abox[4] = {(uint32_t)p.a_atom, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    const char* xb = (const char*)x + (size_t)d->x_coff * 2;
+    int first_used = -1;
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw) {
+            const int mi = ph * s + pw;
+            if (!used[mi]) continue;
+            if (first_used < 0) first_used = mi;
+            const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)((d->W - pw + s - 1) / s), (uint64_t)((d->H - ph + s - 1) / s), (uint64_t)d->N};
+            const uint64_t strides[3] = {(uint64_t)s * d->x_ld * 2, (uint64_t)s * d->W * d->x_ld * 2, (uint64_t)d->H * d->W * d->x_ld * 2};
+            int rc = encode_map(&maps.a[mi], xb + ((size_t)ph * d->W + pw) * d->x_ld * 2, 4, dims, strides, abox, p.a_atom * 2);
+            if (rc) return rc;
+        }
+    for (int mi = 0; mi < 4; ++mi) if (mi >= s * s || !used[mi]) maps.a[mi] = maps.a[first_used];
+    {
+        const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->Q, (uint64_t)d->P, (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)d->y_ld * 2, (uint64_t)d->Q * d->y_ld * 2, (uint64_t)d->P * d->Q * d->y_ld * 2};
+        const uint32_t bbox[4] = {(uint32_t)p.b_atom, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+        int rc = encode_map(&maps.b, (const char*)dy + (size_t)d->y_coff * 2, 4, dims, strides, bbox, p.b_atom * 2);
+        if (rc) return rc;
+    }
+    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps * d->C * d->K, st));
+    dim3 grid(splits, p.n_mtiles * n_ntiles, tap_groups);
+#define URIR_WG(BNv, Tv, STv) if (BN == BNv && T == Tv) return launch_wg<BNv, Tv, STv>(maps, p, grid, st);
+    URIR_WG(128, 3, 3) URIR_WG(64, 3, 3) URIR_WG(32, 3, 3)
+    URIR_WG(128, 1, 4) URIR_WG(64, 1, 4) URIR_WG(32, 1, 4)
+#undef URIR_WG
+    return fail(URIR_ERR_UNSUP, "wgrad(tcgen05): no kernel for BLOCK_N=%d T=%d", BN, T);
+}
+
+}  // namespace urir

@@ -1,0 +1,437 @@
+// Bandwidth-bound kernels of the train step: BatchNorm(+ReLU) forward / backward, the fused
+// amp/phase loss (forward scalars + dL/dy in one pass), flat Adam/SGD, and small helpers.
+// All of them are HBM-bound (DESIGN.md roofline table): 128-bit accesses, one pass per tensor,
+// warp-shuffle + shared-memory reductions, a handful of atomics per block.
+#include "urir_common.cuh"
+
+namespace urir {
+
+// =========================================================================================
+// BatchNormalization (Keras: eps 1e-3, momentum .99, biased batch variance) -- u_net.py:367-369
+// =========================================================================================
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float momentum, float eps, int unbiased, float* __restrict__ scale_shift,
+                                   float* __restrict__ mean_rstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, var;
+    if (stats) {
+        const double m = (double)stats[c] / count;
+        double v = (double)stats[C + c] / count - m * m;
+        if (v < 0) v = 0;
+        mean = (float)m; var = (float)v;
+        if (moving_mean) {
+            const double mv = unbiased ? v * (count / (count > 1 ? count - 1 : 1)) : v;
+            moving_mean[c] = moving_mean[c] * momentum + mean * (1.f - momentum);
+            moving_var[c] = moving_var[c] * momentum + (float)mv * (1.f - momentum);
+        }
+    } else {
+        mean = moving_mean[c]; var = moving_var[c];
+    }
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    scale_shift[c] = g * rstd;
+    scale_shift[C + c] = b - mean * g * rstd;
+    if (mean_rstd) { mean_rstd[c] = mean; mean_rstd[C + c] = rstd; }
+}
+
+// y = relu(x*scale+shift), 8 channels (one 128-bit access) per thread iteration
+__global__ void __launch_bounds__(256)
+bn_relu_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
+                   const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ y, int y_ld,
+                   int y_coff, long long npix, int C, int relu) {
+    extern __shared__ float ss[];   // [2C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ss[i] = scale_shift[i];
+    __syncthreads();
+    const int G = C >> 3;
+    const long long total = npix * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / G;
+        const int c = (int)(i - pix * G) << 3;
+        const uint4 u = ld_nc_v4(x + pix * x_ld + x_coff + c);
+        const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+        uint32_t out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 v = unpack_bf16x2(in[j]);
+            v.x = fmaf(v.x, ss[c + 2 * j], ss[C + c + 2 * j]);
+            v.y = fmaf(v.y, ss[c + 2 * j + 1], ss[C + c + 2 * j + 1]);
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+            out[j] = pack_bf16x2(v.x, v.y);
+        }
+        *reinterpret_cast<uint4*>(y + pix * y_ld + y_coff + c) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+}
+
+// sums[c] = sum g, sums[C+c] = sum g*xhat, g = dy * (x*scale+shift > 0)
+// block = 256 threads; thread owns one 8-channel group and strides over pixels.
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff,
+                          const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
+                          const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
+                          float* __restrict__ sums, long long npix, int C) {
+    extern __shared__ float sm[];              // [4C] consts, then [256][17] reduction scratch
+    float* cs = sm;
+    float* red = sm + 4 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) { cs[i] = scale_shift[i]; cs[2 * C + i] = mean_rstd[i]; }
+    __syncthreads();
+    const int G = C >> 3;                      // channel groups
+    const int lanes = 256 / G;                 // pixel lanes per block (G <= 256)
+    const int g = threadIdx.x % G, lane = threadIdx.x / G;
+    const int c = g << 3;
+    float a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+    if (lane < lanes) {
+        for (long long pix = (long long)blockIdx.x * lanes + lane; pix < npix; pix += (long long)gridDim.x * lanes) {
+            const uint4 ud = ld_nc_v4(dy + pix * dy_ld + dy_coff + c);
+            const uint4 ux = ld_nc_v4(x + pix * x_ld + x_coff + c);
+            const uint32_t d4[4] = {ud.x, ud.y, ud.z, ud.w}, x4[4] = {ux.x, ux.y, ux.z, ux.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 dv = unpack_bf16x2(d4[j]), xv = unpack_bf16x2(x4[j]);
+                const int c0 = c + 2 * j, c1 = c0 + 1;
+                const float g0 = fmaf(xv.x, cs[c0], cs[C + c0]) > 0.f ? dv.x : 0.f;
+                const float g1 = fmaf(xv.y, cs[c1], cs[C + c1]) > 0.f ? dv.y : 0.f;
+                const float h0 = (xv.x - cs[2 * C + c0]) * cs[3 * C + c0];
+                const float h1 = (xv.y - cs[2 * C + c1]) * cs[3 * C + c1];
+                a1[2 * j] += g0; a1[2 * j + 1] += g1;
+                a2[2 * j] = fmaf(g0, h0, a2[2 * j]); a2[2 * j + 1] = fmaf(g1, h1, a2[2 * j + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 17 + j] = a1[j]; red[threadIdx.x * 17 + 8 + j] = a2[j]; }
+    __syncthreads();
+    // thread t < 2C : sums entry t ; reduce over pixel lanes
+    for (int t = threadIdx.x; t < 2 * C; t += blockDim.x) {
+        const int which = t / C, ch = t % C;
+        const int gg = ch >> 3, j = ch & 7;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(l * G + gg) * 17 + which * 8 + j];
+        atomicAdd(sums + t, s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff,
+                         const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
+                         const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
+                         const float* __restrict__ gamma, const float* __restrict__ sums,
+                         __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                         long long npix, int C) {
+    extern __shared__ float sm[];   // scale, shift, mean, rstd, a=gamma*rstd, mg, mgx : 7C ; then [256][9] scratch
+    const float inv_n = 1.f / (float)npix;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        sm[i] = scale_shift[i]; sm[C + i] = scale_shift[C + i];
+        sm[2 * C + i] = mean_rstd[i]; sm[3 * C + i] = mean_rstd[C + i];
+        sm[4 * C + i] = (gamma ? gamma[i] : 1.f) * mean_rstd[C + i];
+        sm[5 * C + i] = sums[i] * inv_n; sm[6 * C + i] = sums[C + i] * inv_n;
+        if (blockIdx.x == 0) { if (dgamma) dgamma[i] = sums[C + i]; if (dbeta) dbeta[i] = sums[i]; }
+    }
+    __syncthreads();
+    const int G = C >> 3;
+    const long long total = npix * G;
+    float bsum[8];                  // sum of dx over this thread's (fixed, since G | 256) channel group
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / G;
+        const int c = (int)(i - pix * G) << 3;
+        const uint4 ud = ld_nc_v4(dy + pix * dy_ld + dy_coff + c);
+        const uint4 ux = ld_nc_v4(x + pix * x_ld + x_coff + c);
+        const uint32_t d4[4] = {ud.x, ud.y, ud.z, ud.w}, x4[4] = {ux.x, ux.y, ux.z, ux.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 dv = unpack_bf16x2(d4[j]), xv = unpack_bf16x2(x4[j]);
+            float r[2];
+            const float dvv[2] = {dv.x, dv.y}, xvv[2] = {xv.x, xv.y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cc = c + 2 * j + e;
+                const float g = fmaf(xvv[e], sm[cc], sm[C + cc]) > 0.f ? dvv[e] : 0.f;
+                const float h = (xvv[e] - sm[2 * C + cc]) * sm[3 * C + cc];
+                r[e] = sm[4 * C + cc] * (g - sm[5 * C + cc] - h * sm[6 * C + cc]);
+            }
+            o[j] = pack_bf16x2(r[0], r[1]);
+            bsum[2 * j] += r[0]; bsum[2 * j + 1] += r[1];
+        }
+        *reinterpret_cast<uint4*>(dx + pix * dx_ld + dx_coff + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (dbias) {                    // gradient of the preceding conv's bias = sum of dx (analytically ~0)
+        float* red = sm + 7 * C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = bsum[j];
+        __syncthreads();
+        for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+            const int gg = ch >> 3, j = ch & 7;
+            float s = 0.f;
+            for (int l = 0; l < 256 / G; ++l) s += red[(l * G + gg) * 9 + j];
+            atomicAdd(dbias + ch, s);
+        }
+    }
+}
+
+static int grid_for(long long work_items, int threads) {
+    long long b = (work_items + threads - 1) / threads;
+    const long long cap = 148LL * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+static bool vec8_ok(int C, int ld, int coff) { return C % 8 == 0 && ld % 8 == 0 && coff % 8 == 0; }
+
+int bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* mm, float* mv,
+                float momentum, float eps, int unbiased, float* scale_shift, float* mean_rstd, int C, cudaStream_t st) {
+    URIR_CHECK_ARG(C > 0 && scale_shift, "bn_finalize: bad args");
+    URIR_CHECK_ARG(stats || (mm && mv), "bn_finalize: inference mode needs moving statistics");
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats, count, gamma, beta, mm, mv, momentum, eps, unbiased,
+                                                     scale_shift, mean_rstd, C);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+int bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* ss, void* y, int y_ld, int y_coff,
+                long long npix, int C, int relu, cudaStream_t st) {
+    URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, y_ld, y_coff), "bn_relu_fwd: C/ld/coff must be multiples of 8");
+    URIR_CHECK_ARG(C <= 2048, "bn_relu_fwd: C too large");
+    bn_relu_fwd_kernel<<<grid_for(npix * (C / 8), 256), 256, 2 * C * sizeof(float), st>>>(
+        (const __nv_bfloat16*)x, x_ld, x_coff, ss, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, relu);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+int bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
+                       const float* mr, float* sums, long long npix, int C, cudaStream_t st) {
+    URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, dy_ld, dy_coff), "bn_bwd_reduce: C/ld/coff must be multiples of 8");
+    URIR_CHECK_ARG(C <= 2048 && (C / 8) <= 256, "bn_bwd_reduce: C too large");
+    URIR_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st));
+    const int lanes = 256 / (C / 8);
+    long long blocks = (npix + lanes - 1) / lanes;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const size_t smem = (4 * C + 256 * 17) * sizeof(float);
+    bn_relu_bwd_reduce_kernel<<<(int)blocks, 256, smem, st>>>((const __nv_bfloat16*)dy, dy_ld, dy_coff,
+                                                              (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+int bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
+                      const float* mr, const float* gamma, const float* sums, void* dx, int dx_ld, int dx_coff,
+                      float* dgamma, float* dbeta, float* dbias, long long npix, int C, cudaStream_t st) {
+    URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, dy_ld, dy_coff) && vec8_ok(C, dx_ld, dx_coff),
+                   "bn_bwd_apply: C/ld/coff must be multiples of 8");
+    URIR_CHECK_ARG(C <= 1024, "bn_bwd_apply: C too large");
+    URIR_CHECK_ARG(!dbias || (256 % (C / 8) == 0), "bn_bwd_apply: dbias needs C/8 to divide 256");
+    if (dbias) URIR_CUDA_OK(cudaMemsetAsync(dbias, 0, C * sizeof(float), st));
+    bn_relu_bwd_apply_kernel<<<grid_for(npix * (C / 8), 256), 256, (7 * C + 256 * 9) * sizeof(float), st>>>(
+        (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, gamma, sums,
+        (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+// =========================================================================================
+// per-channel sums (bias gradients)
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const T* __restrict__ x, long long npix, int C, int ld, int coff, float* __restrict__ out) {
+    // thread owns channel (threadIdx.x % C) when C <= 256, strides over pixels
+    const int lanes = 256 / C > 0 ? 256 / C : 1;
+    __shared__ float red[256];
+    for (int cb = 0; cb < C; cb += 256) {
+        const int c = cb + threadIdx.x % (C < 256 ? C : 256);
+        const int lane = threadIdx.x / (C < 256 ? C : 256);
+        float s = 0.f;
+        if (c < C && lane < lanes)
+            for (long long pix = (long long)blockIdx.x * lanes + lane; pix < npix; pix += (long long)gridDim.x * lanes)
+                s += ld_as_f32(x + pix * ld + coff + c);
+        red[threadIdx.x] = s;
+        __syncthreads();
+        if (lane == 0 && c < C) {
+            const int stride = C < 256 ? C : 256;
+            for (int l = 1; l < lanes; ++l) s += red[l * stride + (threadIdx.x % stride)];
+            atomicAdd(out + c, s);
+        }
+        __syncthreads();
+    }
+}
+
+int channel_sum(const void* x, int dtype, long long npix, int C, int ld, int coff, float* out, cudaStream_t st) {
+    URIR_CHECK_ARG(C > 0 && npix > 0, "channel_sum: bad args");
+    URIR_CUDA_OK(cudaMemsetAsync(out, 0, C * sizeof(float), st));
+    const int lanes = 256 / C > 0 ? 256 / C : 1;
+    long long blocks = (npix + lanes - 1) / lanes;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (dtype == URIR_BF16) channel_sum_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, npix, C, ld, coff, out);
+    else channel_sum_kernel<float><<<(int)blocks, 256, 0, st>>>((const float*)x, npix, C, ld, coff, out);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+// =========================================================================================
+// amp/phase loss: forward scalars and dL/dy_pred (optionally through the sigmoid) in one pass
+// amp_phase_trainer.py:143-168 ; main_training.py:184-190, 203-235
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ yp, long long npair,
+                     long long npix, float w_amp, float w_ph, int sigmoid_bwd, float* __restrict__ losses,
+                     float4* __restrict__ grad) {
+    const float TWO_PI = 6.283185307179586f;
+    float sse = 0.f, pc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float4 t = __ldg(yt + i), p = __ldg(yp + i);     // (amp0, ph0, amp1, ph1)
+        const float da0 = p.x - t.x, da1 = p.z - t.z;
+        const float d0 = TWO_PI * (t.y - p.y), d1 = TWO_PI * (t.w - p.w);
+        float s0, c0, s1, c1;
+        sincosf(d0, &s0, &c0); sincosf(d1, &s1, &c1);
+        sse += da0 * da0 + da1 * da1;
+        pc += (1.f - c0) + (1.f - c1);
+        if (grad) {
+            float4 g;
+            g.x = 2.f * w_amp * da0; g.z = 2.f * w_amp * da1;
+            g.y = -TWO_PI * w_ph * s0; g.w = -TWO_PI * w_ph * s1;
+            if (sigmoid_bwd) { g.x *= p.x * (1.f - p.x); g.y *= p.y * (1.f - p.y); g.z *= p.z * (1.f - p.z); g.w *= p.w * (1.f - p.w); }
+            grad[i] = g;
+        }
+    }
+    __shared__ float r1[8], r2[8];
+    sse = warp_sum(sse); pc = warp_sum(pc);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = sse; r2[threadIdx.x >> 5] = pc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a += r1[i]; b += r2[i]; }
+        const float inv = 1.f / (float)npix;
+        atomicAdd(losses + 0, w_amp * a + w_ph * b);
+        atomicAdd(losses + 1, b * inv);
+        atomicAdd(losses + 2, a * inv);
+    }
+}
+
+int ampphase_loss(const float* yt, const float* yp, long long npix, float w_amp, float w_ph, int sigmoid_bwd,
+                  float* losses, float* grad, cudaStream_t st) {
+    URIR_CHECK_ARG(npix > 0 && npix % 2 == 0, "ampphase_loss: npix must be even");
+    URIR_CUDA_OK(cudaMemsetAsync(losses, 0, 4 * sizeof(float), st));
+    const long long npair = npix / 2;
+    ampphase_loss_kernel<<<grid_for(npair, 256), 256, 0, st>>>((const float4*)yt, (const float4*)yp, npair, npix,
+                                                               w_amp, w_ph, sigmoid_bwd, losses, (float4*)grad);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+// =========================================================================================
+// optimisers (Keras conventions: eps outside the bias-corrected sqrt)
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, const float* __restrict__ lr_dev, const int* __restrict__ step_dev, float b1, float b2,
+            float eps) {
+    const float t = (float)(*step_dev + 1);
+    const float lr_t = *lr_dev * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+#define URIR_ADAM1(f) mm.f = b1 * mm.f + (1.f - b1) * gg.f; vv.f = b2 * vv.f + (1.f - b2) * gg.f * gg.f; \
+                      pp.f -= lr_t * mm.f / (sqrtf(vv.f) + eps);
+        URIR_ADAM1(x) URIR_ADAM1(y) URIR_ADAM1(z) URIR_ADAM1(w)
+#undef URIR_ADAM1
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gg = g[i];
+        const float mm = b1 * m[i] + (1.f - b1) * gg, vv = b2 * v[i] + (1.f - b2) * gg * gg;
+        m[i] = mm; v[i] = vv;
+        p[i] -= lr_t * mm / (sqrtf(vv) + eps);
+    }
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, const float* __restrict__ lr_dev) {
+    const float lr = *lr_dev;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] -= lr * g[i];
+}
+
+__global__ void step_inc_kernel(int* s) { if (threadIdx.x == 0 && blockIdx.x == 0) *s += 1; }
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = fmaf(a, x[i], y[i]);
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ x, long long n, float scale, float* __restrict__ out) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s = fmaf(x[i], x[i], s);
+    __shared__ float r[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float a = 0.f; for (int i = 0; i < 8; ++i) a += r[i]; atomicAdd(out, a * scale); }
+}
+
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 ua = a[i], ub = b[i];
+        const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w}, bb[4] = {ub.x, ub.y, ub.z, ub.w};
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 x = unpack_bf16x2(aa[j]), y = unpack_bf16x2(bb[j]); r[j] = pack_bf16x2(x.x + y.x, x.y + y.y); }
+        o[i] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = f2bf(x[i]);
+}
+
+int adam(float* p, const float* g, float* m, float* v, long long n, const float* lr, const int* step, float b1,
+         float b2, float eps, cudaStream_t st) {
+    URIR_CHECK_ARG(n > 0 && ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0),
+                   "adam: buffers must be 16-byte aligned");
+    adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, st>>>(p, g, m, v, n, lr, step, b1, b2, eps);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+int sgd(float* p, const float* g, long long n, const float* lr, cudaStream_t st) {
+    sgd_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, n, lr);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+int step_increment(int* s, cudaStream_t st) { step_inc_kernel<<<1, 32, 0, st>>>(s); URIR_LAUNCH_OK(0); return URIR_OK; }
+int axpy(float* y, const float* x, float a, long long n, cudaStream_t st) {
+    axpy_kernel<<<grid_for(n, 256), 256, 0, st>>>(y, x, a, n);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+int sumsq(const float* x, long long n, float scale, float* out, int accumulate, cudaStream_t st) {
+    if (!accumulate) URIR_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
+    sumsq_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, n, scale, out);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+int add_bf16(const void* a, const void* b, void* o, long long n, cudaStream_t st) {
+    URIR_CHECK_ARG(n % 8 == 0, "add_bf16: n must be a multiple of 8");
+    add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)o, n / 8);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t st) {
+    cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, (__nv_bfloat16*)y, n);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+}  // namespace urir

@@ -1,0 +1,72 @@
+// Shared helpers for liburir (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/urir.h"
+
+namespace urir {
+
+// ---- error plumbing: thread-local message + monotonically increasing launch counter ------
+void set_error(const char* fmt, ...);
+int  fail(int code, const char* fmt, ...);
+void count_launch(int kind);   // kind: 0 = SIMT/bandwidth kernel, 1 = tcgen05 kernel
+
+#define URIR_CHECK_ARG(cond, ...) do { if (!(cond)) return ::urir::fail(URIR_ERR_ARG, __VA_ARGS__); } while (0)
+
+#define URIR_CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
+    return ::urir::fail(URIR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } while (0)
+
+#define URIR_LAUNCH_OK(kind) do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) \
+    return ::urir::fail(URIR_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, \
+                        cudaGetErrorString(_e)); ::urir::count_launch(kind); } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    float2 r;
+    r.x = __uint_as_float(u << 16);
+    r.y = __uint_as_float(u & 0xffff0000u);
+    return r;
+}
+
+template <typename T> __device__ __forceinline__ float ld_as_f32(const T* p);
+template <> __device__ __forceinline__ float ld_as_f32<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __uint_as_float(((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+template <typename T> __device__ __forceinline__ void st_from_f32(T* p, float v);
+template <> __device__ __forceinline__ void st_from_f32<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_from_f32<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = f2bf(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 128-bit streaming loads / stores (guideline 13: bypass L1 for single-use data)
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace urir

@@ -1,0 +1,436 @@
+"""Device-side execution of the U-Net hot path through liburir's C-ABI.
+
+This is the B200 replacement for what TensorFlow does under `model.model([spec, emb],
+training=...)`, `tape.gradient` and `optimizer.apply_gradients` in the reference
+(amp_phase_trainer.py:130-141, main_training.py:253-268). Python only sequences the calls and
+owns the buffers (torch tensors as device memory); every arithmetic op is a liburir kernel.
+
+Data layout in HBM (all NHWC):
+  * activations bf16. Each encoder output e_i is written by its BN+ReLU pass straight into the
+    left half of the decoder's concat buffer cat_i = [e_i | up_i] and the Conv2DTranspose writes
+    the right half, so `concatenate` (u_net.py:308) never exists as a copy.
+  * raw (pre-BN) conv outputs bf16 are kept for the backward pass; BN batch statistics come out
+    of the conv epilogue (fp32 sum / sum-of-squares per channel).
+  * parameters: ONE flat fp32 buffer in Keras variable order (plan.py), with flat gradient and
+    Adam-moment twins, so the optimiser is a single kernel and the DP all-reduce works on
+    contiguous buckets. bf16 operand copies of every conv kernel ([tap][C][K] and [tap][K][C])
+    and of the Dense kernel are refreshed after each optimiser step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from . import _lib as L
+from . import plan as PL
+
+
+class View:
+    """A C-channel slice, starting at channel `coff`, of an NHWC buffer with `ld` channels."""
+    __slots__ = ("buf", "coff", "C")
+
+    def __init__(self, buf, coff=0, C=None):
+        self.buf, self.coff = buf, coff
+        self.C = buf.shape[3] - coff if C is None else C
+
+    N = property(lambda s: s.buf.shape[0])
+    H = property(lambda s: s.buf.shape[1])
+    W = property(lambda s: s.buf.shape[2])
+    ld = property(lambda s: s.buf.shape[3])
+    npix = property(lambda s: s.buf.shape[0] * s.buf.shape[1] * s.buf.shape[2])
+
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def tensor(self):
+        return self.buf[..., self.coff:self.coff + self.C]
+
+
+def _align(n, a=4):
+    return (n + a - 1) // a * a
+
+
+class UNetEngine:
+    def __init__(self, input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0,
+                 number_filters_0=32, kernels=6, BatchNorm=True, device="cuda", seed=500,
+                 impl=L.IMPL_AUTO, bn_unbiased_moving_var=False):
+        if mode != 0:
+            raise NotImplementedError(
+                "the CUDA engine wires mode=0 (convolutional_block_1), the only mode any reference call "
+                "site uses (u_net.py:392, main_training.py:157, rir_generation.py:119)")
+        if not BatchNorm:
+            raise NotImplementedError("BatchNorm=False is not wired in the CUDA engine")
+        H, W, Cin = input_shape
+        if H % 16 or W % 16:
+            raise ValueError("input H and W must be multiples of 16 (four stride-2 stages)")
+        L.load()
+        self.input_shape, self.inf_vector_shape = tuple(input_shape), tuple(inf_vector_shape)
+        self.mode, self.F0, self.kernels, self.BatchNorm = mode, number_filters_0, kernels, BatchNorm
+        self.device = torch.device(device)
+        self.impl = impl
+        self.bn_unbiased = int(bn_unbiased_moving_var)
+        self.plan = PL.layer_plan(input_shape, inf_vector_shape, mode, number_filters_0, kernels, BatchNorm)
+        self.T = inf_vector_shape[0] * inf_vector_shape[1]
+        self.H5, self.W5 = H // 16, W // 16
+        self.dense_n = self.H5 * self.W5 * PL.VEC_CH
+        self._build_params(seed)
+        self._bufs = {}
+        self.dropout_seed = seed
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.losses_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ parameters
+    def _build_params(self, seed):
+        dev = self.device
+        off, soff = 0, 0
+        self.offsets, self.state_offsets, self.shapes, self.kinds = OrderedDict(), OrderedDict(), {}, {}
+        for name, shape, kind in self.plan:
+            n = 1
+            for s in shape:
+                n *= s
+            self.shapes[name], self.kinds[name] = tuple(shape), kind
+            if kind in PL.TRAINABLE_KINDS:
+                self.offsets[name] = (off, n); off = _align(off + n)
+            else:
+                self.state_offsets[name] = (soff, n); soff = _align(soff + n)
+        self.n_flat = off
+        self.P = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.G = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.M = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.V = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.S = torch.zeros(max(soff, 4), dtype=torch.float32, device=dev)
+        self.param, self.grad, self.state = OrderedDict(), OrderedDict(), OrderedDict()
+        for name, (o, n) in self.offsets.items():
+            self.param[name] = self.P[o:o + n].view(self.shapes[name])
+            self.grad[name] = self.G[o:o + n].view(self.shapes[name])
+        for name, (o, n) in self.state_offsets.items():
+            self.state[name] = self.S[o:o + n].view(self.shapes[name])
+        # bf16 operand copies
+        self.wops = {}
+        for name, shape, kind in self.plan:
+            if kind in ("conv_w", "convT_w"):
+                kh, kw, a, b = shape
+                self.wops[name] = (torch.empty(kh * kw, a, b, dtype=torch.bfloat16, device=dev),
+                                   torch.empty(kh * kw, b, a, dtype=torch.bfloat16, device=dev))
+        self.dense_w16 = torch.empty(self.shapes["vec.dense.w"], dtype=torch.bfloat16, device=dev)
+        # per-BN scratch: stats (zeroed each forward), scale/shift, mean/rstd, backward sums
+        bn_names = [n[:-len(".gamma")] for n in self.offsets if n.endswith(".gamma")]
+        tot = sum(2 * self.shapes[b + ".gamma"][0] for b in bn_names)
+        self.stats_arena = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.ss_arena = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.mr_arena = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.sums_arena = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.bn_slot = {}
+        o = 0
+        for b in bn_names:
+            c = self.shapes[b + ".gamma"][0]
+            self.bn_slot[b] = (o, 2 * c); o += 2 * c
+        # bias-gradient statistics emitted by dgrad epilogues (zeroed each backward)
+        self.bstat_arena = torch.zeros(2 * 4 * (self.F0 * 16) * 12, dtype=torch.float32, device=dev)
+        self.load_state_dict(PL.keras_init(self.plan, seed))
+
+    def trainable_names(self):
+        return list(self.offsets)
+
+    def state_dict(self):
+        d = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.param.items())
+        d.update((k, v.detach().cpu().clone()) for k, v in self.state.items())
+        return d
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            dst = self.param.get(k, None)
+            if dst is None:
+                dst = self.state[k]
+            if tuple(v.shape) != tuple(dst.shape):
+                raise ValueError(f"{k}: shape {tuple(v.shape)} != {tuple(dst.shape)}")
+            dst.copy_(torch.as_tensor(v, dtype=torch.float32))
+        self.refresh_operands()
+
+    def refresh_operands(self):
+        """fp32 masters -> bf16 operand layouts (after load / after every optimiser step)."""
+        for name, (w_ck, w_kc) in self.wops.items():
+            taps, a, b = w_ck.shape
+            L.call("weight_prep", self.param[name].data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), taps, a, b)
+        L.call("cast_f32_to_bf16", self.param["vec.dense.w"].data_ptr(), self.dense_w16.data_ptr(),
+               self.dense_w16.numel())
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, B):
+        if B in self._bufs:
+            return self._bufs[B]
+        dev, bf = self.device, torch.bfloat16
+        H, W, Cin = self.input_shape
+        b = {}
+
+        def act(h, w, c, dtype=bf):
+            return torch.zeros(B, h, w, c, dtype=dtype, device=dev)
+
+        b["x_in"] = act(H, W, Cin, torch.float32)
+        b["emb"] = torch.zeros(B, self.T, dtype=torch.int32, device=dev)
+        b["out"] = act(H, W, 2, torch.float32)
+        b["g_out"] = act(H, W, 2, torch.float32)
+        b["y_true"] = act(H, W, 2, torch.float32)
+        for i in range(1, 6):
+            n = self.F0 * 2 ** (i - 1)
+            h, w = (H, W) if i == 1 else (H >> (i - 1), W >> (i - 1))
+            for nm in ("t", "r"):
+                b[f"{nm}{i}"] = act(h, w, n); b[f"g_{nm}{i}"] = act(h, w, n)
+            if i < 5:
+                b[f"cat{i}"] = act(h, w, 2 * n); b[f"g_cat{i}"] = act(h, w, 2 * n)
+                for nm in ("rf", "f", "rb", "d"):
+                    b[f"{nm}{i}"] = act(h, w, n); b[f"g_{nm}{i}"] = act(h, w, n)
+            else:
+                b["z"] = act(h, w, n); b["g_z"] = act(h, w, n)
+        b["embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=bf, device=dev)
+        b["g_embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=torch.float32, device=dev)
+        b["v16"] = act(self.H5, self.W5, PL.VEC_CH); b["g_v16"] = act(self.H5, self.W5, PL.VEC_CH)
+        b["dense_ws"] = torch.zeros(B, self.dense_n, dtype=torch.float32, device=dev)
+        b["mask"] = torch.ones(B, self.dense_n, dtype=torch.float32, device=dev)
+        self._bufs[B] = b
+        return b
+
+    # ------------------------------------------------------------------ op helpers
+    def _desc(self, x: View, y: View, k, stride, act=L.ACT_NONE, accumulate=0):
+        P, pt = L.same_pad(x.H, k, stride)
+        Q, pl = L.same_pad(x.W, k, stride)
+        assert (P, Q) == (y.H, y.W), ((x.H, x.W), (y.H, y.W), k, stride)
+        return L.ConvDesc(x.N, x.H, x.W, x.C, y.C, k, k, stride, pt, pl, P, Q, x.ld, x.coff, y.ld, y.coff,
+                          L.dtype_code(x.buf), L.dtype_code(y.buf), self.impl, act, accumulate)
+
+    def _w(self, name):
+        w_ck, w_kc = self.wops[name + ".w"]
+        return w_ck.data_ptr(), w_kc.data_ptr()
+
+    def _conv_fprop(self, name, x, y, k, stride, stats=None, act=L.ACT_NONE, accumulate=0, bias=True):
+        d = self._desc(x, y, k, stride, act, accumulate)
+        w_ck, w_kc = self._w(name)
+        L.call("conv2d_fprop", C.byref(d), x.ptr(), w_ck, w_kc,
+               self.param[name + ".b"].data_ptr() if bias else None, y.ptr(),
+               None if stats is None else stats.data_ptr())
+
+    def _conv_dgrad(self, name, dy, dx, k, stride, stats=None, accumulate=0, bias=False):
+        """dx (the conv's input side) from dy (its output side); desc describes the forward conv."""
+        d = self._desc(dx, dy, k, stride, L.ACT_NONE, accumulate)
+        w_ck, w_kc = self._w(name)
+        L.call("conv2d_dgrad", C.byref(d), dy.ptr(), w_ck, w_kc,
+               self.param[name + ".b"].data_ptr() if bias else None, dx.ptr(),
+               None if stats is None else stats.data_ptr())
+
+    def _conv_wgrad(self, name, x, dy, k, stride):
+        d = self._desc(x, dy, k, stride)
+        L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
+
+    def _slot(self, arena, bn):
+        o, n = self.bn_slot[bn]
+        return arena[o:o + n]
+
+    def _cbr_fwd(self, cname, bname, x, raw, out, k, training):
+        """Conv2D(k, SAME) -> BatchNormalization -> ReLU  (convolutional_block_1, u_net.py:363-371)."""
+        stats = self._slot(self.stats_arena, bname) if training else None
+        self._conv_fprop(cname, x, raw, k, 1, stats=stats)
+        c = raw.C
+        ss, mr = self._slot(self.ss_arena, bname), self._slot(self.mr_arena, bname)
+        L.call("bn_finalize", None if stats is None else stats.data_ptr(), float(raw.npix),
+               self.param[bname + ".gamma"].data_ptr(), self.param[bname + ".beta"].data_ptr(),
+               self.state[bname + ".moving_mean"].data_ptr(), self.state[bname + ".moving_var"].data_ptr(),
+               PL.BN_MOMENTUM, PL.BN_EPS, self.bn_unbiased, ss.data_ptr(), mr.data_ptr(), c)
+        L.call("bn_relu_fwd", raw.ptr(), raw.ld, raw.coff, ss.data_ptr(), out.ptr(), out.ld, out.coff,
+               raw.npix, c, 1)
+
+    def _cbr_bwd(self, cname, bname, x, raw, g_out, g_raw, k, g_x=None, g_x_stats=None, accumulate=0):
+        ss, mr = self._slot(self.ss_arena, bname), self._slot(self.mr_arena, bname)
+        sums = self._slot(self.sums_arena, bname)
+        c = raw.C
+        L.call("bn_relu_bwd_reduce", g_out.ptr(), g_out.ld, g_out.coff, raw.ptr(), raw.ld, raw.coff,
+               ss.data_ptr(), mr.data_ptr(), sums.data_ptr(), raw.npix, c)
+        L.call("bn_relu_bwd_apply", g_out.ptr(), g_out.ld, g_out.coff, raw.ptr(), raw.ld, raw.coff,
+               ss.data_ptr(), mr.data_ptr(), self.param[bname + ".gamma"].data_ptr(), sums.data_ptr(),
+               g_raw.ptr(), g_raw.ld, g_raw.coff, self.grad[bname + ".gamma"].data_ptr(),
+               self.grad[bname + ".beta"].data_ptr(), self.grad[cname + ".b"].data_ptr(), raw.npix, c)
+        self._conv_wgrad(cname, x, g_raw, k, 1)
+        if g_x is not None:
+            self._conv_dgrad(cname, g_raw, g_x, k, 1, stats=g_x_stats, accumulate=accumulate)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, spec_in, emb, training=False, dropout_mask=None, dropout=True):
+        """model([spec_in, emb], training) -> fp32 (B, H, W, 2) in (0, 1) (a static buffer).
+
+        dropout_mask: optional (B, dim) fp32 tensor of {0, 1/(1-rate)} to inject (parity tests);
+        otherwise a fresh counter-based mask is drawn when training and dropout is True.
+        """
+        B = spec_in.shape[0]
+        b = self._buffers(B)
+        k = self.kernels
+        b["x_in"].copy_(spec_in.reshape(b["x_in"].shape))
+        b["emb"].copy_(emb.reshape(B, self.T))
+        if training:
+            self.stats_arena.zero_()
+        # ---- encoder (encoding_block, u_net.py:265-289)
+        x = View(b["x_in"])
+        for i in range(1, 6):
+            n = self.F0 * 2 ** (i - 1)
+            t, r = View(b[f"t{i}"]), View(b[f"r{i}"])
+            e = View(b[f"cat{i}"], 0, n) if i < 5 else View(b["z"])
+            self._conv_fprop(f"enc{i}.down", x, t, k, 1 if i == 1 else 2)
+            self._cbr_fwd(f"enc{i}.blk.c1", f"enc{i}.blk.bn1", t, r, e, 3, training)
+            x = e
+        # ---- vector block + Add (u_net.py:253-263, 229)
+        L.call("embedding_fwd", b["emb"].data_ptr(), self.param["vec.emb"].data_ptr(), b["embflat"].data_ptr(),
+               B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+        mask = None
+        if training:
+            if dropout_mask is not None:
+                b["mask"].copy_(dropout_mask); mask = b["mask"]
+            elif dropout:
+                L.call("dropout_mask", b["mask"].data_ptr(), b["mask"].numel(), PL.DROPOUT_RATE,
+                       self.dropout_seed, self.step_dev.data_ptr())
+                mask = b["mask"]
+        self._fwd_mask = mask
+        L.call("dense_fwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.param["vec.dense.b"].data_ptr(),
+               L.ptr(mask), b["v16"].data_ptr(), b["dense_ws"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
+        z = View(b["z"])
+        self._conv_fprop("vec.proj", View(b["v16"]), z, 1, 1, accumulate=1)
+        # ---- decoder (decoding_block, u_net.py:291-321)
+        x = z
+        for j in (2, 3, 4, 5):
+            i = 6 - j
+            n = self.F0 * 2 ** (i - 1)
+            cat = View(b[f"cat{i}"])
+            up = View(b[f"cat{i}"], n, n)
+            self._conv_dgrad(f"dec{j}.up", x, up, k, 2, bias=True)     # Conv2DTranspose forward
+            self._cbr_fwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"f{i}"]), k, training)
+            self._cbr_fwd(f"dec{j}.blk.c1", f"dec{j}.blk.bn1", View(b[f"f{i}"]), View(b[f"rb{i}"]), View(b[f"d{i}"]), 3,
+                          training)
+            x = View(b[f"d{i}"])
+        # ---- head: Conv2D(2, 6x6, same) + sigmoid (u_net.py:247-249)
+        self._conv_fprop("head", x, View(b["out"]), 6, 1, act=L.ACT_SIGMOID)
+        self._last_B = B
+        return b["out"]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, g_head):
+        """g_head: fp32 (B,H,W,2) gradient w.r.t. the head's PRE-sigmoid output. Fills self.grad."""
+        B = self._last_B
+        b = self._buffers(B)
+        k = self.kernels
+        if g_head.data_ptr() != b["g_out"].data_ptr():
+            b["g_out"].copy_(g_head)
+        self.bstat_arena.zero_()
+        bs_off = [0]
+
+        def bstat(c):
+            o = bs_off[0]; bs_off[0] += 2 * c
+            return self.bstat_arena[o:o + 2 * c]
+
+        g_out = View(b["g_out"])
+        d1 = View(b["d1"])
+        # head
+        self._conv_wgrad("head", d1, g_out, 6, 1)
+        L.call("channel_sum", g_out.ptr(), L.F32, g_out.npix, 2, 2, 0, self.grad["head.b"].data_ptr())
+        self._conv_dgrad("head", g_out, View(b["g_d1"]), 6, 1)
+        # decoder, top (level 1) down to level 4
+        for j in (5, 4, 3, 2):
+            i = 6 - j
+            n = self.F0 * 2 ** (i - 1)
+            cat, g_cat = View(b[f"cat{i}"]), View(b[f"g_cat{i}"])
+            self._cbr_bwd(f"dec{j}.blk.c1", f"dec{j}.blk.bn1", View(b[f"f{i}"]), View(b[f"rb{i}"]), View(b[f"g_d{i}"]),
+                          View(b[f"g_rb{i}"]), 3, g_x=View(b[f"g_f{i}"]))
+            st = bstat(2 * n)
+            self._cbr_bwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"g_f{i}"]),
+                          View(b[f"g_rf{i}"]), k, g_x=g_cat, g_x_stats=st)
+            # Conv2DTranspose: bias grad = channel sums of its output gradient (right half of g_cat)
+            self.grad[f"dec{j}.up.b"].copy_(st[n:2 * n])
+            g_up = View(b[f"g_cat{i}"], n, n)
+            x_in = View(b[f"d{i + 1}"]) if j > 2 else View(b["z"])
+            g_x_in = View(b[f"g_d{i + 1}"]) if j > 2 else View(b["g_z"])
+            self._conv_wgrad(f"dec{j}.up", g_up, x_in, k, 2)
+            st2 = bstat(x_in.C) if j == 2 else None
+            self._conv_fprop(f"dec{j}.up", g_up, g_x_in, k, 2, stats=st2, bias=False)   # ConvT dgrad
+            if j == 2:
+                self.grad["vec.proj.b"].copy_(st2[:x_in.C])
+        # bottleneck: z = e5 + proj(v16)
+        g_z = View(b["g_z"])
+        self._conv_wgrad("vec.proj", View(b["v16"]), g_z, 1, 1)
+        self._conv_dgrad("vec.proj", g_z, View(b["g_v16"]), 1, 1)
+        L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), b["g_v16"].data_ptr(),
+               L.ptr(self._fwd_mask), self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
+               b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
+        L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), self.grad["vec.emb"].data_ptr(),
+               B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+        # encoder, level 5 up to level 1
+        g_e = g_z
+        for i in (5, 4, 3, 2, 1):
+            n = self.F0 * 2 ** (i - 1)
+            t, r = View(b[f"t{i}"]), View(b[f"r{i}"])
+            st = bstat(n)
+            self._cbr_bwd(f"enc{i}.blk.c1", f"enc{i}.blk.bn1", t, r, g_e, View(b[f"g_r{i}"]), 3,
+                          g_x=View(b[f"g_t{i}"]), g_x_stats=st)
+            self.grad[f"enc{i}.down.b"].copy_(st[:n])
+            g_t = View(b[f"g_t{i}"])
+            if i > 1:
+                e_prev = View(b[f"cat{i - 1}"], 0, n // 2)
+                g_e_prev = View(b[f"g_cat{i - 1}"], 0, n // 2)
+                self._conv_wgrad(f"enc{i}.down", e_prev, g_t, k, 2)
+                self._conv_dgrad(f"enc{i}.down", g_t, g_e_prev, k, 2, accumulate=1)
+                g_e = g_e_prev
+            else:
+                self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
+
+    # ------------------------------------------------------------------ loss + optimiser
+    def loss_and_grad(self, y_true, w_amp, w_ph, need_grad=True):
+        """Fused amp/phase loss on the last forward output; returns the device tensor
+        [loss, mean(1-cos), mean sq err, 0] and leaves dL/d(pre-sigmoid) in the g_out buffer."""
+        b = self._buffers(self._last_B)
+        b["y_true"].copy_(y_true.reshape(b["y_true"].shape))
+        npix = b["out"].numel() // 2
+        L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), npix, float(w_amp), float(w_ph), 1,
+               self.losses_dev.data_ptr(), b["g_out"].data_ptr() if need_grad else None)
+        return self.losses_dev
+
+    def l2_loss_and_grad(self, scale):
+        """DP loss regulariser (main_training.py:232-233): reg = scale * 0.001 * sum ||W||^2 over the
+        strided convs and ConvTs; its gradient 2*scale*0.001*W is added to the flat gradient."""
+        first = True
+        for name in self.offsets:
+            if PL.l2_regularised(name):
+                p, g = self.param[name], self.grad[name]
+                L.call("sumsq", p.data_ptr(), p.numel(), scale * PL.L2_COEF, self.reg_dev.data_ptr(), 0 if first else 1)
+                L.call("axpy", g.data_ptr(), p.data_ptr(), 2.0 * scale * PL.L2_COEF, p.numel())
+                first = False
+        return self.reg_dev
+
+    def adam_step(self, beta1=0.9, beta2=0.999, eps=1e-7):
+        L.call("adam", self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.n_flat,
+               self.lr_dev.data_ptr(), self.step_dev.data_ptr(), beta1, beta2, eps)
+        L.call("step_increment", self.step_dev.data_ptr())
+        self.refresh_operands()
+
+    def sgd_step(self):
+        L.call("sgd", self.P.data_ptr(), self.G.data_ptr(), self.n_flat, self.lr_dev.data_ptr())
+        L.call("step_increment", self.step_dev.data_ptr())
+        self.refresh_operands()
+
+    def set_lr(self, lr):
+        self.lr_dev.fill_(float(lr))
+
+    # ------------------------------------------------------------------ debugging / parity
+    def debug_tensors(self):
+        """Intermediate tensors of the last forward, keyed like the oracle's taps (fp32, NCHW)."""
+        b = self._buffers(self._last_B)
+        out = {}
+        for i in range(1, 6):
+            out[f"enc{i}.down"] = b[f"t{i}"]
+            out[f"enc{i}.blk.c1"] = b[f"r{i}"]
+        for j in (2, 3, 4, 5):
+            i = 6 - j
+            n = self.F0 * 2 ** (i - 1)
+            out[f"dec{j}.up"] = b[f"cat{i}"][..., n:]
+            out[f"dec{j}.fuse"] = b[f"rf{i}"]
+            out[f"dec{j}.blk.c1"] = b[f"rb{i}"]
+        out["bottleneck"] = b["z"]
+        return {k: v.float().permute(0, 3, 1, 2).contiguous() for k, v in out.items()}
