@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the unet-rir hot path on B200: U-Net amp/phase train step, samples/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
+
+Workload (BASELINE.json configs[1] at N=1, configs[2] at N>1): canonical
+UNet(input_shape=(144,160,2), inf_vector_shape=(2,16), mode=0, number_filters_0=32, kernels=3), synthetic
+spectrograms of the shape dataset.py produces (U(0,1), TensorPadder region zeroed), random embedding ids,
+Keras-default random-init weights, B samples per GPU (default 64 = the reference authors' global batch,
+4 replicas x 16). A "step" is forward + amp/phase loss + backward + Adam (+ gradient all-reduce at N>1)
+over one batch. The per-step working set (activations ~3 GB at B=64) is far larger than the 126 MB L2, so
+no explicit L2 flush is needed between timed iterations.
+
+One JSON line on stdout (rank 0): value = whole-job samples/s with inputs resident in HBM; e2e = the same
+through the public Trainer.step / DistributedTrainer.train_step call with pinned HOST inputs, H2D and the
+loss read-back inside the timed region; roofline = achieved algorithmic TFLOP/s of the dominant kernel
+family from CUDA-event timing of every launch of one step; cpu_baseline = the CPU oracle's train step on
+the host cores. --impl reference times that CPU path (the reference's own TensorFlow code cannot run here:
+DESIGN.md) on the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+H, W = 144, 160
+METRIC = "unet_train_samples_per_sec"
+UNIT = "samples/s"
+FLOP_PER_SAMPLE_TRAIN = 27.2e9       # 3x forward (9.076 GF) minus the stem's unused dgrad
+
+
+def synthetic_batch(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, H, W, 2, generator=g)
+    y = torch.rand(B, H, W, 2, generator=g)
+    for t in (x, y):
+        t[:, 129:] = 0
+        t[:, :, 151:] = 0
+    emb = torch.randint(0, 2000, (B, 2, 16), generator=g, dtype=torch.int32)
+    return x, y, emb
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf=d.get("bf16_tflops", 1590.0),
+                    tf_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_train_step_rate(batch, steps, warmup, threads=None):
+    """The oracle's Trainer.step (fwd + loss + bwd + Keras Adam) on the host cores: samples/s."""
+    from oracle import unet_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    om = O.UNetOracle(kernels=3)
+    params = O.init_params(om.plan, seed=500)
+    st = O.new_opt_state(params, om.plan)
+    x, y, emb = synthetic_batch(batch, 500)
+    mask = (torch.rand(batch, 1440) > 0.3).float() / 0.7
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(om, params, st, x, y, emb, 1e-5, dropout_mask=mask, apply=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch / float(np.mean(times)), float(np.mean(times)), threads
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (restated by the oracle; TensorFlow is not installable
+    here) on the box's host cores, same metric / unit / config. Rank 0 only."""
+    if rank != 0:
+        return
+    batch = 8
+    budget_s = 150.0
+    rate, dt, threads = cpu_train_step_rate(batch, 1, 1)                 # probe
+    per_step = dt
+    total = args.steps + args.warmup
+    while batch > 1 and per_step * total > budget_s:
+        batch //= 2
+        per_step /= 2
+    rate, dt, threads = cpu_train_step_rate(batch, args.steps, args.warmup)
+    sample = f"oracle Trainer.step on batch {batch} (of the {args.batch}-sample workload), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "per_gpu_batch": args.batch, "l2": "working set >> L2"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return ("u_net.py amp/phase training step (UNet 144x160x2, F0=32, kernels=3, mode=0), "
+            f"bf16, {args.batch} samples/GPU, synthetic spectrograms, random-init weights")
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def per_kernel_profile(step_fn):
+    """One eager step with a CUDA-event pair around every liburir launch -> per-family totals."""
+    from unet_rir_b200 import _lib as L
+    L.profile_begin()
+    step_fn()
+    rec = L.profile_end()
+    fam = {}
+    for name, info, ms in rec:
+        if name.startswith("conv2d"):
+            key = name + (".tcgen05" if info.get("tc") else ".simt")
+        else:
+            key = name
+        f = fam.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0})
+        f["ms"] += ms; f["launches"] += 1; f["flops"] += info.get("flops", 0.0)
+    return rec, fam
+
+
+def run_gpu(args, rank, world, local):
+    import torch.distributed as dist
+
+    from unet_rir_b200 import _lib as L
+    from unet_rir_b200.amp_phase_trainer import EarlyStopping, ModelCheckpoint, Trainer
+    from unet_rir_b200.dl_models.u_net import UNet
+    from unet_rir_b200.main_training import DistributedTrainer
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B, K, Wu = args.batch, args.steps, max(args.warmup, 3)
+    unet = UNet(input_shape=(H, W, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+    eng = unet.model.engine
+    if world == 1:
+        tr = Trainer(0.9, 1, "adam", [ModelCheckpoint("/tmp/urir_bench", False, 0), EarlyStopping(5)], [False, 0],
+                     1e-5, "bench")
+        step_host = lambda x, y, e: tr.step(x, y, e, unet)[0]
+        body = lambda: tr._device_step(eng, B)
+    else:
+        dt = DistributedTrainer(unet, per_replica_batch=B, alpha=0.9, lr=5e-7, loss="dp", world=world)
+        step_host = lambda x, y, e: dt.train_step(x, e, y)
+        body = None
+
+    # pinned host batches (distinct per step so no step reuses cached inputs)
+    n_host = 4
+    host = []
+    for i in range(n_host):
+        x, y, e = synthetic_batch(B, 1000 * rank + i)
+        host.append((x.pin_memory(), y.pin_memory(), e.pin_memory()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up through the public call (also captures the CUDA graphs on the 2nd call)
+    for i in range(Wu):
+        step_host(*host[i % n_host])
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs already staged in HBM, replay the captured step
+    x, y, e = host[0]
+    eng.stage(x.to(dev), e.to(dev), y.to(dev))
+    torch.cuda.synchronize()
+    if world == 1:
+        graph = [g for g in tr._graphs.values() if not isinstance(g, str)][0]
+        resident_step = graph.replay
+    else:
+        resident_step = lambda: dt._run(B)
+    for _ in range(2):
+        resident_step()
+    clocks = ClockSampler(local)
+    n0 = L.launch_count(0)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        resident_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / K
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> Trainer.step -> loss read back, every step
+    barrier()
+    ev0.record()
+    last = None
+    for i in range(K):
+        last = step_host(*host[i % n_host])
+        _ = float(last)                       # device->host read of the step's loss
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / K
+    h2d = 2 * B * H * W * 2 * 4 + B * 32 * 4
+    e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    if rank != 0:
+        return
+    # ---- launches per step and per-kernel roofline (rank 0, one eager step with events around each launch)
+    pk = peaks()
+    if world == 1:
+        l0 = L.launch_count(0)
+        rec, fam = per_kernel_profile(body)
+        launches_per_step = L.launch_count(0) - l0
+    else:
+        l0 = L.launch_count(0)
+        save = dt._graphs; dt._graphs = None; w_save = dt.world; dt.world = 1
+        rec, fam = per_kernel_profile(lambda: dt._run(B))
+        dt._graphs, dt.world = save, w_save
+        launches_per_step = L.launch_count(0) - l0
+    tot_ms = sum(f["ms"] for f in fam.values())
+    dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    dname, d = dom
+    tens = [f for k, f in fam.items() if k.endswith(".tcgen05")]
+    tens_ms, tens_fl = sum(f["ms"] for f in tens), sum(f["flops"] for f in tens)
+    if d["flops"] > 0:
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                "share_of_step": d["ms"] / tot_ms, "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                "all_tcgen05_tflops": (tens_fl / (tens_ms * 1e-3) / 1e12) if tens_ms else None,
+                "all_tcgen05_share": tens_ms / tot_ms}
+    else:
+        roof = {"bound": "hbm", "kernel": dname, "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
+                "traffic": None, "share_of_step": d["ms"] / tot_ms}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"kernel_table_n{world}_b{B}.json"), "w") as f:
+        json.dump({"families": fam, "launches": [(n, i, m) for n, i, m in rec], "eager_step_ms": tot_ms}, f)
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rate, dt_cpu, threads = cpu_train_step_rate(8, 2, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "oracle Trainer.step (fwd+loss+bwd+Adam, fp32) on batch 8, 2 timed steps after 1 warm-up"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": "working set (~3 GB/step) >> 126 MB L2, no flush needed",
+                   "cuda_graph": True},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
+        "launches_per_step": int(launches_per_step),
+        "tflops_algorithmic": value * FLOP_PER_SAMPLE_TRAIN / 1e12 / world,
+        "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
+    ap.add_argument("--impl", default="urir", choices=["urir", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    try:
+        run_gpu(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

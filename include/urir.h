@@ -97,6 +97,9 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
  * For a Conv2DTranspose layer pass x = gradient of its output, dy = its input. */
 int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw,
                       void* stream);
+/* which kernel family URIR_IMPL_AUTO picks for this descriptor: op 0 = fprop, 1 = dgrad, 2 = wgrad;
+ * returns 1 = tcgen05 implicit GEMM, 0 = CUDA-core direct convolution. Pure host query. */
+int urir_conv_path(const urir_conv_desc* d, int op);
 /* fp32 HWIO master weights -> the two bf16 operand layouts. */
 int urir_weight_prep(const float* w_hwio, void* w_ck, void* w_kc, int taps, int C, int K,
                      void* stream);

@@ -74,7 +74,8 @@ def test_fprop_dgrad_wgrad(case, impl):
     cbias = torch.randn(Cc, generator=torch.Generator().manual_seed(7))
     dx = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
     dstats = torch.zeros(2 * Cc, device="cuda")
-    U.run_dgrad(d, dyg, w_ck, w_kc, cbias.cuda(), dx, dstats)
+    cbg = cbias.cuda()
+    U.run_dgrad(d, dyg, w_ck, w_kc, cbg, dx, dstats)
     refdx = gx + cbias
     assert U.rel_l2(dx.float(), refdx) < BF16_TOL
     assert U.max_abs(dstats[:Cc], refdx.sum(dim=(0, 1, 2))) < 2e-3 * float(refdx.abs().sum(dim=(0, 1, 2)).max())
@@ -107,7 +108,8 @@ def test_conv_transpose_matches_oracle():
             cat = torch.zeros(N, 2 * Hs, 2 * Ws, 2 * Cout, dtype=torch.bfloat16, device="cuda")
             w_ck, w_kc = U.prep_weights(w.cuda())
             d = U.conv_desc(N, 2 * Hs, 2 * Ws, Cout, Cin, k, 2, x_ld=2 * Cout, x_coff=Cout, impl=impl)
-            U.run_dgrad(d, x.cuda().to(torch.bfloat16), w_ck, w_kc, bias.cuda(), cat, None)
+            xg, bg = x.cuda().to(torch.bfloat16), bias.cuda()
+            U.run_dgrad(d, xg, w_ck, w_kc, bg, cat, None)
             assert U.rel_l2(cat[..., Cout:].float(), ref) < BF16_TOL, (k, impl)
             assert float(cat[..., :Cout].float().abs().max()) == 0.0      # left half untouched
 
@@ -123,11 +125,12 @@ def test_stem_and_head_shapes():
     w_ck, w_kc = U.prep_weights(w.cuda())
     y = torch.empty(N, H, W, 32, dtype=torch.bfloat16, device="cuda")
     d = U.conv_desc(N, H, W, 2, 32, 3, 1, x_dtype=L.F32)
-    U.run_fprop(d, x.cuda(), w_ck, w_kc, b.cuda(), y)
+    xg, bg = x.cuda(), b.cuda()
+    U.run_fprop(d, xg, w_ck, w_kc, bg, y)
     assert U.rel_l2(y.float(), _oracle_fprop(x, w, b, 1)) < BF16_TOL
     with pytest.raises(L.UrirError):
         d.impl = L.IMPL_TC
-        U.run_fprop(d, x.cuda(), w_ck, w_kc, b.cuda(), y)
+        U.run_fprop(d, xg, w_ck, w_kc, bg, y)
 
     xh = U.bf16_round(torch.randn(N, H, W, 32, generator=g))
     wh = U.bf16_round(torch.randn(6, 6, 32, 2, generator=g) * 0.05)
@@ -135,6 +138,7 @@ def test_stem_and_head_shapes():
     w_ck, w_kc = U.prep_weights(wh.cuda())
     out = torch.empty(N, H, W, 2, device="cuda")
     dh = U.conv_desc(N, H, W, 32, 2, 6, 1, y_dtype=L.F32, act=L.ACT_SIGMOID)
-    U.run_fprop(dh, xh.cuda().to(torch.bfloat16), w_ck, w_kc, bh.cuda(), out)
+    xhg, bhg = xh.cuda().to(torch.bfloat16), bh.cuda()
+    U.run_fprop(dh, xhg, w_ck, w_kc, bhg, out)
     ref = torch.sigmoid(_oracle_fprop(xh, wh, bh, 1))
     assert U.max_abs(out, ref) < 1e-5

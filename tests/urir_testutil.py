@@ -24,7 +24,9 @@ def prep_weights(w_hwio_cuda):
     kh, kw, c, k = w_hwio_cuda.shape
     w_ck = torch.empty(kh * kw, c, k, dtype=torch.bfloat16, device="cuda")
     w_kc = torch.empty(kh * kw, k, c, dtype=torch.bfloat16, device="cuda")
-    L.call("weight_prep", w_hwio_cuda.contiguous().data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), kh * kw, c, k)
+    src = w_hwio_cuda.contiguous()
+    L.call("weight_prep", src.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), kh * kw, c, k)
+    torch.cuda.current_stream().synchronize()      # `src` may be a temporary of the caller
     return w_ck, w_kc
 
 

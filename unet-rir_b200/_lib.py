@@ -43,6 +43,7 @@ _PROTOS = {
     "urir_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_conv2d_dgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_conv2d_wgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "urir_conv_path": (_i, [C.POINTER(ConvDesc), _i]),
     "urir_weight_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "urir_channel_sum": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp]),
     "urir_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _i, _vp]),
@@ -110,10 +111,45 @@ def launch_count(kind: int = 0) -> int:
     return int(load().urir_launch_count(kind))
 
 
+_profile = None     # when a list: every call appends (name, conv-desc-or-None, start_event, end_event)
+
+
+def profile_begin():
+    """Starts recording a CUDA-event pair around every urir_* call (bench.py's per-kernel timing)."""
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """-> list of (name, info dict, milliseconds); synchronises."""
+    global _profile
+    rec, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    return [(n, info, s.elapsed_time(e)) for n, info, s, e in rec]
+
+
+def _conv_info(name, args):
+    d = args[0]._obj if hasattr(args[0], "_obj") else None
+    if not isinstance(d, ConvDesc):
+        return {}
+    op = {"conv2d_fprop": 0, "conv2d_dgrad": 1, "conv2d_wgrad": 2}[name]
+    tc = int(load().urir_conv_path(C.byref(d), op))
+    return dict(tc=tc, N=d.N, H=d.H, W=d.W, C=d.C, K=d.K, R=d.R, S=d.S, stride=d.stride, P=d.P, Q=d.Q,
+                x_ld=d.x_ld, y_ld=d.y_ld, x_dtype=d.x_dtype, y_dtype=d.y_dtype, impl=d.impl,
+                flops=2.0 * d.N * d.P * d.Q * d.K * d.C * d.R * d.S)
+
+
 def call(name: str, *args):
     """Calls `urir_<name>`; the last argument (stream) is appended automatically."""
     fn = getattr(load(), "urir_" + name)
+    if _profile is None:
+        check(fn(*args, stream()), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
     check(fn(*args, stream()), name)
+    e.record()
+    _profile.append((name, _conv_info(name, args) if name.startswith("conv2d") else {}, s, e))
 
 
 def same_pad(in_size: int, k: int, s: int):

@@ -1,0 +1,411 @@
+"""`Trainer` and friends with the reference's names and semantics (amp_phase_trainer.py:12-306),
+running the step on the sm_100a engine.
+
+Trainer.step(spec_in, spec_out, emb, model) does what the reference does under its GradientTape
+(amp_phase_trainer.py:130-141): forward with training=True, amp-MSE + phase-(1-cos) loss, gradients
+for all 77 trainable variables, optimiser update -- as one fused device sequence
+(forward -> fused loss fwd+bwd -> backward -> Adam -> bf16 operand refresh), captured in a CUDA graph
+after the first call for a given batch size. It returns (loss, loss_phase, loss_stft) as 0-d device
+tensors so the loop does not synchronise per step (the reference syncs once per epoch, :94-96).
+
+Documented differences from the reference, which is not runnable as shipped:
+  * generators may yield either (spec_in, spec_out, emb) via __next__ (what Trainer.train unpacks,
+    :65) or be indexable DataGenerators returning (spec_in, emb, spec_out); both are accepted.
+  * matplotlib is imported lazily inside plot_graphs (it is not installed here).
+"""
+from __future__ import annotations
+
+import json
+import math
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _dev_tensor(x, dtype, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype, non_blocking=True)
+    return torch.as_tensor(np.asarray(x), dtype=dtype).to(device, non_blocking=True)
+
+
+def _mean(values):
+    """np.mean over a list of python floats or 0-d device tensors (one sync)."""
+    if len(values) == 0:
+        return float("nan")
+    if isinstance(values[0], torch.Tensor):
+        return float(torch.stack([v.reshape(()) for v in values]).float().mean().item())
+    return float(np.mean(values))
+
+
+class _KerasNadam:
+    """tf.keras.optimizers.Nadam (Dozat 2015 with Keras' momentum schedule) on the flat buffers.
+    Elementwise torch ops: the Nadam branch (amp_phase_trainer.py:30-31) is not on the measured path."""
+
+    def __init__(self, engine, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.e, self.b1, self.b2, self.eps = engine, beta_1, beta_2, epsilon
+        self.t, self.m_schedule = 0, 1.0
+
+    def apply(self, lr):
+        e = self.e
+        self.t += 1
+        t = self.t
+        u_t = self.b1 * (1.0 - 0.5 * 0.96 ** (0.004 * t))
+        u_t1 = self.b1 * (1.0 - 0.5 * 0.96 ** (0.004 * (t + 1)))
+        m_sched_new = self.m_schedule * u_t
+        m_sched_next = m_sched_new * u_t1
+        self.m_schedule = m_sched_new
+        g = e.G
+        e.M.mul_(self.b1).add_(g, alpha=1 - self.b1)
+        e.V.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+        g_prime = g / (1.0 - m_sched_new)
+        m_prime = e.M / (1.0 - m_sched_next)
+        v_prime = e.V / (1.0 - self.b2 ** t)
+        m_bar = (1.0 - u_t) * g_prime + u_t1 * m_prime
+        e.P.sub_(lr * m_bar / (v_prime.sqrt() + self.eps))
+        e.refresh_operands()
+
+
+class Trainer:
+
+    def __init__(self, alpha, n_epochs, optimizer, callbacks, lr_exp_decay, lr0, file_name):
+
+        'Initialization'
+        self.alpha = alpha            # stored and unused, like the reference (:17, loss at :155)
+        self.n_epochs = n_epochs
+        self.lr0 = lr0
+        self.model_checkpoint = callbacks[0]
+        self.early_stop = callbacks[1]
+        self.lr_exp_decay = lr_exp_decay[0]
+        self.lr_exp_decay_epoch = lr_exp_decay[1]
+        self.file_name = file_name
+
+        'Secondary initialization'
+        self.train_loss_history = np.empty((n_epochs, 3), dtype=np.float32)
+        self.val_loss_history = np.empty((n_epochs, 3), dtype=np.float32)
+
+        # substring match in the reference's order: "nadam" contains "adam" (:30-35)
+        if 'nadam' in optimizer:
+            self.optimizer = 'nadam'
+        elif 'sgd' in optimizer:
+            self.optimizer = 'sgd'
+        elif 'adam' in optimizer:
+            self.optimizer = 'adam'
+        else:
+            raise ValueError(f"optimizer must contain 'nadam', 'sgd' or 'adam', got {optimizer!r}")
+        self.learning_rate = lr0
+        self._nadam = None
+        self._graphs = {}
+        self.use_cuda_graph = True
+        self.dropout = True
+
+    # ------------------------------------------------------------------ epoch loop (:37-127)
+    @staticmethod
+    def _next_batch(gen, i):
+        if hasattr(gen, "__next__"):
+            return gen.__next__()                       # (spec_in, spec_out, emb), as :65 unpacks
+        spec_in, emb, spec_out = gen.__getitem__(i)[:3]  # DataGenerator order (datageneratorv2.py:101)
+        return spec_in, spec_out, emb
+
+    def train(self, model, train_generator, val_generator):
+        print("[INFO]: Training model...")
+        numUpdates = train_generator.__len__()
+        numUpdates_val = val_generator.__len__()
+
+        for epoch in range(0, self.n_epochs):
+            train_loss, train_loss_phase, train_loss_stft = [], [], []
+            val_loss, val_loss_phase, val_loss_stft = [], [], []
+
+            print("\n[INFO]: Starting epoch {}/{}...".format(epoch + 1, self.n_epochs), end="\n")
+            sys.stdout.flush()
+            epochStart = time.time()
+
+            # exponential lr in last epochs (:56-59)
+            if self.lr_exp_decay:
+                if epoch >= self.lr_exp_decay_epoch:
+                    self.learning_rate = self.lr0 * np.exp(-0.25 * (epoch - self.lr_exp_decay_epoch))
+
+            for i in range(0, numUpdates):
+                spec_in, spec_out, emb = self._next_batch(train_generator, i)
+                loss, loss_phase, loss_stft = self.step(spec_in, spec_out, emb, model)
+                train_loss.append(loss)
+                train_loss_phase.append(loss_phase)
+                train_loss_stft.append(loss_stft)
+
+            for i in range(0, numUpdates_val):
+                spec_in, spec_out, emb = self._next_batch(val_generator, i)
+                with torch.no_grad():
+                    spec_generated = model.model([spec_in, emb], training=False)
+                loss, loss_phase, loss_stft = self.model_loss(spec_out, spec_generated)
+                val_loss.append(loss)
+                val_loss_phase.append(loss_phase)
+                val_loss_stft.append(loss_stft)
+
+            elapsed = (time.time() - epochStart)
+            print("took {:.4} seconds".format(elapsed))
+
+            train_loss = _mean(train_loss)
+            train_loss_phase = _mean(train_loss_phase)
+            train_loss_stft = _mean(train_loss_stft)
+            print("Perdidas training:")
+            print(" - Perdidas: " + str(train_loss))
+            print(" - Perdidas fase: " + str(train_loss_phase))
+            print(" - Perdidas módulo: " + str(train_loss_stft))
+
+            val_loss = _mean(val_loss)
+            val_loss_phase = _mean(val_loss_phase)
+            val_loss_stft = _mean(val_loss_stft)
+            print("Perdidas validation:")
+            print(" - Perdidas combinadas: " + str(val_loss))
+            print(" - Perdidas fase: " + str(val_loss_phase))
+            print(" - Perdidas módulo: " + str(val_loss_stft))
+
+            self.train_loss_history[epoch][0] = train_loss
+            self.train_loss_history[epoch][1] = train_loss_phase
+            self.train_loss_history[epoch][2] = train_loss_stft
+            self.val_loss_history[epoch][0] = val_loss
+            self.val_loss_history[epoch][1] = val_loss_phase
+            self.val_loss_history[epoch][2] = val_loss_stft
+
+            improve = self.model_checkpoint.checkpoint(train_loss=train_loss, val_loss=val_loss, model=model)
+            stop = self.early_stop.stop_count(improve=improve)
+
+            if stop:
+                break
+
+        n_epochs = epoch + 1
+        H = History(n_epochs, self.train_loss_history[:n_epochs, :], self.val_loss_history[:n_epochs, :])
+        return model, H
+
+    # ------------------------------------------------------------------ one optimiser step (:130-141)
+    def _device_step(self, eng, B):
+        """forward -> loss -> backward -> optimiser on the engine's static buffers."""
+        H, W, _ = eng.input_shape
+        n = B * H * W
+        b = eng._buffers(B)
+        eng._forward_body(B, training=True, dropout=self.dropout)
+        L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), n, 1.0 / n, 1.0 / n, 1,
+               eng.losses_dev.data_ptr(), b["g_out"].data_ptr())
+        eng._backward_body(B)
+        if self.optimizer == 'adam':
+            eng.adam_step()
+        elif self.optimizer == 'sgd':
+            eng.sgd_step()
+
+    def step(self, spec_in, spec_out, emb, model):
+        eng = model.model.engine
+        dev = eng.device
+        spec_in = _dev_tensor(spec_in, torch.float32, dev)
+        spec_out = _dev_tensor(spec_out, torch.float32, dev)
+        emb = _dev_tensor(emb, torch.int32, dev)
+        B = spec_in.shape[0]
+        eng.set_lr(self.learning_rate)
+        eng.stage(spec_in, emb, spec_out)
+        if self.optimizer == 'nadam':
+            self._device_step(eng, B)
+            if self._nadam is None:
+                self._nadam = _KerasNadam(eng)
+            self._nadam.apply(self.learning_rate)
+        elif not self.use_cuda_graph:
+            self._device_step(eng, B)
+        else:
+            key = (id(eng), B, self.optimizer, self.dropout)
+            state = self._graphs.get(key)
+            if state is None:                      # first call: eager (also sets kernel attributes)
+                self._device_step(eng, B)
+                self._graphs[key] = "warm"
+            elif state == "warm":                  # second call: capture, then replay
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._device_step(eng, B)
+                self._graphs[key] = g
+                g.replay()
+            else:
+                state.replay()
+        losses = eng.losses_dev.clone()
+        return losses[0], losses[1], losses[2]
+
+    # ------------------------------------------------------------------ losses (:143-168)
+    def model_loss(self, y_true, y_pred):
+        """(loss, loss_phase, loss_stft): loss_stft = mean((a_t-a_p)^2), loss_phase =
+        mean(1-cos(2*pi*(p_t-p_p))), loss = loss_phase + loss_stft."""
+        dev = y_pred.device if isinstance(y_pred, torch.Tensor) and y_pred.is_cuda else torch.device("cuda")
+        yt = _dev_tensor(y_true, torch.float32, dev).contiguous()
+        yp = _dev_tensor(y_pred, torch.float32, dev).contiguous()
+        n = yt.numel() // 2
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        L.call("ampphase_loss", yt.data_ptr(), yp.data_ptr(), n, 1.0 / n, 1.0 / n, 0, out.data_ptr(), None)
+        return out[0], out[1], out[2]
+
+    def amplitude_loss(self, y_true, y_pred):
+        yt = _dev_tensor(y_true, torch.float32, "cuda")
+        yp = _dev_tensor(y_pred, torch.float32, "cuda")
+        pair_t = torch.stack([yt, torch.zeros_like(yt)], dim=-1).contiguous()
+        pair_p = torch.stack([yp, torch.zeros_like(yp)], dim=-1).contiguous()
+        return self.model_loss(pair_t, pair_p)[2]
+
+    def phase_loss(self, y_true, y_pred):
+        yt = _dev_tensor(y_true, torch.float32, "cuda")
+        yp = _dev_tensor(y_pred, torch.float32, "cuda")
+        pair_t = torch.stack([torch.zeros_like(yt), yt], dim=-1).contiguous()
+        pair_p = torch.stack([torch.zeros_like(yp), yp], dim=-1).contiguous()
+        return self.model_loss(pair_t, pair_p)[1]
+
+
+########################################################
+# Callbacks
+########################################################
+
+class ModelCheckpoint(object):
+    def __init__(self, filepath, save_best_only, verbose):
+        self.filepath = filepath
+        self.save_best_only = save_best_only
+        self.verbose = verbose
+
+        'Secondary initialization'
+        self.train_loss_min = 10
+        self.val_loss_min = 10
+
+    def checkpoint(self, train_loss, val_loss, model):
+        improve = False
+        if val_loss < self.val_loss_min:
+
+            if self.verbose:
+                print('Validation loss improved from ' + str(self.val_loss_min) + ' to ' + str(val_loss))
+
+            if self.save_best_only:
+                model.save(self.filepath)
+
+            self.val_loss_min = val_loss
+            self.train_loss_min = train_loss
+            improve = True
+
+        else:
+            if self.verbose:
+                print('Validation loss did not improve')
+
+        return improve
+
+
+class EarlyStopping(object):
+    def __init__(self, patience):
+        self.patience = patience
+
+        'Secondary initialization'
+        self.count = 0
+
+    def stop_count(self, improve):
+        stop = False
+        if improve:
+            self.count = 0
+        else:
+            self.count = self.count + 1
+
+        if self.count == self.patience:
+            stop = True
+
+        return stop
+
+
+class History(object):
+
+    def __init__(self, epochs, train_loss_history, val_loss_history, train_acc_history=None, val_acc_history=None):
+        self.epochs = epochs
+        self.train_loss_history = train_loss_history
+        self.train_acc_history = train_acc_history
+        self.val_loss_history = val_loss_history
+        self.val_acc_history = val_acc_history
+
+
+def plot_graphs(x1=None, y1=None, x2=None, y2=None, x3=None, y3=None, x4=None, y4=None, label1='', label2='',
+                label3='', label4='', filename='./Graphic.png'):
+    import matplotlib.pyplot as plt      # lazy: matplotlib is optional here
+    if x1 is None:
+        x1 = np.arange(0, len(y1))
+    if y2 is not None and x2 is None:
+        x2 = np.arange(0, len(y2))
+    if y3 is not None and x3 is None:
+        x3 = np.arange(0, len(y3))
+    if y4 is not None and x4 is None:
+        x4 = np.arange(0, len(y4))
+    plt.style.use("ggplot")
+    plt.figure()
+    plt.plot(x1, y1, label=label1)
+    for xx, yy, ll in ((x2, y2, label2), (x3, y3, label3), (x4, y4, label4)):
+        if yy is not None:
+            plt.plot(xx, yy, label=ll)
+    plt.title("Graphic")
+    plt.xlabel("Epoch ")
+    plt.ylabel("Loss")
+    plt.legend()
+    plt.savefig(filename)
+    plt.close()
+
+
+def params_saver(file_name, batch_size, optimizer, criterion, lr, BatchNorm, normalization, epochs,
+                 callbacks, alpha, beta, number_filters_0):
+    params = {}
+    params['batch_size'] = batch_size
+    params['optimizer'] = str(optimizer)
+    params['criterion'] = str(criterion)
+    params['epochs'] = epochs
+    params['lr'] = lr
+    params['alpha'] = alpha
+    params['beta'] = beta
+    params['batch_norm'] = BatchNorm
+    params['normalization'] = normalization
+    params['number_filters_0'] = number_filters_0
+    params['val_loss'] = float(callbacks[0].val_loss_min)
+    params['train_loss'] = float(callbacks[0].train_loss_min)
+    params['patience'] = callbacks[1].patience
+
+    with open(file_name + '/hiperparametros.json', 'w') as fp:
+        json.dump(params, fp)
+
+
+def rmse_coef(y_true, y_pred):
+    yt = torch.as_tensor(y_true, dtype=torch.float32).flatten()
+    yp = torch.as_tensor(y_pred, dtype=torch.float32).flatten().to(yt.device)
+    return torch.sqrt(torch.mean((yt - yp) ** 2) + 1.0e-12)
+
+
+def fit_mse(unet, x_train1, x_train2, y_train, x_val1, x_val2, y_val, batch_size, num_epochs, steps_per_epoch,
+            learning_rate, callbacks):
+    """UNet.compile_and_fit (u_net.py:83-118): Adam with InverseTimeDecay(lr, steps_per_epoch*100, rate 1),
+    MeanSquaredError over both channels, shuffle=False, EarlyStopping(val_loss, patience 20)."""
+    eng = unet.model.engine
+    hist = {"loss": [], "val_loss": []}
+    early = callbacks[1] if len(callbacks) > 1 else EarlyStopping(20)
+    it, best = 0, float("inf")
+    n_train = len(x_train1)
+    for epoch in range(num_epochs):
+        tl = []
+        for i in range(0, n_train, batch_size):
+            xb = _dev_tensor(x_train1[i:i + batch_size], torch.float32, eng.device)
+            eb = _dev_tensor(x_train2[i:i + batch_size], torch.int32, eng.device)
+            yb = _dev_tensor(y_train[i:i + batch_size], torch.float32, eng.device)
+            eng.set_lr(learning_rate / (1.0 + it / (steps_per_epoch * 100.0)))
+            out = eng.forward(xb, eb, training=True)
+            diff = out - yb
+            n = diff.numel()
+            eng.backward((2.0 / n) * diff * out * (1.0 - out))
+            eng.adam_step()
+            tl.append((diff * diff).mean())
+            it += 1
+        vl = []
+        for i in range(0, len(x_val1), batch_size):
+            xb = _dev_tensor(x_val1[i:i + batch_size], torch.float32, eng.device)
+            eb = _dev_tensor(x_val2[i:i + batch_size], torch.int32, eng.device)
+            yb = _dev_tensor(y_val[i:i + batch_size], torch.float32, eng.device)
+            out = eng.forward(xb, eb, training=False)
+            vl.append(((out - yb) ** 2).mean())
+        hist["loss"].append(_mean(tl)); hist["val_loss"].append(_mean(vl))
+        improve = hist["val_loss"][-1] < best
+        best = min(best, hist["val_loss"][-1])
+        if early.stop_count(improve):
+            break
+    return hist

@@ -117,6 +117,13 @@ int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, fl
     return use_tc ? conv_wgrad_tc(d, x, dy, dw, st) : conv_wgrad_simt_dispatch(d, x, dy, dw, st);
 }
 
+int urir_conv_path(const urir_conv_desc* d, int op) {
+    if (!d || d->impl == URIR_IMPL_SIMT || (d->impl == URIR_IMPL_AUTO && env_force_simt())) return 0;
+    if (op == 0) return igemm_fprop_supported(d) ? 1 : 0;
+    if (op == 1) return igemm_dgrad_supported(d) ? 1 : 0;
+    return wgrad_tc_supported(d) ? 1 : 0;
+}
+
 int urir_weight_prep(const float* w, void* w_ck, void* w_kc, int taps, int C, int K, void* stream) {
     URIR_CHECK_ARG(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, "weight_prep: bad args");
     return weight_prep(w, w_ck, w_kc, taps, C, K, (cudaStream_t)stream);

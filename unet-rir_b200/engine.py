@@ -257,17 +257,31 @@ class UNetEngine:
             self._conv_dgrad(cname, g_raw, g_x, k, 1, stats=g_x_stats, accumulate=accumulate)
 
     # ------------------------------------------------------------------ forward
+    def stage(self, spec_in, emb, spec_out=None):
+        """Copies one batch into the static input buffers (outside any captured graph)."""
+        B = spec_in.shape[0]
+        b = self._buffers(B)
+        b["x_in"].copy_(spec_in.reshape(b["x_in"].shape), non_blocking=True)
+        b["emb"].copy_(emb.reshape(B, self.T), non_blocking=True)
+        if spec_out is not None:
+            b["y_true"].copy_(spec_out.reshape(b["y_true"].shape), non_blocking=True)
+        self._last_B = B
+        return b
+
     def forward(self, spec_in, emb, training=False, dropout_mask=None, dropout=True):
         """model([spec_in, emb], training) -> fp32 (B, H, W, 2) in (0, 1) (a static buffer).
 
         dropout_mask: optional (B, dim) fp32 tensor of {0, 1/(1-rate)} to inject (parity tests);
         otherwise a fresh counter-based mask is drawn when training and dropout is True.
         """
-        B = spec_in.shape[0]
+        b = self.stage(spec_in, emb)
+        if training and dropout_mask is not None:
+            b["mask"].copy_(dropout_mask)
+        return self._forward_body(spec_in.shape[0], training, dropout, injected_mask=dropout_mask is not None)
+
+    def _forward_body(self, B, training, dropout=True, injected_mask=False):
         b = self._buffers(B)
         k = self.kernels
-        b["x_in"].copy_(spec_in.reshape(b["x_in"].shape))
-        b["emb"].copy_(emb.reshape(B, self.T))
         if training:
             self.stats_arena.zero_()
         # ---- encoder (encoding_block, u_net.py:265-289)
@@ -284,8 +298,8 @@ class UNetEngine:
                B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
         mask = None
         if training:
-            if dropout_mask is not None:
-                b["mask"].copy_(dropout_mask); mask = b["mask"]
+            if injected_mask:
+                mask = b["mask"]
             elif dropout:
                 L.call("dropout_mask", b["mask"].data_ptr(), b["mask"].numel(), PL.DROPOUT_RATE,
                        self.dropout_seed, self.step_dev.data_ptr())
@@ -317,69 +331,82 @@ class UNetEngine:
         """g_head: fp32 (B,H,W,2) gradient w.r.t. the head's PRE-sigmoid output. Fills self.grad."""
         B = self._last_B
         b = self._buffers(B)
-        k = self.kernels
         if g_head.data_ptr() != b["g_out"].data_ptr():
             b["g_out"].copy_(g_head)
-        self.bstat_arena.zero_()
-        bs_off = [0]
+        self._backward_body(B)
 
-        def bstat(c):
-            o = bs_off[0]; bs_off[0] += 2 * c
-            return self.bstat_arena[o:o + 2 * c]
+    def _bstat(self, key, c):
+        """Persistent slot of the bias-statistics arena ([sum | sumsq] of 2c floats) for `key`."""
+        slots = self.__dict__.setdefault("_bstat_slots", {})
+        if key not in slots:
+            o = sum(n for _, n in slots.values())
+            assert o + 2 * c <= self.bstat_arena.numel()
+            slots[key] = (o, 2 * c)
+        o, n = slots[key]
+        return self.bstat_arena[o:o + n]
 
-        g_out = View(b["g_out"])
-        d1 = View(b["d1"])
-        # head
-        self._conv_wgrad("head", d1, g_out, 6, 1)
-        L.call("channel_sum", g_out.ptr(), L.F32, g_out.npix, 2, 2, 0, self.grad["head.b"].data_ptr())
-        self._conv_dgrad("head", g_out, View(b["g_d1"]), 6, 1)
-        # decoder, top (level 1) down to level 4
-        for j in (5, 4, 3, 2):
-            i = 6 - j
-            n = self.F0 * 2 ** (i - 1)
-            cat, g_cat = View(b[f"cat{i}"]), View(b[f"g_cat{i}"])
-            self._cbr_bwd(f"dec{j}.blk.c1", f"dec{j}.blk.bn1", View(b[f"f{i}"]), View(b[f"rb{i}"]), View(b[f"g_d{i}"]),
-                          View(b[f"g_rb{i}"]), 3, g_x=View(b[f"g_f{i}"]))
-            st = bstat(2 * n)
-            self._cbr_bwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"g_f{i}"]),
-                          View(b[f"g_rf{i}"]), k, g_x=g_cat, g_x_stats=st)
-            # Conv2DTranspose: bias grad = channel sums of its output gradient (right half of g_cat)
-            self.grad[f"dec{j}.up.b"].copy_(st[n:2 * n])
-            g_up = View(b[f"g_cat{i}"], n, n)
-            x_in = View(b[f"d{i + 1}"]) if j > 2 else View(b["z"])
-            g_x_in = View(b[f"g_d{i + 1}"]) if j > 2 else View(b["g_z"])
-            self._conv_wgrad(f"dec{j}.up", g_up, x_in, k, 2)
-            st2 = bstat(x_in.C) if j == 2 else None
-            self._conv_fprop(f"dec{j}.up", g_up, g_x_in, k, 2, stats=st2, bias=False)   # ConvT dgrad
-            if j == 2:
-                self.grad["vec.proj.b"].copy_(st2[:x_in.C])
-        # bottleneck: z = e5 + proj(v16)
-        g_z = View(b["g_z"])
-        self._conv_wgrad("vec.proj", View(b["v16"]), g_z, 1, 1)
-        self._conv_dgrad("vec.proj", g_z, View(b["g_v16"]), 1, 1)
-        L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), b["g_v16"].data_ptr(),
-               L.ptr(self._fwd_mask), self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
-               b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
-        L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), self.grad["vec.emb"].data_ptr(),
-               B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
-        # encoder, level 5 up to level 1
-        g_e = g_z
-        for i in (5, 4, 3, 2, 1):
-            n = self.F0 * 2 ** (i - 1)
-            t, r = View(b[f"t{i}"]), View(b[f"r{i}"])
-            st = bstat(n)
-            self._cbr_bwd(f"enc{i}.blk.c1", f"enc{i}.blk.bn1", t, r, g_e, View(b[f"g_r{i}"]), 3,
-                          g_x=View(b[f"g_t{i}"]), g_x_stats=st)
-            self.grad[f"enc{i}.down.b"].copy_(st[:n])
-            g_t = View(b[f"g_t{i}"])
-            if i > 1:
-                e_prev = View(b[f"cat{i - 1}"], 0, n // 2)
-                g_e_prev = View(b[f"g_cat{i - 1}"], 0, n // 2)
-                self._conv_wgrad(f"enc{i}.down", e_prev, g_t, k, 2)
-                self._conv_dgrad(f"enc{i}.down", g_t, g_e_prev, k, 2, accumulate=1)
-                g_e = g_e_prev
-            else:
-                self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
+    def _backward_body(self, B, segment=None):
+        """segment: None = everything; 0 = head + decoder, 1 = bottleneck / vector block, 2 = encoder
+        (the order gradients become final, used for bucketed all-reduce overlap)."""
+        b = self._buffers(B)
+        k = self.kernels
+        if segment in (None, 0):
+            self.bstat_arena.zero_()
+            g_out = View(b["g_out"])
+            d1 = View(b["d1"])
+            # head
+            self._conv_wgrad("head", d1, g_out, 6, 1)
+            L.call("channel_sum", g_out.ptr(), L.F32, g_out.npix, 2, 2, 0, self.grad["head.b"].data_ptr())
+            self._conv_dgrad("head", g_out, View(b["g_d1"]), 6, 1)
+            # decoder, top (level 1) down to level 4
+            for j in (5, 4, 3, 2):
+                i = 6 - j
+                n = self.F0 * 2 ** (i - 1)
+                cat, g_cat = View(b[f"cat{i}"]), View(b[f"g_cat{i}"])
+                self._cbr_bwd(f"dec{j}.blk.c1", f"dec{j}.blk.bn1", View(b[f"f{i}"]), View(b[f"rb{i}"]),
+                              View(b[f"g_d{i}"]), View(b[f"g_rb{i}"]), 3, g_x=View(b[f"g_f{i}"]))
+                st = self._bstat(f"dec{j}.cat", 2 * n)
+                self._cbr_bwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"g_f{i}"]),
+                              View(b[f"g_rf{i}"]), k, g_x=g_cat, g_x_stats=st)
+                # Conv2DTranspose: bias grad = channel sums of its output gradient (right half of g_cat)
+                self.grad[f"dec{j}.up.b"].copy_(st[n:2 * n])
+                g_up = View(b[f"g_cat{i}"], n, n)
+                x_in = View(b[f"d{i + 1}"]) if j > 2 else View(b["z"])
+                g_x_in = View(b[f"g_d{i + 1}"]) if j > 2 else View(b["g_z"])
+                self._conv_wgrad(f"dec{j}.up", g_up, x_in, k, 2)
+                st2 = self._bstat("z", x_in.C) if j == 2 else None
+                self._conv_fprop(f"dec{j}.up", g_up, g_x_in, k, 2, stats=st2, bias=False)   # ConvT dgrad
+                if j == 2:
+                    self.grad["vec.proj.b"].copy_(st2[:x_in.C])
+        if segment in (None, 1):
+            # bottleneck: z = e5 + proj(v16)
+            g_z = View(b["g_z"])
+            self._conv_wgrad("vec.proj", View(b["v16"]), g_z, 1, 1)
+            self._conv_dgrad("vec.proj", g_z, View(b["g_v16"]), 1, 1)
+            L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), b["g_v16"].data_ptr(),
+                   L.ptr(self._fwd_mask), self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
+                   b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
+            L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), self.grad["vec.emb"].data_ptr(),
+                   B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+        if segment in (None, 2):
+            # encoder, level 5 up to level 1
+            g_e = View(b["g_z"])
+            for i in (5, 4, 3, 2, 1):
+                n = self.F0 * 2 ** (i - 1)
+                t, r = View(b[f"t{i}"]), View(b[f"r{i}"])
+                st = self._bstat(f"enc{i}.t", n)
+                self._cbr_bwd(f"enc{i}.blk.c1", f"enc{i}.blk.bn1", t, r, g_e, View(b[f"g_r{i}"]), 3,
+                              g_x=View(b[f"g_t{i}"]), g_x_stats=st)
+                self.grad[f"enc{i}.down.b"].copy_(st[:n])
+                g_t = View(b[f"g_t{i}"])
+                if i > 1:
+                    e_prev = View(b[f"cat{i - 1}"], 0, n // 2)
+                    g_e_prev = View(b[f"g_cat{i - 1}"], 0, n // 2)
+                    self._conv_wgrad(f"enc{i}.down", e_prev, g_t, k, 2)
+                    self._conv_dgrad(f"enc{i}.down", g_t, g_e_prev, k, 2, accumulate=1)
+                    g_e = g_e_prev
+                else:
+                    self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
 
     # ------------------------------------------------------------------ loss + optimiser
     def loss_and_grad(self, y_true, w_amp, w_ph, need_grad=True):
