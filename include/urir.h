@@ -153,9 +153,12 @@ int urir_dropout_mask(float* mask, long long n, float rate, uint64_t seed,
 /* y_true, y_pred fp32 [npix, 2] (amp, phase). losses[4] (overwritten) =
  *   [w_amp*SSE + w_ph*sum(1-cos), mean(1-cos), mean sq err, 0];
  * grad (optional, fp32 [npix,2]) = dL/dy_pred, times y(1-y) when sigmoid_bwd != 0 (the head's
- * "sigmoid_layer", u_net.py:249). */
+ * "sigmoid_layer", u_net.py:249). grad_bf16 (optional): the same gradient as bf16 with
+ * `grad_bf16_ld` elements per pixel (only the first 2 are written) -- the TMA-loadable operand of the
+ * head's tensor-core dgrad / wgrad. */
 int urir_ampphase_loss(const float* y_true, const float* y_pred, long long npix, float w_amp,
-                       float w_ph, int sigmoid_bwd, float* losses, float* grad, void* stream);
+                       float w_ph, int sigmoid_bwd, float* losses, float* grad, void* grad_bf16,
+                       int grad_bf16_ld, void* stream);
 
 /* ---- optimiser (amp_phase_trainer.py:30-35,139 ; Keras conventions) ------ */
 /* flat Adam over n contiguous fp32 elements; lr and step (0-based count of completed steps)

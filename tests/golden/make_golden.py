@@ -1,0 +1,73 @@
+"""Generates tests/golden/*.npz / *.json from the REFERENCE's own code, run in the build container.
+
+TensorFlow / librosa are not installed, so the reference's modules cannot be imported; but a few of its
+classes are pure numpy / pure Python. This script lifts exactly those definitions out of the reference
+sources with `ast` (no reference source is copied into the repo), executes them, and records their
+outputs on seeded inputs:
+  * preprocess.py : Normalizer.normalize / denormalize, TensorPadder.pad_amp_phase / un_pad, sigmoid
+  * amp_phase_trainer.py : ModelCheckpoint.checkpoint / EarlyStopping.stop_count decision traces
+The U-Net graph (Keras), the STFT (librosa) and the losses (tf ops) cannot be executed here; for those the
+oracle is a restatement (parity unpinned, see oracle/*.py headers).
+
+Run:  python tests/golden/make_golden.py   (needs /root/reference; the outputs are committed)
+"""
+import ast
+import json
+import math
+import os
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def lift(path, names):
+    src = open(path).read()
+    tree = ast.parse(src)
+    body = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in names]
+    ns = {"np": np, "math": math}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def main():
+    rng = np.random.default_rng(500)
+    pre = lift(os.path.join(REF, "preprocess.py"), {"Normalizer", "TensorPadder", "sigmoid"})
+    amp = np.abs(rng.standard_normal((129, 151))).astype(np.float32) * np.exp(rng.uniform(-12, 3, (129, 151))).astype(np.float32)
+    amp[0, 0] = 0.0                                      # exact zero -> the -100 dB floor
+    phase = rng.uniform(-math.pi, math.pi, (129, 151)).astype(np.float32)
+    nz = pre["Normalizer"]()
+    a_n, p_n = nz.normalize(amp, phase)
+    a_d, p_d = nz.denormalize(a_n, p_n)
+    pad = pre["TensorPadder"]((144, 160))
+    a_p, p_p = pad.pad_amp_phase(a_n, p_n)
+    a_u, p_u = pre["TensorPadder"].un_pad(a_p, p_p, (129, 151))
+    big = rng.standard_normal((150, 10))
+    big_out = pre["TensorPadder"]((144, 160)).transform(big)     # larger than desired in dim 0 -> unchanged
+    sig = pre["sigmoid"](0.5, (144, 160))
+    np.savez_compressed(os.path.join(OUT, "preprocess_golden.npz"), amp=amp, phase=phase, amp_norm=a_n, phase_norm=p_n,
+                        amp_denorm=a_d, phase_denorm=p_d, amp_pad=a_p, phase_pad=p_p, amp_unpad=a_u, phase_unpad=p_u,
+                        big=big, big_out=big_out, sigmoid=sig.astype(np.float32))
+
+    cb = lift(os.path.join(REF, "amp_phase_trainer.py"), {"ModelCheckpoint", "EarlyStopping"})
+
+    class FakeModel:
+        def __init__(self): self.saved = 0
+        def save(self, path): self.saved += 1
+
+    val = [12.0, 9.5, 9.7, 9.1, 9.1, 9.3, 9.2, 9.4, 8.0, 8.1, 8.2, 8.3]
+    trn = [11.0, 9.0, 8.0, 7.0, 6.5, 6.0, 5.5, 5.0, 4.5, 4.0, 3.5, 3.0]
+    mc, es, fm = cb["ModelCheckpoint"]("ckpt", True, 0), cb["EarlyStopping"](3), FakeModel()
+    trace = []
+    for t, v in zip(trn, val):
+        imp = mc.checkpoint(train_loss=t, val_loss=v, model=fm)
+        stop = es.stop_count(improve=imp)
+        trace.append({"train": t, "val": v, "improve": bool(imp), "stop": bool(stop), "count": es.count,
+                      "val_min": mc.val_loss_min, "train_min": mc.train_loss_min, "saved": fm.saved})
+    json.dump({"patience": 3, "trace": trace}, open(os.path.join(OUT, "callbacks_golden.json"), "w"), indent=1)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()

@@ -142,3 +142,54 @@ def test_stem_and_head_shapes():
     U.run_fprop(dh, xhg, w_ck, w_kc, bhg, out)
     ref = torch.sigmoid(_oracle_fprop(xh, wh, bh, 1))
     assert U.max_abs(out, ref) < 1e-5
+
+
+def test_small_channel_tensor_core_paths():
+    """Channel counts below the 32-wide MMA tile ride on TMA zero-fill + masked epilogues: the 6x6 32->2
+    sigmoid head (fprop fp32 out, wgrad from the padded bf16 gradient) and the 1x1 16->512 vector
+    projection (u_net.py:248-249, 262)."""
+    g = torch.Generator().manual_seed(11)
+    N, H, W = 2, 16, 32
+    # ---- head fprop on tensor cores
+    xh = U.bf16_round(torch.randn(N, H, W, 32, generator=g))
+    wh = U.bf16_round(torch.randn(6, 6, 32, 2, generator=g) * 0.05)
+    bh = torch.randn(2, generator=g) * 0.1
+    w_ck, w_kc = U.prep_weights(wh.cuda())
+    xhg, bhg = xh.cuda().to(torch.bfloat16), bh.cuda()
+    out = torch.empty(N, H, W, 2, device="cuda")
+    dh = U.conv_desc(N, H, W, 32, 2, 6, 1, y_dtype=L.F32, act=L.ACT_SIGMOID, impl=L.IMPL_TC)
+    U.run_fprop(dh, xhg, w_ck, w_kc, bhg, out)
+    ref = torch.sigmoid(_oracle_fprop(xh, wh, bh, 1))
+    assert U.max_abs(out, ref) < 1e-5
+    # ---- head wgrad: dy = bf16 gradient with a 16-byte pixel pitch (2 valid channels of 8)
+    dz = U.bf16_round(torch.randn(N, H, W, 2, generator=g))
+    dz8 = torch.zeros(N, H, W, 8, dtype=torch.bfloat16, device="cuda")
+    dz8[..., :2] = dz.cuda().to(torch.bfloat16)
+    xr, wr = xh.clone(), wh.clone().requires_grad_(True)
+    gw, = torch.autograd.grad(_oracle_fprop(xr, wr, None, 1), [wr], dz)
+    dw = torch.full((6, 6, 32, 2), 7.0, device="cuda")
+    dwd = U.conv_desc(N, H, W, 32, 2, 6, 1, y_ld=8, impl=L.IMPL_TC)
+    U.run_wgrad(dwd, xhg, dz8, dw)
+    assert U.rel_l2(dw, gw) < F32_TOL
+    # ---- vector projection: 1x1, C=16 -> K=64, accumulate into an existing tensor
+    xp = U.bf16_round(torch.randn(N, 9, 10, 16, generator=g))
+    wp = U.bf16_round(torch.randn(1, 1, 16, 64, generator=g) * 0.2)
+    bp = torch.randn(64, generator=g) * 0.1
+    base = U.bf16_round(torch.randn(N, 9, 10, 64, generator=g))
+    w_ck, w_kc = U.prep_weights(wp.cuda())
+    xpg, bpg = xp.cuda().to(torch.bfloat16), bp.cuda()
+    y = base.cuda().to(torch.bfloat16)
+    dp = U.conv_desc(N, 9, 10, 16, 64, 1, 1, impl=L.IMPL_TC, accumulate=1)
+    U.run_fprop(dp, xpg, w_ck, w_kc, bpg, y)
+    assert U.rel_l2(y.float(), _oracle_fprop(xp, wp, bp, 1) + base) < BF16_TOL
+    dy = U.bf16_round(torch.randn(N, 9, 10, 64, generator=g))
+    xr, wr = xp.clone().requires_grad_(True), wp.clone().requires_grad_(True)
+    gx, gw = torch.autograd.grad(_oracle_fprop(xr, wr, None, 1), [xr, wr], dy)
+    dyg = dy.cuda().to(torch.bfloat16)
+    dx = torch.empty(N, 9, 10, 16, dtype=torch.bfloat16, device="cuda")
+    dp.accumulate = 0
+    U.run_dgrad(dp, dyg, w_ck, w_kc, None, dx)
+    assert U.rel_l2(dx.float(), gx) < BF16_TOL
+    dw = torch.empty(1, 1, 16, 64, device="cuda")
+    U.run_wgrad(dp, xpg, dyg, dw)
+    assert U.rel_l2(dw, gw) < F32_TOL

@@ -85,8 +85,10 @@ def test_ampphase_loss_and_grad(kind):
     gz, = torch.autograd.grad(loss, z)
     losses = torch.empty(4, device="cuda"); grad = torch.empty(B, H, W, 2, device="cuda")
     yt_g, yp_g = yt.cuda(), yp.detach().cuda()
+    g16 = torch.zeros(B, H, W, 8, dtype=torch.bfloat16, device="cuda")
     L.call("ampphase_loss", yt_g.data_ptr(), yp_g.data_ptr(), B * H * W, w_amp, w_ph, 1,
-           losses.data_ptr(), grad.data_ptr())
+           losses.data_ptr(), grad.data_ptr(), g16.data_ptr(), 8)
+    assert U.rel_l2(g16[..., :2].float(), gz) < 4e-3 and float(g16[..., 2:].float().abs().max()) == 0.0
     assert abs(float(losses[0]) - float(loss)) < 1e-5 * max(1.0, abs(float(loss)))
     assert abs(float(losses[1]) - float(lp)) < 1e-5 and abs(float(losses[2]) - float(ls)) < 1e-6
     assert U.rel_l2(grad, gz) < 1e-5
@@ -205,4 +207,4 @@ def test_unsupported_shapes_fail_loudly():
     with pytest.raises(L.UrirError):
         L.call("stft_ampphase", wav.data_ptr(), 1, C.byref(d), spec.data_ptr())
     with pytest.raises(L.UrirError):
-        L.call("ampphase_loss", wav.data_ptr(), wav.data_ptr(), 3, 1.0, 1.0, 0, wav.data_ptr(), None)
+        L.call("ampphase_loss", wav.data_ptr(), wav.data_ptr(), 3, 1.0, 1.0, 0, wav.data_ptr(), None, None, 0)

@@ -188,7 +188,7 @@ class Trainer:
         b = eng._buffers(B)
         eng._forward_body(B, training=True, dropout=self.dropout)
         L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), n, 1.0 / n, 1.0 / n, 1,
-               eng.losses_dev.data_ptr(), b["g_out"].data_ptr())
+               eng.losses_dev.data_ptr(), b["g_out"].data_ptr(), b["g_out8"].data_ptr(), 8)
         eng._backward_body(B)
         if self.optimizer == 'adam':
             eng.adam_step()
@@ -238,7 +238,7 @@ class Trainer:
         yp = _dev_tensor(y_pred, torch.float32, dev).contiguous()
         n = yt.numel() // 2
         out = torch.empty(4, dtype=torch.float32, device=dev)
-        L.call("ampphase_loss", yt.data_ptr(), yp.data_ptr(), n, 1.0 / n, 1.0 / n, 0, out.data_ptr(), None)
+        L.call("ampphase_loss", yt.data_ptr(), yp.data_ptr(), n, 1.0 / n, 1.0 / n, 0, out.data_ptr(), None, None, 0)
         return out[0], out[1], out[2]
 
     def amplitude_loss(self, y_true, y_pred):

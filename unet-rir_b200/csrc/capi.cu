@@ -37,7 +37,7 @@ int bn_relu_bwd_reduce(const void*, int, int, const void*, int, int, const float
 int bn_relu_bwd_apply(const void*, int, int, const void*, int, int, const float*, const float*, const float*, const float*,
                       void*, int, int, float*, float*, float*, long long, int, cudaStream_t);
 int channel_sum(const void*, int, long long, int, int, int, float*, cudaStream_t);
-int ampphase_loss(const float*, const float*, long long, float, float, int, float*, float*, cudaStream_t);
+int ampphase_loss(const float*, const float*, long long, float, float, int, float*, float*, void*, int, cudaStream_t);
 int adam(float*, const float*, float*, float*, long long, const float*, const int*, float, float, float, cudaStream_t);
 int sgd(float*, const float*, long long, const float*, cudaStream_t);
 int step_increment(int*, cudaStream_t);
@@ -180,9 +180,10 @@ int urir_dropout_mask(float* mask, long long n, float rate, uint64_t seed, const
 }
 
 int urir_ampphase_loss(const float* y_true, const float* y_pred, long long npix, float w_amp, float w_ph,
-                       int sigmoid_bwd, float* losses, float* grad, void* stream) {
+                       int sigmoid_bwd, float* losses, float* grad, void* grad_bf16, int grad_bf16_ld, void* stream) {
     URIR_CHECK_ARG(y_true && y_pred && losses, "ampphase_loss: null tensor");
-    return ampphase_loss(y_true, y_pred, npix, w_amp, w_ph, sigmoid_bwd, losses, grad, (cudaStream_t)stream);
+    return ampphase_loss(y_true, y_pred, npix, w_amp, w_ph, sigmoid_bwd, losses, grad, grad_bf16, grad_bf16_ld,
+                         (cudaStream_t)stream);
 }
 
 int urir_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, const int32_t* step_dev,

@@ -41,8 +41,10 @@ struct IgemmParams {
     int accumulate;
     const float* bias;              // [Ngemm] or null
     float* stats;                   // [2*Ngemm] or null
-    __nv_bfloat16* out;
-    int n_total;                    // Ngemm
+    void* out;                      // bf16, or fp32 when out_f32
+    int n_total;                    // Ngemm (valid output channels; may be < gridDim.y * BLOCK_N)
+    int out_f32;                    // 1: fp32 output (head), columns stored individually
+    int act;                        // URIR_ACT_SIGMOID only with out_f32
     IgemmTap taps[36];
 };
 
@@ -170,11 +172,14 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
             const int row = warp * 32 + lane;
             const int iw = row % p.bw, ih = (row / p.bw) % p.bh, in = row / (p.bw * p.bh);
             const bool valid = (row < p.bw * p.bh * p.bn) && (w0 + iw < OW) && (h0 + ih < OH) && (n0 + in < p.NB);
-            __nv_bfloat16* orow = p.out + p.cls_off[cls] + (long long)(n0 + in) * p.o_sn + (long long)(h0 + ih) * p.o_sh +
-                                  (long long)(w0 + iw) * p.o_sw + (long long)n_tile * BLOCK_N;
+            const long long o_elem = p.cls_off[cls] + (long long)(n0 + in) * p.o_sn + (long long)(h0 + ih) * p.o_sh +
+                                     (long long)(w0 + iw) * p.o_sw + (long long)n_tile * BLOCK_N;
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + o_elem;
+            float* orow_f = reinterpret_cast<float*>(p.out) + o_elem;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const int n_left = p.n_total - n_tile * BLOCK_N;           // valid columns of this N tile
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+            for (int c0 = 0; c0 < BLOCK_N && c0 < n_left; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(lane_addr + c0, r);
                 tmem_ld_wait();
@@ -182,24 +187,36 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     v[j] = __uint_as_float(r[j]);
-                    if (p.bias) v[j] += __ldg(p.bias + n_tile * BLOCK_N + c0 + j);
-                    if (!valid) v[j] = 0.f;
+                    if (p.bias && c0 + j < n_left) v[j] += __ldg(p.bias + n_tile * BLOCK_N + c0 + j);
+                    if (!valid || c0 + j >= n_left) v[j] = 0.f;
                 }
                 if (valid) {
-                    uint4 o0, o1;
-                    if (p.accumulate) {
-                        const uint4 e0 = *reinterpret_cast<const uint4*>(orow + c0), e1 = *reinterpret_cast<const uint4*>(orow + c0 + 8);
-                        const uint32_t ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-                        uint32_t oo[8];
+                    if (p.out_f32) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float2 f = unpack_bf16x2(ee[j]); oo[j] = pack_bf16x2(v[2 * j] + f.x, v[2 * j + 1] + f.y); }
-                        o0 = make_uint4(oo[0], oo[1], oo[2], oo[3]); o1 = make_uint4(oo[4], oo[5], oo[6], oo[7]);
+                        for (int j = 0; j < 16; ++j) {
+                            if (c0 + j < n_left) {
+                                float o = v[j];
+                                if (p.act == URIR_ACT_SIGMOID) o = 1.f / (1.f + __expf(-o));
+                                if (p.accumulate) o += orow_f[c0 + j];
+                                orow_f[c0 + j] = o;
+                            }
+                        }
                     } else {
-                        o0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                        o1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                        uint4 o0, o1;
+                        if (p.accumulate) {
+                            const uint4 e0 = *reinterpret_cast<const uint4*>(orow + c0), e1 = *reinterpret_cast<const uint4*>(orow + c0 + 8);
+                            const uint32_t ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                            uint32_t oo[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { const float2 f = unpack_bf16x2(ee[j]); oo[j] = pack_bf16x2(v[2 * j] + f.x, v[2 * j + 1] + f.y); }
+                            o0 = make_uint4(oo[0], oo[1], oo[2], oo[3]); o1 = make_uint4(oo[4], oo[5], oo[6], oo[7]);
+                        } else {
+                            o0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                            o1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                        }
+                        *reinterpret_cast<uint4*>(orow + c0) = o0;
+                        *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
                     }
-                    *reinterpret_cast<uint4*>(orow + c0) = o0;
-                    *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
                 }
                 if (p.stats) {
                     float q[16];
@@ -221,7 +238,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
     if (p.stats && tile_live) {
         for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) {
             const int which = i / BLOCK_N, col = i % BLOCK_N;
-            atomicAdd(p.stats + which * p.n_total + n_tile * BLOCK_N + col, sstats[i]);
+            if (n_tile * BLOCK_N + col < p.n_total)
+                atomicAdd(p.stats + which * p.n_total + n_tile * BLOCK_N + col, sstats[i]);
         }
     }
     if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
@@ -304,7 +322,7 @@ static int launch_cfg(const IgemmMaps& maps, const IgemmParams& p, int n_tiles, 
 }
 
 static int launch_igemm(const IgemmMaps& maps, const IgemmParams& p, int block_n, int block_k, cudaStream_t st) {
-    const int n_tiles = p.n_total / block_n;
+    const int n_tiles = (p.n_total + block_n - 1) / block_n;
 #define URIR_CFG(BN, BK, ST) if (block_n == BN && block_k == BK) return launch_cfg<BN, BK, ST>(maps, p, n_tiles, st);
     URIR_CFG(128, 64, 3) URIR_CFG(64, 64, 4) URIR_CFG(32, 64, 4)
     URIR_CFG(128, 32, 4) URIR_CFG(64, 32, 4) URIR_CFG(32, 32, 4)
@@ -312,15 +330,20 @@ static int launch_igemm(const IgemmMaps& maps, const IgemmParams& p, int block_n
     return fail(URIR_ERR_UNSUP, "igemm: no kernel for BLOCK_N=%d BLOCK_K=%d", block_n, block_k);
 }
 
-static int pick_block_n(int n) { return (n % 128 == 0) ? 128 : (n % 64 == 0) ? 64 : (n % 32 == 0) ? 32 : 0; }
+// GEMM-N tile: channel counts that are not a multiple of 32 run a masked 32-wide tile (TMA zero-fills
+// the missing weight rows); GEMM-K chunks likewise zero-fill channels past the tensor's extent.
+static int pick_block_n(int n) { return (n % 128 == 0) ? 128 : (n % 64 == 0) ? 64 : 32; }
+static int pick_block_k(int k) { return (k % 64 == 0) ? 64 : 32; }
 
 bool igemm_fprop_supported(const urir_conv_desc* d) {
-    return d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16 && d->C % 32 == 0 && pick_block_n(d->K) != 0 &&
-           d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 &&
-           (d->stride == 1 || d->stride == 2) && d->act == URIR_ACT_NONE && d->R * d->S <= 36;
+    if (d->x_dtype != URIR_BF16 || d->x_ld % 8 || d->x_coff % 8 || d->C % 8 || d->R * d->S > 36) return false;
+    if (d->stride != 1 && d->stride != 2) return false;
+    if (d->y_dtype == URIR_BF16)
+        return d->K % 16 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 && d->act == URIR_ACT_NONE;
+    return d->K <= 32;                       // fp32 output (the sigmoid head): scalar stores, one masked N tile
 }
 bool igemm_dgrad_supported(const urir_conv_desc* d) {
-    return d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16 && d->K % 32 == 0 && pick_block_n(d->C) != 0 &&
+    return d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16 && d->C % 16 == 0 && d->K % 8 == 0 &&
            d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 &&
            (d->stride == 1 || d->stride == 2) && d->R * d->S <= 36;
 }
@@ -329,15 +352,16 @@ bool igemm_dgrad_supported(const urir_conv_desc* d) {
 int conv_fprop_igemm(const urir_conv_desc* d, const void* x, const void* w_kc, const float* bias, void* y,
                      float* stats, cudaStream_t st) {
     URIR_CHECK_ARG(w_kc != nullptr, "fprop(tcgen05) needs w_kc");
-    const int BK = (d->C % 64 == 0) ? 64 : 32, BN = pick_block_n(d->K);
+    const int BK = pick_block_k(d->C), BN = pick_block_n(d->K);
     IgemmMaps maps; IgemmParams p;
     memset(&p, 0, sizeof(p));
+    p.out_f32 = d->y_dtype == URIR_F32; p.act = d->act;
     choose_box(d->Q, d->P, d->N, 128, &p.bw, &p.bh, &p.bn);
     p.tiles_w = cdiv(d->Q, p.bw); p.tiles_h = cdiv(d->P, p.bh); p.tiles_n = cdiv(d->N, p.bn);
     p.NB = d->N; p.n_classes = 1; p.cls_OW[0] = d->Q; p.cls_OH[0] = d->P; p.cls_off[0] = d->y_coff;
     p.o_sn = (long long)d->P * d->Q * d->y_ld; p.o_sh = (long long)d->Q * d->y_ld; p.o_sw = d->y_ld;
-    p.kchunks = d->C / BK; p.accumulate = d->accumulate; p.bias = bias; p.stats = stats;
-    p.out = (__nv_bfloat16*)y; p.n_total = d->K;
+    p.kchunks = (d->C + BK - 1) / BK; p.accumulate = d->accumulate; p.bias = bias; p.stats = stats;
+    p.out = y; p.n_total = d->K;
     const int s = d->stride;
     const char* xb = (const char*)x + (size_t)d->x_coff * 2;
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
@@ -378,7 +402,7 @@ int conv_fprop_igemm(const urir_conv_desc* d, const void* x, const void* w_kc, c
 int conv_dgrad_igemm(const urir_conv_desc* d, const void* dy, const void* w_ck, const float* bias, void* dx,
                      float* stats, cudaStream_t st) {
     URIR_CHECK_ARG(w_ck != nullptr, "dgrad(tcgen05) needs w_ck");
-    const int BK = (d->K % 64 == 0) ? 64 : 32, BN = pick_block_n(d->C);
+    const int BK = pick_block_k(d->K), BN = pick_block_n(d->C);
     IgemmMaps maps; IgemmParams p;
     memset(&p, 0, sizeof(p));
     const int s = d->stride;
@@ -387,8 +411,8 @@ int conv_dgrad_igemm(const urir_conv_desc* d, const void* dy, const void* w_ck, 
     p.tiles_w = cdiv(LW, p.bw); p.tiles_h = cdiv(LH, p.bh); p.tiles_n = cdiv(d->N, p.bn);
     p.NB = d->N; p.n_classes = s * s;
     p.o_sn = (long long)d->H * d->W * d->x_ld; p.o_sh = (long long)s * d->W * d->x_ld; p.o_sw = (long long)s * d->x_ld;
-    p.kchunks = d->K / BK; p.accumulate = d->accumulate; p.bias = bias; p.stats = stats;
-    p.out = (__nv_bfloat16*)dx; p.n_total = d->C;
+    p.kchunks = (d->K + BK - 1) / BK; p.accumulate = d->accumulate; p.bias = bias; p.stats = stats;
+    p.out = dx; p.n_total = d->C;
     int nt = 0;
     for (int pi = 0; pi < s; ++pi)
         for (int pj = 0; pj < s; ++pj) {

@@ -230,10 +230,16 @@ static int launch_wgrad(const ConvP& p, const void* x, const void* dy, float* dw
     return URIR_OK;
 }
 
+bool stem_fprop_supported(const urir_conv_desc* d, const float* stats);
+bool stem_wgrad_supported(const urir_conv_desc* d);
+int stem_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, const float* bias, void* y, cudaStream_t st);
+int stem_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
+
 int conv_fprop_simt_dispatch(const urir_conv_desc* d, const void* x, const void* w_ck, const float* bias,
                              void* y, float* stats, cudaStream_t st) {
     ConvP p = to_p(d);
     URIR_CHECK_ARG(w_ck != nullptr, "fprop(SIMT) needs w_ck");
+    if (stem_fprop_supported(d, stats)) return stem_fprop(d, x, w_ck, bias, y, st);
     if (d->x_dtype == URIR_F32 && d->y_dtype == URIR_BF16) return launch_fprop<float, __nv_bfloat16>(p, x, w_ck, bias, y, stats, st);
     if (d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16) return launch_fprop<__nv_bfloat16, __nv_bfloat16>(p, x, w_ck, bias, y, stats, st);
     if (d->x_dtype == URIR_BF16 && d->y_dtype == URIR_F32) return launch_fprop<__nv_bfloat16, float>(p, x, w_ck, bias, y, stats, st);
@@ -252,6 +258,7 @@ int conv_dgrad_simt_dispatch(const urir_conv_desc* d, const void* dy, const void
 
 int conv_wgrad_simt_dispatch(const urir_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
     ConvP p = to_p(d);
+    if (stem_wgrad_supported(d)) return stem_wgrad(d, x, dy, dw, st);
     if (d->x_dtype == URIR_F32 && d->y_dtype == URIR_BF16) return launch_wgrad<float, __nv_bfloat16>(p, x, dy, dw, st);
     if (d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16) return launch_wgrad<__nv_bfloat16, __nv_bfloat16>(p, x, dy, dw, st);
     if (d->x_dtype == URIR_BF16 && d->y_dtype == URIR_F32) return launch_wgrad<__nv_bfloat16, float>(p, x, dy, dw, st);

@@ -160,10 +160,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
                     tmem_ld16(lane_addr + ti * BLOCK_N + c0, r);
                     tmem_ld_wait();
                     if (valid) {
+                        const int n_left = p.K - n_tile * BLOCK_N - c0;      // valid columns from c0 on
+                        if (n_left >= 16 && (p.K & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                            for (int j = 0; j < 16; j += 4)
+                                red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < n_left) atomicAdd(drow + c0 + j, __uint_as_float(r[j]));
+                        }
                     }
                 }
             }
@@ -208,11 +215,12 @@ static int launch_wg(const WgradMaps& maps, const WgradParams& p, dim3 grid, cud
     return URIR_OK;
 }
 
-static int pick_n(int k) { return (k % 128 == 0) ? 128 : (k % 64 == 0) ? 64 : (k % 32 == 0) ? 32 : 0; }
+// channel counts that are not multiples of the tile run masked tiles; TMA zero-fills the missing channels
+static int pick_n(int k) { return (k % 128 == 0) ? 128 : (k % 64 == 0) ? 64 : 32; }
 
 bool wgrad_tc_supported(const urir_conv_desc* d) {
-    return d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16 && d->C % 32 == 0 && (d->C <= 64 || d->C % 128 == 0) &&
-           pick_n(d->K) != 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 &&
+    return d->x_dtype == URIR_BF16 && d->y_dtype == URIR_BF16 && (d->C <= 64 || d->C % 128 == 0) &&
+           d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 &&
            (d->stride == 1 || d->stride == 2) && d->R * d->S <= 36;
 }
 
@@ -229,9 +237,9 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
     p.C = d->C; p.K = d->K; p.ntaps = ntaps; p.dw = dw;
     p.a_atom = (d->C % 64 == 0) ? 64 : 32; p.b_atom = (d->K % 64 == 0) ? 64 : 32;
     const int m_valid = d->C < 128 ? d->C : 128;
-    p.a_atoms = m_valid / p.a_atom; p.b_atoms = BN / p.b_atom;
+    p.a_atoms = (m_valid + p.a_atom - 1) / p.a_atom; p.b_atoms = BN / p.b_atom;
     p.n_mtiles = cdiv(d->C, 128);
-    const int n_ntiles = d->K / BN, tap_groups = ntaps / T;
+    const int n_ntiles = (d->K + BN - 1) / BN, tap_groups = ntaps / T;
     const int units = p.n_mtiles * n_ntiles * tap_groups;
     int splits = (148 * 2 + units - 1) / units;
     if (splits > p.total_tiles) splits = p.total_tiles;

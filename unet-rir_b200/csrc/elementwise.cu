@@ -284,7 +284,7 @@ int channel_sum(const void* x, int dtype, long long npix, int C, int ld, int cof
 __global__ void __launch_bounds__(256)
 ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ yp, long long npair,
                      long long npix, float w_amp, float w_ph, int sigmoid_bwd, float* __restrict__ losses,
-                     float4* __restrict__ grad) {
+                     float4* __restrict__ grad, __nv_bfloat16* __restrict__ grad16, int ld16) {
     const float TWO_PI = 6.283185307179586f;
     float sse = 0.f, pc = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
@@ -302,6 +302,10 @@ ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ y
             g.y = -TWO_PI * w_ph * s0; g.w = -TWO_PI * w_ph * s1;
             if (sigmoid_bwd) { g.x *= p.x * (1.f - p.x); g.y *= p.y * (1.f - p.y); g.z *= p.z * (1.f - p.z); g.w *= p.w * (1.f - p.w); }
             grad[i] = g;
+            if (grad16) {       // bf16 copy, `ld16` elements per pixel (only the first two are written)
+                *reinterpret_cast<uint32_t*>(grad16 + (2 * i) * ld16) = pack_bf16x2(g.x, g.y);
+                *reinterpret_cast<uint32_t*>(grad16 + (2 * i + 1) * ld16) = pack_bf16x2(g.z, g.w);
+            }
         }
     }
     __shared__ float r1[8], r2[8];
@@ -319,12 +323,14 @@ ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ y
 }
 
 int ampphase_loss(const float* yt, const float* yp, long long npix, float w_amp, float w_ph, int sigmoid_bwd,
-                  float* losses, float* grad, cudaStream_t st) {
+                  float* losses, float* grad, void* grad16, int ld16, cudaStream_t st) {
     URIR_CHECK_ARG(npix > 0 && npix % 2 == 0, "ampphase_loss: npix must be even");
+    URIR_CHECK_ARG(!grad16 || (grad && ld16 >= 2 && ld16 % 2 == 0), "ampphase_loss: grad16 needs grad and an even pitch >= 2");
     URIR_CUDA_OK(cudaMemsetAsync(losses, 0, 4 * sizeof(float), st));
     const long long npair = npix / 2;
     ampphase_loss_kernel<<<grid_for(npair, 256), 256, 0, st>>>((const float4*)yt, (const float4*)yp, npair, npix,
-                                                               w_amp, w_ph, sigmoid_bwd, losses, (float4*)grad);
+                                                               w_amp, w_ph, sigmoid_bwd, losses, (float4*)grad,
+                                                               (__nv_bfloat16*)grad16, ld16);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
