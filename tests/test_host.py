@@ -1,0 +1,193 @@
+"""CPU suite, part 2: host logic and the C-ABI surface (no device work).
+
+  * liburir.so loads without a GPU and exports every function include/urir.h declares;
+  * ConvDesc / StftDesc ctypes layouts match the C structs;
+  * plan / parameter inventory, optimizer-name matching, LR schedules, batch contract, bucket ranges;
+  * world-size-2 gloo run of the data-parallel arithmetic (sharding, bucketed SUM all-reduce, loss
+    scaling, per-replica BatchNorm) against a single process, using the CPU oracle as the model.
+"""
+import ctypes
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "urir.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(urir_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from unet_rir_b200 import _lib as L
+    lib = L.load()
+    declared = _header_functions()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/urir.h but not exported"
+    assert sorted(L.EXPORTED_SYMBOLS) == declared          # the Python binding covers the whole header
+    assert lib.urir_version() == 100
+    assert L.launch_count(0) >= 0 and L.last_error() == ""
+
+
+def test_ctypes_struct_layouts_match_header():
+    from unet_rir_b200 import _lib as L
+    src = open(os.path.join(ROOT, "include", "urir.h")).read()
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in re.findall(r"int32_t\s+([^;]+);", body):
+            out += [f.strip() for f in decl.split(",")]
+        return out
+
+    assert [f for f, _ in L.ConvDesc._fields_] == fields("urir_conv_desc")
+    assert [f for f, _ in L.StftDesc._fields_] == fields("urir_stft_desc")
+    assert ctypes.sizeof(L.ConvDesc) == 4 * len(L.ConvDesc._fields_)
+
+
+def test_bad_arguments_are_rejected_without_a_device():
+    from unet_rir_b200 import _lib as L
+    lib = L.load()
+    d = L.ConvDesc(1, 8, 8, 32, 32, 3, 3, 3, 1, 1, 8, 8, 32, 0, 32, 0, L.BF16, L.BF16, 0, 0, 0)   # stride 3
+    rc = lib.urir_conv2d_fprop(ctypes.byref(d), 1, 1, 1, None, 1, None, None)
+    assert rc == -1 and "stride" in L.last_error()
+    d.stride = 1
+    d.x_ld = 16                                                                                     # slice > pitch
+    assert lib.urir_conv2d_wgrad(ctypes.byref(d), 1, 1, 1, None) == -1
+    assert lib.urir_conv_path(ctypes.byref(L.ConvDesc(1, 8, 8, 32, 32, 3, 3, 1, 1, 1, 8, 8, 32, 0, 32, 0, 1, 1, 0, 0, 0)), 0) == 1
+    assert lib.urir_conv_path(ctypes.byref(L.ConvDesc(1, 8, 8, 2, 32, 3, 3, 1, 1, 1, 8, 8, 2, 0, 32, 0, 0, 1, 0, 0, 0)), 0) == 0
+    with pytest.raises(L.UrirError):
+        L.check(-1, "probe")
+
+
+def test_trainer_host_logic():
+    from unet_rir_b200.amp_phase_trainer import EarlyStopping, History, ModelCheckpoint, Trainer
+    cbs = [ModelCheckpoint("x", False, 0), EarlyStopping(2)]
+    assert Trainer(0.5, 3, "nadam", cbs, [True, 1], 1e-3, "f").optimizer == "nadam"      # "nadam" contains "adam"
+    assert Trainer(0.5, 3, "my_adam_v2", cbs, [True, 1], 1e-3, "f").optimizer == "adam"
+    assert Trainer(0.5, 3, "sgd", cbs, [True, 1], 1e-3, "f").optimizer == "sgd"
+    with pytest.raises(ValueError):
+        Trainer(0.5, 3, "rmsprop", cbs, [True, 1], 1e-3, "f")
+    t = Trainer(0.5, 4, "adam", cbs, [True, 2], 1e-3, "f")
+    assert t.train_loss_history.shape == (4, 3) and t.train_loss_history.dtype == np.float32
+    assert t.alpha == 0.5 and t.lr_exp_decay is True and t.lr_exp_decay_epoch == 2
+    h = History(2, np.zeros((2, 3)), np.ones((2, 3)))
+    assert h.epochs == 2 and h.train_acc_history is None
+    from unet_rir_b200.main_training import gradient_buckets, lr_schedule, shard_batch
+    assert lr_schedule(5e-7, 10) == 5e-7 and abs(lr_schedule(5e-7, 80) - 5e-7 * 0.9) < 1e-18
+    assert abs(lr_schedule(5e-7, 160) - 5e-7 * 0.81) < 1e-18
+    a = np.arange(16).reshape(8, 2)
+    assert np.array_equal(shard_batch([a], 1, 4)[0], a[2:4])
+
+
+def test_flat_parameter_layout_and_buckets():
+    from unet_rir_b200 import plan as PL
+    from unet_rir_b200.main_training import gradient_buckets
+    plan = PL.layer_plan(kernels=3)
+    off, offsets = 0, {}
+    for name, shape, kind in plan:
+        if kind in PL.TRAINABLE_KINDS:
+            n = int(np.prod(shape)); offsets[name] = (off, n); off = (off + n + 3) // 4 * 4
+    b = gradient_buckets(offsets, off)
+    assert b[0][1] == off and b[0][0] == b[1][1] and b[1][0] == b[2][1] and b[2][0] == 0
+    names0 = [n for n, (o, _) in offsets.items() if b[0][0] <= o < b[0][1]]
+    assert names0[0] == "dec2.up.w" and names0[-1] == "head.b"
+    names1 = [n for n, (o, _) in offsets.items() if b[1][0] <= o < b[1][1]]
+    assert names1 == ["vec.emb", "vec.dense.w", "vec.dense.b", "vec.proj.w", "vec.proj.b"]
+    assert sum(PL.l2_regularised(n) for n in offsets) == 9
+    assert all(o % 4 == 0 for o, _ in offsets.values())            # 16-byte aligned for vector reductions
+
+
+class _FakeDataset:
+    seed = 500
+
+    def __init__(self, n=40):
+        self.index_in = list(range(n)); self.index_out = list(range(n))[::-1]
+        self.amp = np.random.default_rng(0).random((n, 144, 160)).astype(np.float64)
+        self.emb = np.arange(n * 16).reshape(n, 16) % 1999
+
+    def __getitem__(self, i):
+        return self.amp[i], self.amp[i] * 0.5, self.emb[i]
+
+    def return_characteristics(self):
+        return [["Room", "A", "Planar", i, i] for i in range(len(self.index_in))]
+
+
+def test_data_generator_batch_contract():
+    from unet_rir_b200.datageneratorv2 import DataGenerator
+    ds = _FakeDataset(40)
+    tr = DataGenerator(ds, batch_size=4, partition="train", shuffle=False)
+    va = DataGenerator(ds, batch_size=4, partition="val", shuffle=False)
+    te = DataGenerator(ds, batch_size=4, partition="test", shuffle=False, characteristics=True)
+    assert (len(tr), len(va), len(te)) == (28 // 4, 8 // 4, 4 // 4)            # 70 / 20 / 10, remainder dropped
+    spec_in, emb, spec_out = tr[0]
+    assert spec_in.shape == (4, 144, 160, 2) and spec_in.dtype == np.float32
+    assert emb.shape == (4, 2, 16) and emb.dtype == np.int32 and spec_out.shape == (4, 144, 160, 2)
+    i0 = tr.index_in[0]
+    assert np.array_equal(spec_in[0, :, :, 0], ds.amp[i0].astype(np.float32))
+    assert np.array_equal(emb[0, 0], ds.emb[i0]) and np.array_equal(emb[0, 1], ds.emb[tr.index_out[0]])
+    a, b, c = tr.__next__()                                                      # (spec_in, spec_out, emb) order
+    assert np.array_equal(a, spec_in) and np.array_equal(b, spec_out) and np.array_equal(c, emb)
+    assert len(te[0]) == 4 and te[0][3].shape == (4, 5, 2)
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import unet_oracle as O
+from unet_rir_b200.main_training import gradient_buckets, shard_batch, init_distributed
+rank, world, _ = init_distributed(backend="gloo")
+torch.set_num_threads(2)
+om = O.UNetOracle(input_shape=(32, 32, 2), kernels=3, number_filters_0=8)
+params = O.init_params(om.plan, seed=7)
+g = torch.Generator().manual_seed(3)
+B = 4
+x, y = torch.rand(B, 32, 32, 2, generator=g), torch.rand(B, 32, 32, 2, generator=g)
+emb = torch.randint(0, 2000, (B, 2, 16), generator=g)
+names = O.trainable_names(om.plan)
+def flat_grads(xs, ys, es, gb, replicas):
+    st = O.new_opt_state(params, om.plan)
+    _, grads, _ = O.train_step(om, params, st, xs, ys, es, 1e-3, loss_kind="dp", alpha=0.9, global_batch=gb,
+                               num_replicas=replicas, apply=False)
+    offs, off = {}, 0
+    for n in names:
+        offs[n] = (off, grads[n].numel()); off = (off + grads[n].numel() + 3) // 4 * 4
+    flat = torch.zeros(off)
+    for n in names:
+        o, k = offs[n]; flat[o:o + k] = grads[n].flatten()
+    return flat, offs, off
+xs, ys, es = shard_batch([x, y, emb], rank, world)
+flat, offs, n_flat = flat_grads(xs, ys, es, B, world)
+for lo, hi in gradient_buckets({k: v for k, v in offs.items()}, n_flat):     # bucketed SUM all-reduce
+    dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
+if rank == 0:
+    # single process: each shard through its own BatchNorm statistics, gradients summed
+    ref = sum(flat_grads(*shard_batch([x, y, emb], r, world), B, world)[0] for r in range(world))
+    err = float((flat - ref).norm() / ref.norm())
+    full = flat_grads(x, y, emb, B, 1)[0]                                   # different BN statistics: must differ
+    print("DP_ERR", err, float((flat - full).norm() / full.norm()))
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_arithmetic_world2_gloo(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("DP_ERR")][0].split()
+    assert float(line[1]) < 1e-5            # bucketed all-reduce == sum of per-replica gradients
+    assert float(line[2]) > 1e-3            # and is NOT the full-batch-BN gradient (BN is per replica)

@@ -1,0 +1,50 @@
+"""Runs a handful of conv launches at bench shapes (B=64) for ncu / CUDA-event timing.
+usage: python tools/prof_conv.py [which ...]   which in {wgrad_full, wgrad_mid, fprop_full, fprop_deep, dgrad_s2, head_wgrad}"""
+import ctypes as C
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from unet_rir_b200 import _lib as L
+
+CASES = {
+    "wgrad_full": ("wgrad", 64, 144, 160, 32, 32, 3, 1),
+    "wgrad_mid": ("wgrad", 64, 36, 40, 128, 128, 3, 1),
+    "fprop_full": ("fprop", 64, 144, 160, 32, 32, 3, 1),
+    "fprop_full64": ("fprop", 64, 144, 160, 64, 32, 3, 1),
+    "fprop_deep": ("fprop", 64, 9, 10, 512, 512, 3, 1),
+    "fprop_mid": ("fprop", 64, 36, 40, 256, 128, 3, 1),
+    "dgrad_s2": ("dgrad", 64, 144, 160, 32, 64, 3, 2),
+    "head_wgrad": ("wgrad", 64, 144, 160, 32, 2, 6, 1),
+}
+
+
+def run(which, reps=3):
+    op, N, H, W, Cc, K, k, s = CASES[which]
+    P, pt = L.same_pad(H, k, s); Q, pl = L.same_pad(W, k, s)
+    y_ld = 8 if K < 8 else K
+    x = torch.randn(N, H, W, Cc, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(N, P, Q, y_ld, device="cuda").to(torch.bfloat16)
+    w_ck = torch.randn(k * k, Cc, K, device="cuda").to(torch.bfloat16)
+    w_kc = torch.randn(k * k, K, Cc, device="cuda").to(torch.bfloat16)
+    dw = torch.zeros(k, k, Cc, K, device="cuda")
+    d = L.ConvDesc(N, H, W, Cc, K, k, k, s, pt, pl, P, Q, Cc, 0, y_ld, 0, L.BF16, L.BF16, L.IMPL_TC, 0, 0)
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if op == "wgrad":
+            L.call("conv2d_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr())
+        elif op == "fprop":
+            L.call("conv2d_fprop", C.byref(d), x.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, dy.data_ptr(), None)
+        else:
+            L.call("conv2d_dgrad", C.byref(d), dy.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, x.data_ptr(), None)
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    fl = 2.0 * N * P * Q * K * Cc * k * k
+    print(f"{which:14s} {min(ts):8.3f} ms  {fl / (min(ts) * 1e-3) / 1e12:8.1f} TF/s", flush=True)
+
+
+if __name__ == "__main__":
+    for w in (sys.argv[1:] or list(CASES)):
+        run(w)
