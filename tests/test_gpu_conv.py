@@ -193,3 +193,19 @@ def test_small_channel_tensor_core_paths():
     dw = torch.empty(1, 1, 16, 64, device="cuda")
     U.run_wgrad(dp, xpg, dyg, dw)
     assert U.rel_l2(dw, gw) < F32_TOL
+
+
+def test_head_dgrad_from_fp32_gradient():
+    """Input-gradient of the K=2 head conv from the fp32 loss gradient (specialised CUDA-core kernel)."""
+    g = torch.Generator().manual_seed(12)
+    for (N, H, W, k) in ((2, 16, 32, 6), (1, 19, 45, 6), (2, 9, 10, 3)):
+        x = U.bf16_round(torch.randn(N, H, W, 32, generator=g)).requires_grad_(True)
+        w = U.bf16_round(torch.randn(k, k, 32, 2, generator=g) * 0.05)
+        dz = torch.randn(N, H, W, 2, generator=g)
+        gx, = torch.autograd.grad(_oracle_fprop(x, w, None, 1), [x], dz)
+        w_ck, w_kc = U.prep_weights(w.cuda())
+        dzg = dz.cuda()
+        dx = torch.empty(N, H, W, 32, dtype=torch.bfloat16, device="cuda")
+        d = U.conv_desc(N, H, W, 32, 2, k, 1, y_dtype=L.F32)
+        U.run_dgrad(d, dzg, w_ck, w_kc, None, dx)
+        assert U.rel_l2(dx.float(), gx) < BF16_TOL, (N, H, W, k)

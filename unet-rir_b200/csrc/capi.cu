@@ -22,7 +22,7 @@ void count_launch(int kind) { g_launches_all++; if (kind == 1) g_launches_tc++; 
 
 // implemented in the other translation units
 int conv_fprop_simt_dispatch(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
-int conv_dgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
+int conv_dgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t, const void*);
 int conv_wgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int weight_prep(const float*, void*, void*, int, int, int, cudaStream_t);
 bool igemm_fprop_supported(const urir_conv_desc*);
@@ -104,7 +104,7 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
     const bool tc_ok = igemm_dgrad_supported(d) && w_ck != nullptr;
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
-    return use_tc ? conv_dgrad_igemm(d, dy, w_ck, bias, dx, stats, st) : conv_dgrad_simt_dispatch(d, dy, w_kc, bias, dx, stats, st);
+    return use_tc ? conv_dgrad_igemm(d, dy, w_ck, bias, dx, stats, st) : conv_dgrad_simt_dispatch(d, dy, w_kc, bias, dx, stats, st, w_ck);
 }
 
 int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {

@@ -246,9 +246,13 @@ int conv_fprop_simt_dispatch(const urir_conv_desc* d, const void* x, const void*
     return launch_fprop<float, float>(p, x, w_ck, bias, y, stats, st);
 }
 
+bool head_dgrad_supported(const urir_conv_desc* d, const float* bias, const float* stats);
+int head_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck, void* dx, cudaStream_t st);
+
 int conv_dgrad_simt_dispatch(const urir_conv_desc* d, const void* dy, const void* w_kc, const float* bias,
-                             void* dx, float* stats, cudaStream_t st) {
+                             void* dx, float* stats, cudaStream_t st, const void* w_ck) {
     ConvP p = to_p(d);
+    if (w_ck && head_dgrad_supported(d, bias, stats)) return head_dgrad(d, dy, w_ck, dx, st);
     URIR_CHECK_ARG(w_kc != nullptr, "dgrad(SIMT) needs w_kc");
     if (d->y_dtype == URIR_F32 && d->x_dtype == URIR_BF16) return launch_dgrad<float, __nv_bfloat16>(p, dy, w_kc, bias, dx, stats, st);
     if (d->y_dtype == URIR_BF16 && d->x_dtype == URIR_BF16) return launch_dgrad<__nv_bfloat16, __nv_bfloat16>(p, dy, w_kc, bias, dx, stats, st);

@@ -28,8 +28,12 @@ struct WgradParams {
     int tiles_w, tiles_h, tiles_n;  // pixel tiles over (Q, P, N)
     int tiles_per_cta, total_tiles;
     int C, K;                       // channels of x and dy
-    int a_atom, b_atom;             // channels per TMA box / swizzle atom: 64 (128B) or 32 (64B)
-    int a_atoms, b_atoms;           // valid atoms per operand tile (<= 2 for A, BLOCK_N/b_atom for B)
+    int a_atom, b_atom;             // channels per TMA box / swizzle atom: 64 (128B rows) or 32 (64B rows)
+    int a_atoms, b_atoms;           // atoms per tap tile of A (<= 2), atoms of the B tile (BLOCK_N / b_atom)
+    int T;                          // taps per CTA (1 or 3)
+    int apm, n_mma;                 // A atoms consumed per MMA (128 / a_atom); accumulators per CTA
+    int stages, stage_bytes, a_region_bytes;
+    int tmem_cols;
     int ntaps, n_mtiles;
     float* dw;
     WgradTap taps[36];
@@ -38,41 +42,37 @@ struct WgradParams {
 struct WgradMaps { CUtensorMap a[4]; CUtensorMap b; };
 
 constexpr int WG_KP = 64;                    // max pixels per stage
-constexpr int WG_A_BYTES = WG_KP * 256;      // 128 channels x 64 pixels x 2 B
-template <int BLOCK_N, int T, int STAGES>
-struct WgradSmem {
-    static constexpr int B_BYTES = WG_KP * BLOCK_N * 2;
-    static constexpr int STAGE_BYTES = T * WG_A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
-};
+constexpr int WG_MAX_STAGES = 8;
+constexpr int WG_SMEM_BUDGET = 200 * 1024;
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BLOCK_N, int T, int STAGES>
+// Shared memory of one stage: [A atoms: T taps x a_atoms, each kp rows x (a_atom*2) bytes, contiguous]
+// [padding up to n_mma*apm atoms][B atoms]. One tcgen05.mma consumes `apm` consecutive A atoms as its
+// M = 128 rows (leading-byte-offset = atom size), so for C = 32 three taps share one MMA and for C = 64
+// two do: the tensor pipe reads the same 4 KB of A per instruction whatever N is, so stacking taps
+// along M is what keeps it busy on the thin layers.
+template <int BLOCK_N>
 __global__ void __launch_bounds__(192)
 conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ WgradParams p) {
-    using L = WgradSmem<BLOCK_N, T, STAGES>;
-    constexpr uint32_t TMEM_COLS = (T * BLOCK_N <= 32) ? 32 : (T * BLOCK_N <= 64) ? 64 : (T * BLOCK_N <= 128) ? 128
-                                 : (T * BLOCK_N <= 256) ? 256 : 512;
-    static_assert(T * BLOCK_N <= 512, "accumulators exceed TMEM");
     constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N, 1, 1);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+    uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + WG_MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.y % p.n_mtiles, n_tile = blockIdx.y / p.n_mtiles;
-    const int tap0 = blockIdx.z * T;
+    const int tap0 = blockIdx.z * p.T;
     const int tile_begin = blockIdx.x * p.tiles_per_cta;
     int tile_end = tile_begin + p.tiles_per_cta; if (tile_end > p.total_tiles) tile_end = p.total_tiles;
     const int n_iters = tile_end > tile_begin ? tile_end - tile_begin : 0;
+    const int STAGES = p.stages;
 
     const uint32_t a_row = p.a_atom * 2, b_row = p.b_atom * 2;         // bytes per smem row
     const uint32_t a_swz = p.a_atom == 64 ? SWZ_128B : SWZ_64B, b_swz = p.b_atom == 64 ? SWZ_128B : SWZ_64B;
@@ -83,7 +83,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
     if (warp == 4 && lane == 0) { prefetch_tmap(&maps.b); prefetch_tmap(&maps.a[0]); }
     fence_before_sync();
     __syncthreads();
@@ -93,7 +93,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
     if (warp == 4) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)T * p.a_atoms * a_atom_bytes + (uint32_t)p.b_atoms * b_atom_bytes;
+            const uint32_t bytes = (uint32_t)p.T * p.a_atoms * a_atom_bytes + (uint32_t)p.b_atoms * b_atom_bytes;
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < n_iters; ++it) {
                 int t = tile_begin + it;
@@ -101,39 +101,36 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 const int w0 = tw * p.bw, h0 = th * p.bh, n0 = t * p.bn;
                 mbar_wait(empty_bar + stage, phase ^ 1);
-                uint8_t* st_base = smem + stage * L::STAGE_BYTES;
+                uint8_t* st_base = smem + stage * p.stage_bytes;
                 mbar_expect_tx(full_bar + stage, bytes);
-#pragma unroll
-                for (int ti = 0; ti < T; ++ti) {
+                for (int ti = 0; ti < p.T; ++ti) {
                     const WgradTap tp = p.taps[tap0 + ti];
                     for (int a = 0; a < p.a_atoms; ++a)
-                        tma_load_4d(&maps.a[tp.map], full_bar + stage, st_base + ti * WG_A_BYTES + a * a_atom_bytes,
+                        tma_load_4d(&maps.a[tp.map], full_bar + stage, st_base + (ti * p.a_atoms + a) * a_atom_bytes,
                                     m_tile * 128 + a * p.a_atom, w0 + tp.dw, h0 + tp.dh, n0);
                 }
                 for (int b = 0; b < p.b_atoms; ++b)
-                    tma_load_4d(&maps.b, full_bar + stage, st_base + T * WG_A_BYTES + b * b_atom_bytes,
+                    tma_load_4d(&maps.b, full_bar + stage, st_base + p.a_region_bytes + b * b_atom_bytes,
                                 n_tile * BLOCK_N + b * p.b_atom, w0, h0, n0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        const uint32_t a_lbo = p.a_atoms > 1 ? a_atom_bytes : 0;     // single valid atom: alias it (rows >= C are discarded)
-        const uint32_t b_lbo = b_atom_bytes;
         const int ksteps = p.kp / 16;
         int stage = 0; uint32_t phase = 0;
         for (int it = 0; it < n_iters; ++it) {
             mbar_wait(full_bar + stage, phase);
             fence_after_sync();
             if (lane == 0) {
-                const uint32_t s_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-                const uint32_t b_addr = s_addr + T * WG_A_BYTES;
+                const uint32_t s_addr = smem_u32(smem + stage * p.stage_bytes);
+                const uint32_t b_addr = s_addr + p.a_region_bytes;
                 for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t bd = make_smem_desc(b_addr + k * 16 * b_row, b_lbo, 8 * b_row, b_swz);
-#pragma unroll
-                    for (int ti = 0; ti < T; ++ti) {
-                        const uint64_t ad = make_smem_desc(s_addr + ti * WG_A_BYTES + k * 16 * a_row, a_lbo, 8 * a_row, a_swz);
-                        umma_bf16(tmem_base + ti * BLOCK_N, ad, bd, IDESC, (it | k) != 0);
+                    const uint64_t bd = make_smem_desc(b_addr + k * 16 * b_row, b_atom_bytes, 8 * b_row, b_swz);
+                    for (int j = 0; j < p.n_mma; ++j) {
+                        const uint64_t ad = make_smem_desc(s_addr + j * p.apm * a_atom_bytes + k * 16 * a_row,
+                                                           a_atom_bytes, 8 * a_row, a_swz);
+                        umma_bf16(tmem_base + j * BLOCK_N, ad, bd, IDESC, (it | k) != 0);
                     }
                 }
                 umma_commit(empty_bar + stage);
@@ -147,29 +144,32 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
         if (n_iters > 0) {
             mbar_wait(tmem_full_bar, 0);
             fence_after_sync();
-            const int c = m_tile * 128 + warp * 32 + lane;
-            const bool valid = c < p.C;
+            const int row = warp * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-            for (int ti = 0; ti < T; ++ti) {
-                const int wtap = p.taps[tap0 + ti].wtap;
+            for (int j = 0; j < p.n_mma; ++j) {
+                const int g = j * p.apm + row / p.a_atom;                  // A atom this accumulator row came from
+                const int ti = g / p.a_atoms;
+                const int c = m_tile * 128 + (g % p.a_atoms) * p.a_atom + row % p.a_atom;
+                const bool valid = ti < p.T && c < p.C;
+                const int wtap = p.taps[tap0 + (valid ? ti : 0)].wtap;
                 float* drow = p.dw + ((size_t)wtap * p.C + (valid ? c : 0)) * p.K + n_tile * BLOCK_N;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
                     uint32_t r[16];
-                    tmem_ld16(lane_addr + ti * BLOCK_N + c0, r);
+                    tmem_ld16(lane_addr + j * BLOCK_N + c0, r);
                     tmem_ld_wait();
                     if (valid) {
                         const int n_left = p.K - n_tile * BLOCK_N - c0;      // valid columns from c0 on
                         if (n_left >= 16 && (p.K & 3) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4)
-                                red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                            for (int q = 0; q < 16; q += 4)
+                                red_add_v4(drow + c0 + q, __uint_as_float(r[q]), __uint_as_float(r[q + 1]),
+                                           __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (j < n_left) atomicAdd(drow + c0 + j, __uint_as_float(r[j]));
+                            for (int q = 0; q < 16; ++q)
+                                if (q < n_left) atomicAdd(drow + c0 + q, __uint_as_float(r[q]));
                         }
                     }
                 }
@@ -178,7 +178,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
         }
     }
     __syncthreads();
-    if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,16 +201,15 @@ static void choose_kbox(int OW, int OH, int NB, int* bw, int* bh, int* bn) {
     *bw = bbw; *bh = bbh; *bn = bbn;
 }
 
-template <int BLOCK_N, int T, int STAGES>
-static int launch_wg(const WgradMaps& maps, const WgradParams& p, dim3 grid, cudaStream_t st) {
-    using L = WgradSmem<BLOCK_N, T, STAGES>;
+template <int BLOCK_N>
+static int launch_wg(const WgradMaps& maps, const WgradParams& p, dim3 grid, int smem_bytes, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = conv_wgrad_tc_kernel<BLOCK_N, T, STAGES>;
+    auto kern = conv_wgrad_tc_kernel<BLOCK_N>;
     if (!attr_set) {
-        URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BUDGET + 4096));
         attr_set = true;
     }
-    kern<<<grid, 192, L::TOTAL, st>>>(maps, p);
+    kern<<<grid, 192, smem_bytes, st>>>(maps, p);
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }
@@ -234,11 +233,22 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
     p.kp = p.bw * p.bh * p.bn;
     p.tiles_w = cdiv(d->Q, p.bw); p.tiles_h = cdiv(d->P, p.bh); p.tiles_n = cdiv(d->N, p.bn);
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    p.C = d->C; p.K = d->K; p.ntaps = ntaps; p.dw = dw;
+    p.C = d->C; p.K = d->K; p.ntaps = ntaps; p.dw = dw; p.T = T;
     p.a_atom = (d->C % 64 == 0) ? 64 : 32; p.b_atom = (d->K % 64 == 0) ? 64 : 32;
     const int m_valid = d->C < 128 ? d->C : 128;
     p.a_atoms = (m_valid + p.a_atom - 1) / p.a_atom; p.b_atoms = BN / p.b_atom;
     p.n_mtiles = cdiv(d->C, 128);
+    p.apm = 128 / p.a_atom;
+    p.n_mma = cdiv(T * p.a_atoms, p.apm);
+    const int a_atom_bytes = p.kp * p.a_atom * 2, b_atom_bytes = p.kp * p.b_atom * 2;
+    p.a_region_bytes = p.n_mma * p.apm * a_atom_bytes;            // includes the unused tail atoms of the last MMA
+    p.stage_bytes = p.a_region_bytes + p.b_atoms * b_atom_bytes;
+    p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+    p.stages = WG_SMEM_BUDGET / p.stage_bytes;
+    if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+    if (p.stages < 2) return fail(URIR_ERR_UNSUP, "wgrad(tcgen05): stage of %d bytes does not fit twice", p.stage_bytes);
+    { int cols = p.n_mma * BN; p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512; }
+    const int smem_bytes = p.stages * p.stage_bytes + (2 * WG_MAX_STAGES + 2) * 8 + 16 + 1024;
     const int n_ntiles = (d->K + BN - 1) / BN, tap_groups = ntaps / T;
     const int units = p.n_mtiles * n_ntiles * tap_groups;
     int splits = (148 * 2 + units - 1) / units;
@@ -282,10 +292,9 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
     }
     URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps * d->C * d->K, st));
     dim3 grid(splits, p.n_mtiles * n_ntiles, tap_groups);
-#define URIR_WG(BNv, Tv, STv) if (BN == BNv && T == Tv) return launch_wg<BNv, Tv, STv>(maps, p, grid, st);
-    URIR_WG(128, 3, 3) URIR_WG(64, 3, 3) URIR_WG(32, 3, 3)
-    URIR_WG(128, 1, 4) URIR_WG(64, 1, 4) URIR_WG(32, 1, 4)
-#undef URIR_WG
+    if (BN == 128) return launch_wg<128>(maps, p, grid, smem_bytes, st);
+    if (BN == 64) return launch_wg<64>(maps, p, grid, smem_bytes, st);
+    if (BN == 32) return launch_wg<32>(maps, p, grid, smem_bytes, st);
     return fail(URIR_ERR_UNSUP, "wgrad(tcgen05): no kernel for BLOCK_N=%d T=%d", BN, T);
 }
 
