@@ -131,16 +131,20 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
         if (lane == 0) {
             const uint32_t a_bytes = (uint32_t)(p.bw * p.bh * p.bn) * ROW_BYTES;
             int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < total_iters; ++it) {
-                const int ti = it / p.kchunks, kc = it - ti * p.kchunks;
+            uint8_t* a_dst = smem;
+            const int b_n0 = n_tile * BLOCK_N;
+            for (int ti = 0; ti < (tile_live ? ntaps : 0); ++ti) {
                 const IgemmTap tp = p.taps[tap0 + ti];
-                mbar_wait(empty_bar + stage, phase ^ 1);
-                uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + L::A_BYTES;
-                mbar_expect_tx(full_bar + stage, a_bytes + L::B_BYTES);
-                tma_load_4d(&maps.a[tp.map], full_bar + stage, a_dst, kc * BLOCK_K, w0 + tp.dw, h0 + tp.dh, n0);
-                tma_load_3d(&maps.b, full_bar + stage, b_dst, kc * BLOCK_K, n_tile * BLOCK_N, tp.wtap);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                const CUtensorMap* am = &maps.a[tp.map];
+                const int cw = w0 + tp.dw, ch = h0 + tp.dh, wt = tp.wtap;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    mbar_expect_tx(full_bar + stage, a_bytes + L::B_BYTES);
+                    tma_load_4d(am, full_bar + stage, a_dst, kc * BLOCK_K, cw, ch, n0);
+                    tma_load_3d(&maps.b, full_bar + stage, a_dst + L::A_BYTES, kc * BLOCK_K, b_n0, wt);
+                    a_dst += L::STAGE_BYTES;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; a_dst = smem; }
+                }
             }
         }
     } else if (warp == 5) {

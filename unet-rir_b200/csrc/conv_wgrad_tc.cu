@@ -92,52 +92,87 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
 
     if (warp == 4) {
         // ===================== TMA producer =====================
+        // Everything per-iteration is incremental (no divisions, no parameter-table reads in the loop):
+        // the single issuing thread must stay well under the ~45 cycles one MMA takes.
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)p.T * p.a_atoms * a_atom_bytes + (uint32_t)p.b_atoms * b_atom_bytes;
+            const CUtensorMap* tmap[3]; int tdw[3], tdh[3];
+#pragma unroll
+            for (int ti = 0; ti < 3; ++ti) {
+                const WgradTap tp = p.taps[tap0 + (ti < p.T ? ti : 0)];
+                tmap[ti] = &maps.a[tp.map]; tdw[ti] = tp.dw; tdh[ti] = tp.dh;
+            }
+            int t = tile_begin;
+            int tw = t % p.tiles_w; t /= p.tiles_w;
+            int th = t % p.tiles_h; int tn = t / p.tiles_h;
+            const int a_c0 = m_tile * 128, b_c0 = n_tile * BLOCK_N;
             int stage = 0; uint32_t phase = 0;
+            uint8_t* st_base = smem;
             for (int it = 0; it < n_iters; ++it) {
-                int t = tile_begin + it;
-                const int tw = t % p.tiles_w; t /= p.tiles_w;
-                const int th = t % p.tiles_h; t /= p.tiles_h;
-                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = t * p.bn;
+                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
                 mbar_wait(empty_bar + stage, phase ^ 1);
-                uint8_t* st_base = smem + stage * p.stage_bytes;
                 mbar_expect_tx(full_bar + stage, bytes);
-                for (int ti = 0; ti < p.T; ++ti) {
-                    const WgradTap tp = p.taps[tap0 + ti];
-                    for (int a = 0; a < p.a_atoms; ++a)
-                        tma_load_4d(&maps.a[tp.map], full_bar + stage, st_base + (ti * p.a_atoms + a) * a_atom_bytes,
-                                    m_tile * 128 + a * p.a_atom, w0 + tp.dw, h0 + tp.dh, n0);
+                uint8_t* dst = st_base;
+#pragma unroll
+                for (int ti = 0; ti < 3; ++ti) {
+                    if (ti < p.T) {
+                        tma_load_4d(tmap[ti], full_bar + stage, dst, a_c0, w0 + tdw[ti], h0 + tdh[ti], n0);
+                        dst += a_atom_bytes;
+                        if (p.a_atoms > 1) {
+                            tma_load_4d(tmap[ti], full_bar + stage, dst, a_c0 + p.a_atom, w0 + tdw[ti], h0 + tdh[ti], n0);
+                            dst += a_atom_bytes;
+                        }
+                    }
                 }
-                for (int b = 0; b < p.b_atoms; ++b)
-                    tma_load_4d(&maps.b, full_bar + stage, st_base + p.a_region_bytes + b * b_atom_bytes,
-                                n_tile * BLOCK_N + b * p.b_atom, w0, h0, n0);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                dst = st_base + p.a_region_bytes;
+                tma_load_4d(&maps.b, full_bar + stage, dst, b_c0, w0, h0, n0);
+                if (p.b_atoms > 1) tma_load_4d(&maps.b, full_bar + stage, dst + b_atom_bytes, b_c0 + p.b_atom, w0, h0, n0);
+                if (p.b_atoms > 2) {
+                    tma_load_4d(&maps.b, full_bar + stage, dst + 2 * b_atom_bytes, b_c0 + 2 * p.b_atom, w0, h0, n0);
+                    tma_load_4d(&maps.b, full_bar + stage, dst + 3 * b_atom_bytes, b_c0 + 3 * p.b_atom, w0, h0, n0);
+                }
+                if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
+                st_base += p.stage_bytes;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; st_base = smem; }
             }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
+        // Descriptors: high word (SBO | version | swizzle) and the LBO half of the low word are loop
+        // invariants; per MMA only the 14-bit start-address field changes (base + precomputed offset).
         const int ksteps = p.kp / 16;
+        const uint32_t a_hi = ((8 * a_row) >> 4) | (1u << 14) | (a_swz << 29);
+        const uint32_t b_hi = ((8 * b_row) >> 4) | (1u << 14) | (b_swz << 29);
+        const uint32_t a_lo0 = ((a_atom_bytes >> 4) << 16) | (smem_u32(smem) >> 4);
+        const uint32_t b_lo0 = ((b_atom_bytes >> 4) << 16) | ((smem_u32(smem) + p.a_region_bytes) >> 4);
+        const uint32_t stage16 = p.stage_bytes >> 4;
+        const uint32_t a_k16 = (16 * a_row) >> 4, b_k16 = (16 * b_row) >> 4, a_j16 = (p.apm * a_atom_bytes) >> 4;
         int stage = 0; uint32_t phase = 0;
+        uint32_t soff = 0;
         for (int it = 0; it < n_iters; ++it) {
             mbar_wait(full_bar + stage, phase);
             fence_after_sync();
             if (lane == 0) {
-                const uint32_t s_addr = smem_u32(smem + stage * p.stage_bytes);
-                const uint32_t b_addr = s_addr + p.a_region_bytes;
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t bd = make_smem_desc(b_addr + k * 16 * b_row, b_atom_bytes, 8 * b_row, b_swz);
-                    for (int j = 0; j < p.n_mma; ++j) {
-                        const uint64_t ad = make_smem_desc(s_addr + j * p.apm * a_atom_bytes + k * 16 * a_row,
-                                                           a_atom_bytes, 8 * a_row, a_swz);
-                        umma_bf16(tmem_base + j * BLOCK_N, ad, bd, IDESC, (it | k) != 0);
+                const uint32_t acc = it != 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < ksteps) {
+                        const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + soff + k * b_k16);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            if (j < p.n_mma) {
+                                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + soff + k * a_k16 + j * a_j16);
+                                umma_bf16(tmem_base + j * BLOCK_N, ad, bd, IDESC, acc | (k != 0));
+                            }
+                        }
                     }
                 }
                 umma_commit(empty_bar + stage);
                 if (it == n_iters - 1) umma_commit(tmem_full_bar);
             }
             __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            soff += stage16;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; soff = 0; }
         }
     } else if (warp < 4) {
         // ===================== epilogue: TMEM -> red.global.add into dw =====================
