@@ -2,10 +2,14 @@
 the CUDA-core cross-check) against the fp32 CPU oracle on identical weights, inputs and dropout mask.
 
 Tolerances (bf16 activations and GEMM operands vs the oracle's fp32; TF itself would run these convs
-in TF32): per-layer activations rel-L2 <= 3e-2, sigmoid output abs <= 1e-2 and rel-L2
-<= 5e-3, losses rel 2e-3, gradients rel-L2 <= 5e-2 per tensor (biases of BN-followed convs, whose true
-gradient is analytically zero, are checked in absolute terms). tcgen05 vs CUDA-core engine runs, which
-share the arithmetic contract, must agree to 3e-3."""
+in TF32): per-layer activations rel-L2 <= 3e-2, sigmoid output abs <= 1e-2 (eval) and
+rel-L2 <= 5e-3 (eval) / 1.5e-2 (batch-stat BN on a batch of 2), losses rel 2e-3.
+Gradients are compared per tensor, rel-L2 <= 4e-2, with the oracle evaluated under the device path's
+storage contract (UNetOracle(emulate_bf16=True): operands and stored activations rounded to bf16, fp32
+accumulation). Reason, measured on the CPU alone: between the pure-fp32 and the bf16-storage evaluation
+of the SAME graph ~0.3 % of the ReLU gates flip, each ReLU layer adds ~5 % rel-L2 of unbiased gradient
+noise, and the deepest tensors differ by ~30 % -- a property of bf16 storage, not of an implementation.
+Biases of BN-followed convs (true gradient analytically zero) are checked in absolute terms."""
 import pytest
 import torch
 
@@ -50,8 +54,10 @@ def test_train_forward_backward_matches_oracle():
     om, params, x, y, emb, mask = _setup(B=2, kernels=3)
     om.taps = {}
     st = O.new_opt_state(params, om.plan)
-    (loss, lp, ls), grads, ref_out = O.train_step(om, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    (loss, lp, ls), _, ref_out = O.train_step(om, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
     taps = {k: v.detach() for k, v in om.taps.items()}
+    oq = O.UNetOracle(kernels=3, emulate_bf16=True)
+    _, grads, _ = O.train_step(oq, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
 
     results = {}
     for impl in (L.IMPL_SIMT, L.IMPL_AUTO):
@@ -79,7 +85,7 @@ def test_train_forward_backward_matches_oracle():
             if is_dead_bias:      # true gradient is 0 (BatchNorm removes the mean); only rounding noise
                 ok = U.max_abs(got, ref) < 2e-3
             else:
-                ok = U.rel_l2(got, ref) < 5e-2 or U.max_abs(got, ref) < 1e-6 + 1e-3 * scale
+                ok = U.rel_l2(got, ref) < 4e-2 or U.max_abs(got, ref) < 1e-7 + 1e-3 * scale
             if not ok:
                 bad.append((name, U.rel_l2(got, ref), U.max_abs(got, ref), scale))
         assert not bad, (impl, bad)
@@ -102,7 +108,8 @@ def test_adam_step_moves_parameters_like_oracle():
     st = O.new_opt_state(params, om.plan)
     p0 = {k: v.clone() for k, v in params.items()}
     lr = 1e-3
-    _, ref_grads, _ = O.train_step(om, params, st, x, y, emb, lr, dropout_mask=mask, apply=True)
+    oq = O.UNetOracle(kernels=3, emulate_bf16=True)
+    _, ref_grads, _ = O.train_step(oq, params, st, x, y, emb, lr, dropout_mask=mask, apply=True)
     eng.set_lr(lr)
     eng.forward(x.cuda(), emb.cuda(), training=True, dropout_mask=mask.cuda())
     n = 2 * 144 * 160

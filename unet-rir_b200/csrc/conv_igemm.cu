@@ -94,7 +94,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     float* sstats = reinterpret_cast<float*>(smem + L::STAT_OFF);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
 
     // tile coordinates
     int t = blockIdx.x;
@@ -128,20 +128,21 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
 
     if (warp == 4) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        {   // warp-convergent: one elected lane issues, operands stay in uniform registers
             const uint32_t a_bytes = (uint32_t)(p.bw * p.bh * p.bn) * ROW_BYTES;
             int stage = 0; uint32_t phase = 0;
             uint8_t* a_dst = smem;
             const int b_n0 = n_tile * BLOCK_N;
             for (int ti = 0; ti < (tile_live ? ntaps : 0); ++ti) {
                 const IgemmTap tp = p.taps[tap0 + ti];
-                const CUtensorMap* am = &maps.a[tp.map];
-                const int cw = w0 + tp.dw, ch = h0 + tp.dh, wt = tp.wtap;
+                const CUtensorMap* am = &maps.a[__shfl_sync(0xffffffffu, (int)tp.map, 0)];
+                const int cw = w0 + __shfl_sync(0xffffffffu, (int)tp.dw, 0), ch = h0 + __shfl_sync(0xffffffffu, (int)tp.dh, 0);
+                const int wt = __shfl_sync(0xffffffffu, (int)tp.wtap, 0);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
-                    mbar_expect_tx(full_bar + stage, a_bytes + L::B_BYTES);
-                    tma_load_4d(am, full_bar + stage, a_dst, kc * BLOCK_K, cw, ch, n0);
-                    tma_load_3d(&maps.b, full_bar + stage, a_dst + L::A_BYTES, kc * BLOCK_K, b_n0, wt);
+                    mbar_expect_tx_elect(full_bar + stage, a_bytes + L::B_BYTES);
+                    tma_load_4d_elect(am, full_bar + stage, a_dst, kc * BLOCK_K, cw, ch, n0);
+                    tma_load_3d_elect(&maps.b, full_bar + stage, a_dst + L::A_BYTES, kc * BLOCK_K, b_n0, wt);
                     a_dst += L::STAGE_BYTES;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; a_dst = smem; }
                 }
@@ -150,23 +151,23 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         int stage = 0; uint32_t phase = 0;
+        const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t d_hi = (SBO >> 4) | (1u << 14) | (SWZ << 29);      // SBO | sm100 version | swizzle
+        uint32_t a_lo = smem_u32(smem) >> 4;
         for (int it = 0; it < total_iters; ++it) {
             mbar_wait(full_bar + stage, phase);
             fence_after_sync();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k) {
-                    const uint64_t ad = make_smem_desc(a_addr + k * 32, 0, SBO, SWZ);
-                    const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, SBO, SWZ);
-                    umma_bf16(tmem_base, ad, bd, IDESC, (it | k) != 0);
-                }
-                umma_commit(empty_bar + stage);
-                if (it == total_iters - 1) umma_commit(tmem_full_bar);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                const uint64_t ad = ((uint64_t)d_hi << 32) | (a_lo + 2 * k);
+                const uint64_t bd = ((uint64_t)d_hi << 32) | (a_lo + (L::A_BYTES >> 4) + 2 * k);
+                umma_bf16_elect(tm0, ad, bd, IDESC, (it | k) != 0);
             }
+            umma_commit_elect(empty_bar + stage);
+            if (it == total_iters - 1) umma_commit_elect(tmem_full_bar);
             __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            a_lo += L::STAGE_BYTES >> 4;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; a_lo = smem_u32(smem) >> 4; }
         }
     } else if (warp < 4) {
         // ===================== epilogue =====================

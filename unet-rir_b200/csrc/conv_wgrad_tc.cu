@@ -11,6 +11,7 @@
 // A CTA owns (tap group of T taps, 128-channel c tile, BLOCK_N k tile) and a contiguous range of
 // pixel tiles (split-K); T accumulators of BLOCK_N columns live in TMEM; the epilogue adds them
 // into dw with vectorised global reductions.
+#include <stdlib.h>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -36,6 +37,7 @@ struct WgradParams {
     int tmem_cols;
     int ntaps, n_mtiles;
     float* dw;
+    long long* trace;               // debug: per-iteration clock64 stamps of CTA (0,0,0) when non-null
     WgradTap taps[36];
 };
 
@@ -66,7 +68,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
     uint64_t* tmem_full_bar = empty_bar + WG_MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
     const int m_tile = blockIdx.y % p.n_mtiles, n_tile = blockIdx.y / p.n_mtiles;
     const int tap0 = blockIdx.z * p.T;
     const int tile_begin = blockIdx.x * p.tiles_per_cta;
@@ -94,13 +96,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
         // ===================== TMA producer =====================
         // Everything per-iteration is incremental (no divisions, no parameter-table reads in the loop):
         // the single issuing thread must stay well under the ~45 cycles one MMA takes.
-        if (lane == 0) {
+        {
             const uint32_t bytes = (uint32_t)p.T * p.a_atoms * a_atom_bytes + (uint32_t)p.b_atoms * b_atom_bytes;
             const CUtensorMap* tmap[3]; int tdw[3], tdh[3];
 #pragma unroll
             for (int ti = 0; ti < 3; ++ti) {
                 const WgradTap tp = p.taps[tap0 + (ti < p.T ? ti : 0)];
-                tmap[ti] = &maps.a[tp.map]; tdw[ti] = tp.dw; tdh[ti] = tp.dh;
+                // shuffles tell the compiler these are warp-uniform, so the TMA operands stay in uniform registers
+                tmap[ti] = &maps.a[__shfl_sync(0xffffffffu, (int)tp.map, 0)];
+                tdw[ti] = __shfl_sync(0xffffffffu, (int)tp.dw, 0); tdh[ti] = __shfl_sync(0xffffffffu, (int)tp.dh, 0);
             }
             int t = tile_begin;
             int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -110,26 +114,29 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
             uint8_t* st_base = smem;
             for (int it = 0; it < n_iters; ++it) {
                 const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+                const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 256 && lane == 0;
+                if (tr) p.trace[it * 4 + 0] = clock64();
                 mbar_wait(empty_bar + stage, phase ^ 1);
-                mbar_expect_tx(full_bar + stage, bytes);
+                if (tr) p.trace[it * 4 + 1] = clock64();
+                mbar_expect_tx_elect(full_bar + stage, bytes);
                 uint8_t* dst = st_base;
 #pragma unroll
                 for (int ti = 0; ti < 3; ++ti) {
                     if (ti < p.T) {
-                        tma_load_4d(tmap[ti], full_bar + stage, dst, a_c0, w0 + tdw[ti], h0 + tdh[ti], n0);
+                        tma_load_4d_elect(tmap[ti], full_bar + stage, dst, a_c0, w0 + tdw[ti], h0 + tdh[ti], n0);
                         dst += a_atom_bytes;
                         if (p.a_atoms > 1) {
-                            tma_load_4d(tmap[ti], full_bar + stage, dst, a_c0 + p.a_atom, w0 + tdw[ti], h0 + tdh[ti], n0);
+                            tma_load_4d_elect(tmap[ti], full_bar + stage, dst, a_c0 + p.a_atom, w0 + tdw[ti], h0 + tdh[ti], n0);
                             dst += a_atom_bytes;
                         }
                     }
                 }
                 dst = st_base + p.a_region_bytes;
-                tma_load_4d(&maps.b, full_bar + stage, dst, b_c0, w0, h0, n0);
-                if (p.b_atoms > 1) tma_load_4d(&maps.b, full_bar + stage, dst + b_atom_bytes, b_c0 + p.b_atom, w0, h0, n0);
+                tma_load_4d_elect(&maps.b, full_bar + stage, dst, b_c0, w0, h0, n0);
+                if (p.b_atoms > 1) tma_load_4d_elect(&maps.b, full_bar + stage, dst + b_atom_bytes, b_c0 + p.b_atom, w0, h0, n0);
                 if (p.b_atoms > 2) {
-                    tma_load_4d(&maps.b, full_bar + stage, dst + 2 * b_atom_bytes, b_c0 + 2 * p.b_atom, w0, h0, n0);
-                    tma_load_4d(&maps.b, full_bar + stage, dst + 3 * b_atom_bytes, b_c0 + 3 * p.b_atom, w0, h0, n0);
+                    tma_load_4d_elect(&maps.b, full_bar + stage, dst + 2 * b_atom_bytes, b_c0 + 2 * p.b_atom, w0, h0, n0);
+                    tma_load_4d_elect(&maps.b, full_bar + stage, dst + 3 * b_atom_bytes, b_c0 + 3 * p.b_atom, w0, h0, n0);
                 }
                 if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
                 st_base += p.stage_bytes;
@@ -140,7 +147,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
         // ===================== MMA issuer =====================
         // Descriptors: high word (SBO | version | swizzle) and the LBO half of the low word are loop
         // invariants; per MMA only the 14-bit start-address field changes (base + precomputed offset).
-        const int ksteps = p.kp / 16;
+        const int ksteps = p.kp / 16, n_mma = p.n_mma;
+        const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t a_hi = ((8 * a_row) >> 4) | (1u << 14) | (a_swz << 29);
         const uint32_t b_hi = ((8 * b_row) >> 4) | (1u << 14) | (b_swz << 29);
         const uint32_t a_lo0 = ((a_atom_bytes >> 4) << 16) | (smem_u32(smem) >> 4);
@@ -150,9 +158,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
         int stage = 0; uint32_t phase = 0;
         uint32_t soff = 0;
         for (int it = 0; it < n_iters; ++it) {
+            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 256 && lane == 0;
+            if (tr) p.trace[it * 4 + 2] = clock64();
             mbar_wait(full_bar + stage, phase);
+            if (tr) p.trace[it * 4 + 3] = clock64();
             fence_after_sync();
-            if (lane == 0) {
+            {
                 const uint32_t acc = it != 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -160,15 +171,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
                         const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + soff + k * b_k16);
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
-                            if (j < p.n_mma) {
+                            if (j < n_mma) {
                                 const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + soff + k * a_k16 + j * a_j16);
-                                umma_bf16(tmem_base + j * BLOCK_N, ad, bd, IDESC, acc | (k != 0));
+                                umma_bf16_elect(tm0 + j * BLOCK_N, ad, bd, IDESC, acc | (k != 0));
                             }
                         }
                     }
                 }
-                umma_commit(empty_bar + stage);
-                if (it == n_iters - 1) umma_commit(tmem_full_bar);
+                umma_commit_elect(empty_bar + stage);
+                if (it == n_iters - 1) umma_commit_elect(tmem_full_bar);
             }
             __syncwarp();
             soff += stage16;
@@ -269,6 +280,10 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
     p.tiles_w = cdiv(d->Q, p.bw); p.tiles_h = cdiv(d->P, p.bh); p.tiles_n = cdiv(d->N, p.bn);
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.C = d->C; p.K = d->K; p.ntaps = ntaps; p.dw = dw; p.T = T;
+    {   // URIR_WGRAD_TRACE=<device pointer, hex> : debug timeline of CTA (0,0,0)
+        const char* e = getenv("URIR_WGRAD_TRACE");
+        p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr;
+    }
     p.a_atom = (d->C % 64 == 0) ? 64 : 32; p.b_atom = (d->K % 64 == 0) ? 64 : 32;
     const int m_valid = d->C < 128 ? d->C : 128;
     p.a_atoms = (m_valid + p.a_atom - 1) / p.a_atom; p.b_atoms = BN / p.b_atom;
