@@ -213,6 +213,11 @@ class UNetOracle:
         self.bn_unbiased = bn_moving_var_unbiased
         self.plan = layer_plan(input_shape, inf_vector_shape, mode, number_filters_0, kernels, BatchNorm)
         self.taps = None   # optional dict collecting intermediates for per-layer parity
+        # optional dict name -> tensor: forward VALUES to substitute (straight-through) at every stored
+        # tensor and BatchNorm statistic. With the device path's own forward state plugged in, autograd
+        # back-propagates through exactly the ReLU gates / saved activations the device used, which turns
+        # the (chaotic) end-to-end gradient comparison into a test of the backward kernels alone.
+        self.override = None
 
     # -- layers ---------------------------------------------------------------------
     def _r(self, t):
@@ -220,6 +225,12 @@ class UNetOracle:
         if not self.q:
             return t
         return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+    def _sub(self, name, t):
+        """value substitution with a straight-through gradient"""
+        if self.override is not None and name in self.override:
+            return t + (self.override[name].to(t.dtype) - t).detach()
+        return t
 
     def _tap(self, name, t):
         if self.taps is not None:
@@ -236,6 +247,7 @@ class UNetOracle:
                     xq = self._r(x)
                     mean = mean + (xq.mean(dim=(0, 2, 3)) - xq.mean(dim=(0, 2, 3)).detach())
                     var = var + (xq.var(dim=(0, 2, 3), unbiased=False) - xq.var(dim=(0, 2, 3), unbiased=False).detach())
+                mean, var = self._sub(name + ".mean", mean), self._sub(name + ".var", var)
                 if new_stats is not None:
                     n = x.shape[0] * x.shape[2] * x.shape[3]
                     mv = var * (n / max(n - 1, 1)) if self.bn_unbiased else var
@@ -247,10 +259,14 @@ class UNetOracle:
                 mean, var = p[name + ".moving_mean"], p[name + ".moving_var"]
             inv = torch.rsqrt(var + BN_EPS)
             x = (self._r(x) - mean.view(1, -1, 1, 1)) * (inv * g).view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+        if self.override is not None and (name + ".out") in self.override:
+            # pin the ReLU gates to the substituted output: gradient passes exactly where that output is > 0
+            y = x * (self.override[name + ".out"] > 0).to(x.dtype)
+            return self._sub(name + ".out", y)
         return self._r(F.relu(x))
 
     def _cbr(self, x, p, cname, bname, training, new_stats):
-        x = conv2d_same(x, self._r(p[cname + ".w"]), p[cname + ".b"], 1)
+        x = self._sub(cname, conv2d_same(x, self._r(p[cname + ".w"]), p[cname + ".b"], 1))
         self._tap(cname, x)
         return self._bn_relu(x, p, bname, training, new_stats)
 
@@ -273,12 +289,12 @@ class UNetOracle:
         raise ValueError(m)
 
     def _encoding_block(self, x, p, i, stride, training, new_stats):
-        x = self._r(conv2d_same(x, self._r(p[f"enc{i}.down.w"]), p[f"enc{i}.down.b"], stride))   # no BN / act
+        x = self._sub(f"enc{i}.down", self._r(conv2d_same(x, self._r(p[f"enc{i}.down.w"]), p[f"enc{i}.down.b"], stride)))   # no BN / act
         self._tap(f"enc{i}.down", x)
         return self._block(x, p, f"enc{i}.blk", training, new_stats)
 
     def _decoding_block(self, x, skip, p, j, training, new_stats):
-        x = self._r(conv2d_transpose_same(x, self._r(p[f"dec{j}.up.w"]), p[f"dec{j}.up.b"], 2))
+        x = self._sub(f"dec{j}.up", self._r(conv2d_transpose_same(x, self._r(p[f"dec{j}.up.w"]), p[f"dec{j}.up.b"], 2)))
         self._tap(f"dec{j}.up", x)
         x = torch.cat([skip, x], dim=1)            # skip FIRST (u_net.py:308)
         x = self._cbr(x, p, f"dec{j}.fuse", f"dec{j}.fuse_bn", training, new_stats)
@@ -293,7 +309,7 @@ class UNetOracle:
         self._tap("vec.dense", x)
         if training and dropout_mask is not None:              # Dropout(.3), inverted
             x = x * dropout_mask
-        x = self._r(x)
+        x = self._sub("vec.dense.out", self._r(x))
         x = x.reshape(B, H5, W5, 16).permute(0, 3, 1, 2)       # Reshape((H5, W5, 16)) NHWC
         x = conv2d_same(x, self._r(p["vec.proj.w"]), p["vec.proj.b"], 1)
         return x
@@ -314,7 +330,7 @@ class UNetOracle:
         e4 = self._encoding_block(e3, p, 4, 2, training, new_stats)
         e5 = self._encoding_block(e4, p, 5, 2, training, new_stats)
         v = self._vector_block(emb_idx, p, training, dropout_mask)
-        z = self._r(e5 + v)                                     # Add() (u_net.py:229)
+        z = self._sub("bottleneck", self._r(e5 + v))            # Add() (u_net.py:229)
         self._tap("bottleneck", z)
         d2 = self._decoding_block(z, e4, p, 2, training, new_stats)
         d3 = self._decoding_block(d2, e3, p, 3, training, new_stats)

@@ -23,6 +23,10 @@ for impl in (L.IMPL_SIMT, L.IMPL_AUTO):
     eng.loss_and_grad(y.cuda(), 1.0 / n, 1.0 / n)
     eng.backward(eng._buffers(B)["g_out"])
     torch.cuda.synchronize()
+    # reference gradients: autograd through the oracle graph with the DEVICE's forward state substituted
+    oq.override = eng.forward_state()
+    _, grads, _ = O.train_step(oq, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    oq.override = None
     print("impl", impl, "out rel", U.rel_l2(out.float(), ref_out))
     for name in eng.trainable_names():
         got, ref = eng.grad[name].cpu(), grads[name]

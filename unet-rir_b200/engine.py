@@ -449,6 +449,38 @@ class UNetEngine:
         self.lr_dev.fill_(float(lr))
 
     # ------------------------------------------------------------------ debugging / parity
+    def forward_state(self):
+        """Every tensor the last TRAINING forward stored, keyed for UNetOracle.override: raw conv outputs,
+        BN+ReLU outputs, BatchNorm batch statistics (fp32 CPU; activations NCHW)."""
+        b = self._buffers(self._last_B)
+        st = {}
+
+        def nchw(t):
+            return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+        def bn(bname):
+            mr = self._slot(self.mr_arena, bname).float().cpu()
+            c = mr.numel() // 2
+            st[bname + ".mean"] = mr[:c].clone()
+            st[bname + ".var"] = (1.0 / (mr[c:] ** 2) - PL.BN_EPS).clone()
+
+        for i in range(1, 6):
+            n = self.F0 * 2 ** (i - 1)
+            st[f"enc{i}.down"] = nchw(b[f"t{i}"])
+            st[f"enc{i}.blk.c1"] = nchw(b[f"r{i}"])
+            bn(f"enc{i}.blk.bn1")
+            if i < 5:
+                st[f"enc{i}.blk.bn1.out"] = nchw(b[f"cat{i}"][..., :n])
+        st["bottleneck"] = nchw(b["z"])
+        st["vec.dense.out"] = b["v16"].float().reshape(self._last_B, -1).cpu()
+        for j in (2, 3, 4, 5):
+            i = 6 - j
+            n = self.F0 * 2 ** (i - 1)
+            st[f"dec{j}.up"] = nchw(b[f"cat{i}"][..., n:])
+            st[f"dec{j}.fuse"] = nchw(b[f"rf{i}"]); bn(f"dec{j}.fuse_bn"); st[f"dec{j}.fuse_bn.out"] = nchw(b[f"f{i}"])
+            st[f"dec{j}.blk.c1"] = nchw(b[f"rb{i}"]); bn(f"dec{j}.blk.bn1"); st[f"dec{j}.blk.bn1.out"] = nchw(b[f"d{i}"])
+        return st
+
     def debug_tensors(self):
         """Intermediate tensors of the last forward, keyed like the oracle's taps (fp32, NCHW)."""
         b = self._buffers(self._last_B)
