@@ -103,6 +103,9 @@ int urir_conv_path(const urir_conv_desc* d, int op);
 /* fp32 HWIO master weights -> the two bf16 operand layouts. */
 int urir_weight_prep(const float* w_hwio, void* w_ck, void* w_kc, int taps, int C, int K,
                      void* stream);
+/* the same for every kernel of a model in ONE launch: table_dev = n_entries x {w fp32 ptr, w_ck ptr,
+ * w_kc ptr, taps, C, K} as int64 in device memory (refresh after each optimiser step). */
+int urir_weight_prep_batched(const int64_t* table_dev, int n_entries, void* stream);
 /* per-channel sum over pixels (bias gradients): out[c] = sum_p x[p*ld + coff + c]; overwritten. */
 int urir_channel_sum(const void* x, int dtype, long long npix, int C, int ld, int coff,
                      float* out, void* stream);
@@ -174,6 +177,9 @@ int urir_sumsq(const float* x, long long n, float scale, float* out, int accumul
 /* elementwise helpers for the alternate block modes (u_net.py:337,359) and casts */
 int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int urir_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+/* fp32 [npix][C] -> bf16 [npix][ld], ld >= C: the 16-byte-pitch bf16 copy of the 2-channel input
+ * spectrogram that the stem's tensor-core weight-gradient reads through TMA (u_net.py:269-276). */
+int urir_cast_pad_bf16(const float* x, void* y, long long npix, int C, int ld, void* stream);
 
 /* ---- signal path (preprocess.py:13-113, postprocess.py:78-133) ------------------------- */
 /* Loader mean removal + FeatureExtractor.extract + Normalizer.normalize + TensorPadder:

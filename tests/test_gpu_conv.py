@@ -209,3 +209,36 @@ def test_head_dgrad_from_fp32_gradient():
         d = U.conv_desc(N, H, W, 32, 2, k, 1, y_dtype=L.F32)
         U.run_dgrad(d, dzg, w_ck, w_kc, None, dx)
         assert U.rel_l2(dx.float(), gx) < BF16_TOL, (N, H, W, k)
+
+
+def test_stem_wgrad_on_tensor_cores_and_batched_weight_prep():
+    """enc1.down's kernel gradient from the 16-byte-pitch bf16 copy of the 2-channel input (TMA zero-fills
+    channels 2..31 of the MMA tile), and the one-launch bf16 operand refresh."""
+    g = torch.Generator().manual_seed(13)
+    N, H, W = 2, 16, 32
+    x = torch.rand(N, H, W, 2, generator=g)
+    xq = U.bf16_round(x)
+    w = U.bf16_round(torch.randn(3, 3, 2, 32, generator=g) * 0.2).requires_grad_(True)
+    dy = U.bf16_round(torch.randn(N, H, W, 32, generator=g))
+    gw, = torch.autograd.grad(_oracle_fprop(xq, w, None, 1), [w], dy)
+    xg = x.cuda()
+    x8 = torch.zeros(N, H, W, 8, dtype=torch.bfloat16, device="cuda")
+    L.call("cast_pad_bf16", xg.data_ptr(), x8.data_ptr(), N * H * W, 2, 8)
+    assert U.max_abs(x8[..., :2].float(), xq) == 0.0 and float(x8[..., 2:].float().abs().max()) == 0.0
+    dyg = dy.cuda().to(torch.bfloat16)
+    dw = torch.full((3, 3, 2, 32), 5.0, device="cuda")
+    d = U.conv_desc(N, H, W, 2, 32, 3, 1, x_ld=8, impl=L.IMPL_TC)
+    U.run_wgrad(d, x8, dyg, dw)
+    assert U.rel_l2(dw, gw) < F32_TOL
+    # batched weight prep == per-kernel weight prep
+    ws = [torch.randn(3, 3, 32, 64, generator=g).cuda(), torch.randn(6, 6, 32, 2, generator=g).cuda()]
+    outs, rows = [], []
+    for wt in ws:
+        kh, kw, c, k = wt.shape
+        ck = torch.zeros(kh * kw, c, k, dtype=torch.bfloat16, device="cuda"); kc = torch.zeros(kh * kw, k, c, dtype=torch.bfloat16, device="cuda")
+        outs.append((ck, kc)); rows.append([wt.data_ptr(), ck.data_ptr(), kc.data_ptr(), kh * kw, c, k])
+    table = torch.tensor(rows, dtype=torch.int64, device="cuda")
+    L.call("weight_prep_batched", table.data_ptr(), len(rows))
+    for wt, (ck, kc) in zip(ws, outs):
+        r_ck, r_kc = U.prep_weights(wt)
+        assert torch.equal(ck, r_ck) and torch.equal(kc, r_kc)

@@ -45,6 +45,7 @@ _PROTOS = {
     "urir_conv2d_wgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "urir_conv_path": (_i, [C.POINTER(ConvDesc), _i]),
     "urir_weight_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "urir_weight_prep_batched": (_i, [_vp, _i, _vp]),
     "urir_channel_sum": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp]),
     "urir_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _i, _vp]),
     "urir_bn_relu_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _ll, _i, _i, _vp]),
@@ -64,6 +65,7 @@ _PROTOS = {
     "urir_sumsq": (_i, [_vp, _ll, _f, _vp, _i, _vp]),
     "urir_add_bf16": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "urir_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "urir_cast_pad_bf16": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "urir_stft_ampphase": (_i, [_vp, _i, C.POINTER(StftDesc), _vp, _vp]),
     "urir_istft_from_ampphase": (_i, [_vp, _i, C.POINTER(StftDesc), _vp, _vp]),
 }

@@ -25,6 +25,7 @@ int conv_fprop_simt_dispatch(const urir_conv_desc*, const void*, const void*, co
 int conv_dgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t, const void*);
 int conv_wgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int weight_prep(const float*, void*, void*, int, int, int, cudaStream_t);
+int weight_prep_batched(const long long*, int, cudaStream_t);
 bool igemm_fprop_supported(const urir_conv_desc*);
 bool igemm_dgrad_supported(const urir_conv_desc*);
 int conv_fprop_igemm(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
@@ -45,6 +46,7 @@ int axpy(float*, const float*, float, long long, cudaStream_t);
 int sumsq(const float*, long long, float, float*, int, cudaStream_t);
 int add_bf16(const void*, const void*, void*, long long, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
+int cast_pad_bf16(const float*, void*, long long, int, int, cudaStream_t);
 int embedding_fwd(const int*, const float*, void*, int, int, int, int, cudaStream_t);
 int embedding_bwd(const int*, const float*, float*, int, int, int, int, cudaStream_t);
 int dense_fwd(const void*, const void*, const float*, const float*, void*, float*, int, int, int, cudaStream_t);
@@ -127,6 +129,11 @@ int urir_conv_path(const urir_conv_desc* d, int op) {
 int urir_weight_prep(const float* w, void* w_ck, void* w_kc, int taps, int C, int K, void* stream) {
     URIR_CHECK_ARG(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, "weight_prep: bad args");
     return weight_prep(w, w_ck, w_kc, taps, C, K, (cudaStream_t)stream);
+}
+
+int urir_weight_prep_batched(const int64_t* table_dev, int n_entries, void* stream) {
+    URIR_CHECK_ARG(table_dev && n_entries > 0, "weight_prep_batched: bad args");
+    return weight_prep_batched(reinterpret_cast<const long long*>(table_dev), n_entries, (cudaStream_t)stream);
 }
 
 int urir_channel_sum(const void* x, int dtype, long long npix, int C, int ld, int coff, float* out, void* stream) {
@@ -214,6 +221,11 @@ int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* st
 int urir_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
     URIR_CHECK_ARG(x && y && n > 0, "cast: bad args");
     return cast_f32_to_bf16(x, y, n, (cudaStream_t)stream);
+}
+
+int urir_cast_pad_bf16(const float* x, void* y, long long npix, int C, int ld, void* stream) {
+    URIR_CHECK_ARG(x && y, "cast_pad_bf16: null tensor");
+    return cast_pad_bf16(x, y, npix, C, ld, (cudaStream_t)stream);
 }
 
 int urir_stft_ampphase(const float* wav, int B, const urir_stft_desc* d, float* spec, void* stream) {

@@ -281,6 +281,30 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
+// all kernels of the model in one launch: table[e] = {w fp32 ptr, w_ck ptr, w_kc ptr, taps, C, K} (int64 each)
+__global__ void weight_prep_batched_kernel(const long long* __restrict__ table) {
+    const long long* e = table + 6 * blockIdx.y;
+    const float* w = reinterpret_cast<const float*>(e[0]);
+    __nv_bfloat16* w_ck = reinterpret_cast<__nv_bfloat16*>(e[1]);
+    __nv_bfloat16* w_kc = reinterpret_cast<__nv_bfloat16*>(e[2]);
+    const int C = (int)e[4], K = (int)e[5];
+    const long long n = e[3] * C * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K), c = (int)((i / K) % C);
+        const long long t = i / ((long long)K * C);
+        const __nv_bfloat16 v = f2bf(w[i]);
+        if (w_ck) w_ck[i] = v;
+        if (w_kc) w_kc[((size_t)t * K + k) * C + c] = v;
+    }
+}
+
+int weight_prep_batched(const long long* table_dev, int n_entries, cudaStream_t st) {
+    dim3 grid(64, n_entries);
+    weight_prep_batched_kernel<<<grid, 256, 0, st>>>(table_dev);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
 int weight_prep(const float* w, void* w_ck, void* w_kc, int taps, int C, int K, cudaStream_t st) {
     const long long n = (long long)taps * C * K;
     int blocks = cdiv(n, 256); if (blocks > 148 * 8) blocks = 148 * 8;

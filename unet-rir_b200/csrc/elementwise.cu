@@ -47,22 +47,32 @@ bn_relu_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
     __syncthreads();
     const int G = C >> 3;
     const long long total = npix * G;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / G;
-        const int c = (int)(i - pix * G) << 3;
-        const uint4 u = ld_nc_v4(x + pix * x_ld + x_coff + c);
-        const uint32_t in[4] = {u.x, u.y, u.z, u.w};
-        uint32_t out[4];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // 4 independent 128-bit loads in flight per thread (memory-level parallelism, guideline 7)
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+        uint4 u[4]; long long pixs[4]; int cs[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 v = unpack_bf16x2(in[j]);
-            v.x = fmaf(v.x, ss[c + 2 * j], ss[C + c + 2 * j]);
-            v.y = fmaf(v.y, ss[c + 2 * j + 1], ss[C + c + 2 * j + 1]);
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
-            out[j] = pack_bf16x2(v.x, v.y);
+        for (int q = 0; q < 4; ++q) {
+            const long long i = i0 + q * stride;
+            pixs[q] = i / G; cs[q] = (int)(i - pixs[q] * G) << 3;
+            if (i < total) u[q] = ld_nc_v4(x + pixs[q] * x_ld + x_coff + cs[q]);
         }
-        *reinterpret_cast<uint4*>(y + pix * y_ld + y_coff + c) = make_uint4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q * stride >= total) break;
+            const int c = cs[q];
+            const uint32_t in[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+            uint32_t out[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 v = unpack_bf16x2(in[j]);
+                v.x = fmaf(v.x, ss[c + 2 * j], ss[C + c + 2 * j]);
+                v.y = fmaf(v.y, ss[c + 2 * j + 1], ss[C + c + 2 * j + 1]);
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                out[j] = pack_bf16x2(v.x, v.y);
+            }
+            *reinterpret_cast<uint4*>(y + pixs[q] * y_ld + y_coff + c) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
     }
 }
 
@@ -86,9 +96,18 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int d
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
     if (lane < lanes) {
-        for (long long pix = (long long)blockIdx.x * lanes + lane; pix < npix; pix += (long long)gridDim.x * lanes) {
-            const uint4 ud = ld_nc_v4(dy + pix * dy_ld + dy_coff + c);
-            const uint4 ux = ld_nc_v4(x + pix * x_ld + x_coff + c);
+        const long long pstride = (long long)gridDim.x * lanes;
+        for (long long pix0 = (long long)blockIdx.x * lanes + lane; pix0 < npix; pix0 += 2 * pstride) {
+          uint4 uds[2], uxs[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+              const long long pix = pix0 + q * pstride;
+              if (pix < npix) { uds[q] = ld_nc_v4(dy + pix * dy_ld + dy_coff + c); uxs[q] = ld_nc_v4(x + pix * x_ld + x_coff + c); }
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (pix0 + q * pstride >= npix) break;
+            const uint4 ud = uds[q], ux = uxs[q];
             const uint32_t d4[4] = {ud.x, ud.y, ud.z, ud.w}, x4[4] = {ux.x, ux.y, ux.z, ux.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -101,6 +120,7 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int d
                 a1[2 * j] += g0; a1[2 * j + 1] += g1;
                 a2[2 * j] = fmaf(g0, h0, a2[2 * j]); a2[2 * j + 1] = fmaf(g1, h1, a2[2 * j + 1]);
             }
+          }
         }
     }
 #pragma unroll
@@ -139,12 +159,21 @@ bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy
     float bsum[8];                  // sum of dx over this thread's (fixed, since G | 256) channel group
 #pragma unroll
     for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / G;
-        const int c = (int)(i - pix * G) << 3;
-        const uint4 ud = ld_nc_v4(dy + pix * dy_ld + dy_coff + c);
-        const uint4 ux = ld_nc_v4(x + pix * x_ld + x_coff + c);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+      uint4 uds[2], uxs[2]; long long pixs[2]; int cs[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+          const long long i = i0 + q * stride;
+          pixs[q] = i / G; cs[q] = (int)(i - pixs[q] * G) << 3;
+          if (i < total) { uds[q] = ld_nc_v4(dy + pixs[q] * dy_ld + dy_coff + cs[q]); uxs[q] = ld_nc_v4(x + pixs[q] * x_ld + x_coff + cs[q]); }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (i0 + q * stride >= total) break;
+        const long long pix = pixs[q];
+        const int c = cs[q];
+        const uint4 ud = uds[q], ux = uxs[q];
         const uint32_t d4[4] = {ud.x, ud.y, ud.z, ud.w}, x4[4] = {ux.x, ux.y, ux.z, ux.w};
         uint32_t o[4];
 #pragma unroll
@@ -163,6 +192,7 @@ bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy
             bsum[2 * j] += r[0]; bsum[2 * j + 1] += r[1];
         }
         *reinterpret_cast<uint4*>(dx + pix * dx_ld + dx_coff + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
     if (dbias) {                    // gradient of the preceding conv's bias = sum of dx (analytically ~0)
         float* red = sm + 7 * C;
@@ -401,6 +431,20 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = f2bf(x[i]);
+}
+
+// fp32 [npix][C] -> bf16 [npix][ld] (first C channels; the rest of each row is left untouched / pre-zeroed)
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long npix, int C, int ld) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix * C; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / C;
+        y[pix * ld + (i - pix * C)] = f2bf(x[i]);
+    }
+}
+int cast_pad_bf16(const float* x, void* y, long long npix, int C, int ld, cudaStream_t st) {
+    URIR_CHECK_ARG(npix > 0 && C > 0 && ld >= C, "cast_pad_bf16: bad args");
+    cast_pad_bf16_kernel<<<grid_for(npix * C, 256), 256, 0, st>>>(x, (__nv_bfloat16*)y, npix, C, ld);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
 }
 
 int adam(float* p, const float* g, float* m, float* v, long long n, const float* lr, const int* step, float b1,

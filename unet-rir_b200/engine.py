@@ -117,6 +117,11 @@ class UNetEngine:
                 self.wops[name] = (torch.empty(kh * kw, a, b, dtype=torch.bfloat16, device=dev),
                                    torch.empty(kh * kw, b, a, dtype=torch.bfloat16, device=dev))
         self.dense_w16 = torch.empty(self.shapes["vec.dense.w"], dtype=torch.bfloat16, device=dev)
+        rows = []
+        for name, (w_ck, w_kc) in self.wops.items():
+            taps, a, b = w_ck.shape
+            rows.append([self.param[name].data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), taps, a, b])
+        self.wprep_table = torch.tensor(rows, dtype=torch.int64, device=dev)
         # per-BN scratch: stats (zeroed each forward), scale/shift, mean/rstd, backward sums
         bn_names = [n[:-len(".gamma")] for n in self.offsets if n.endswith(".gamma")]
         tot = sum(2 * self.shapes[b + ".gamma"][0] for b in bn_names)
@@ -153,9 +158,7 @@ class UNetEngine:
 
     def refresh_operands(self):
         """fp32 masters -> bf16 operand layouts (after load / after every optimiser step)."""
-        for name, (w_ck, w_kc) in self.wops.items():
-            taps, a, b = w_ck.shape
-            L.call("weight_prep", self.param[name].data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), taps, a, b)
+        L.call("weight_prep_batched", self.wprep_table.data_ptr(), self.wprep_table.shape[0])
         L.call("cast_f32_to_bf16", self.param["vec.dense.w"].data_ptr(), self.dense_w16.data_ptr(),
                self.dense_w16.numel())
 
@@ -171,6 +174,7 @@ class UNetEngine:
             return torch.zeros(B, h, w, c, dtype=dtype, device=dev)
 
         b["x_in"] = act(H, W, Cin, torch.float32)
+        b["x_in8"] = act(H, W, 8)        # bf16 copy of x_in, 16-byte pixel pitch: TMA operand of the stem's wgrad
         b["emb"] = torch.zeros(B, self.T, dtype=torch.int32, device=dev)
         b["out"] = act(H, W, 2, torch.float32)
         b["g_out"] = act(H, W, 2, torch.float32)
@@ -408,7 +412,12 @@ class UNetEngine:
                     self._conv_dgrad(f"enc{i}.down", g_t, g_e_prev, k, 2, accumulate=1)
                     g_e = g_e_prev
                 else:
-                    self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
+                    if self.input_shape[2] <= 8:
+                        L.call("cast_pad_bf16", b["x_in"].data_ptr(), b["x_in8"].data_ptr(), b["x_in"].numel() // self.input_shape[2],
+                               self.input_shape[2], 8)
+                        self._conv_wgrad("enc1.down", View(b["x_in8"], 0, self.input_shape[2]), g_t, k, 1)
+                    else:
+                        self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
 
     # ------------------------------------------------------------------ loss + optimiser
     def loss_and_grad(self, y_true, w_amp, w_ph, need_grad=True):
