@@ -128,9 +128,9 @@ def test_stem_and_head_shapes():
     xg, bg = x.cuda(), b.cuda()
     U.run_fprop(d, xg, w_ck, w_kc, bg, y)
     assert U.rel_l2(y.float(), _oracle_fprop(x, w, b, 1)) < BF16_TOL
-    with pytest.raises(L.UrirError):
-        d.impl = L.IMPL_TC
-        U.run_fprop(d, xg, w_ck, w_kc, bg, y)
+    d.impl = L.IMPL_SIMT                                   # the CUDA-core stem kernel stays available
+    U.run_fprop(d, xg, w_ck, w_kc, bg, y)
+    assert U.rel_l2(y.float(), _oracle_fprop(x, w, b, 1)) < BF16_TOL
 
     xh = U.bf16_round(torch.randn(N, H, W, 32, generator=g))
     wh = U.bf16_round(torch.randn(6, 6, 32, 2, generator=g) * 0.05)
@@ -242,3 +242,61 @@ def test_stem_wgrad_on_tensor_cores_and_batched_weight_prep():
     for wt, (ck, kc) in zip(ws, outs):
         r_ck, r_kc = U.prep_weights(wt)
         assert torch.equal(ck, r_ck) and torch.equal(kc, r_kc)
+
+
+THIN_CASES = [(2, 16, 32, 3), (3, 24, 48, 6), (1, 8, 16, 6), (2, 144, 160, 6), (1, 40, 64, 5)]
+
+
+@pytest.mark.parametrize("case", THIN_CASES, ids=[str(c) for c in THIN_CASES])
+def test_thin_channel_tensor_core_kernels(case):
+    """conv_thin.cu: the 2-channel stem (fprop, wgrad) and head (dgrad, wgrad) as one small tcgen05 GEMM per
+    128-pixel tile over an im2col tile built in shared memory from the fp32 thin tensor. The thin operand
+    is rounded to bf16 on chip, so the oracle gets the bf16-rounded tensor."""
+    N, H, W, k = case
+    g = torch.Generator().manual_seed(21 + k)
+    # ---- stem: x fp32 [.,2] -> 32 channels
+    x = torch.rand(N, H, W, 2, generator=g)
+    xq = U.bf16_round(x)
+    w = U.bf16_round(torch.randn(k, k, 2, 32, generator=g) * 0.2)
+    b = torch.randn(32, generator=g) * 0.1
+    dy = U.bf16_round(torch.randn(N, H, W, 32, generator=g))
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    xg, bg, dyg = x.cuda(), b.cuda(), dy.cuda().to(torch.bfloat16)
+    d = U.conv_desc(N, H, W, 2, 32, k, 1, x_dtype=L.F32)
+    assert L.load().urir_conv_path(d, 0) == 1 and L.load().urir_conv_path(d, 2) == 1
+    y = torch.empty(N, H, W, 32, dtype=torch.bfloat16, device="cuda")
+    U.run_fprop(d, xg, w_ck, w_kc, bg, y)
+    assert U.rel_l2(y.float(), _oracle_fprop(xq, w, b, 1)) < BF16_TOL
+    # written inside a wider buffer (channel slice)
+    wide = torch.zeros(N, H, W, 64, dtype=torch.bfloat16, device="cuda")
+    d2 = U.conv_desc(N, H, W, 2, 32, k, 1, x_dtype=L.F32, y_ld=64, y_coff=32)
+    U.run_fprop(d2, xg, w_ck, w_kc, bg, wide)
+    assert torch.equal(wide[..., 32:], y) and float(wide[..., :32].float().abs().max()) == 0.0
+    wr = w.clone().requires_grad_(True)
+    gw, = torch.autograd.grad(_oracle_fprop(xq, wr, None, 1), [wr], dy)
+    dw = torch.full((k, k, 2, 32), 5.0, device="cuda")
+    U.run_wgrad(d, xg, dyg, dw)
+    assert U.rel_l2(dw, gw) < F32_TOL
+    # ---- head: 32 channels -> fp32 [.,2]
+    xh = U.bf16_round(torch.randn(N, H, W, 32, generator=g))
+    wh = U.bf16_round(torch.randn(k, k, 32, 2, generator=g) * 0.05)
+    dz = torch.randn(N, H, W, 2, generator=g)
+    dzq = U.bf16_round(dz)
+    xr, whr = xh.clone().requires_grad_(True), wh.clone().requires_grad_(True)
+    gx, gwh = torch.autograd.grad(_oracle_fprop(xr, whr, None, 1), [xr, whr], dzq)
+    w_ck, w_kc = U.prep_weights(wh.cuda())
+    dh = U.conv_desc(N, H, W, 32, 2, k, 1, y_dtype=L.F32)
+    assert L.load().urir_conv_path(dh, 1) == 1 and L.load().urir_conv_path(dh, 2) == 1
+    dx = torch.empty(N, H, W, 32, dtype=torch.bfloat16, device="cuda")
+    U.run_dgrad(dh, dz.cuda(), w_ck, w_kc, None, dx)
+    assert U.rel_l2(dx.float(), gx) < BF16_TOL
+    dwh = torch.full((k, k, 32, 2), 7.0, device="cuda")
+    U.run_wgrad(dh, xh.cuda().to(torch.bfloat16), dz.cuda(), dwh)
+    assert U.rel_l2(dwh, gwh) < F32_TOL
+    # head forward (conv_head.cu): horizontal taps in GEMM-N, shifted sum in the epilogue, fused sigmoid
+    bh = torch.randn(2, generator=g) * 0.1
+    out = torch.full((N, H, W, 2), -1.0, device="cuda")
+    dhf = U.conv_desc(N, H, W, 32, 2, k, 1, y_dtype=L.F32, act=L.ACT_SIGMOID)
+    assert L.load().urir_conv_path(dhf, 0) == 1
+    U.run_fprop(dhf, xh.cuda().to(torch.bfloat16), w_ck, w_kc, bh.cuda(), out)
+    assert U.max_abs(out, torch.sigmoid(_oracle_fprop(xh, wh, bh, 1))) < 1e-5

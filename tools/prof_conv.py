@@ -16,19 +16,28 @@ CASES = {
     "fprop_mid": ("fprop", 64, 36, 40, 256, 128, 3, 1),
     "dgrad_s2": ("dgrad", 64, 144, 160, 32, 64, 3, 2),
     "head_wgrad": ("wgrad", 64, 144, 160, 32, 2, 6, 1),
+    "head_fprop": ("fprop", 64, 144, 160, 32, 2, 6, 1),
+    "head_dgrad": ("dgrad", 64, 144, 160, 32, 2, 6, 1),
+    "stem_fprop": ("fprop", 64, 144, 160, 2, 32, 3, 1),
+    "stem_wgrad": ("wgrad", 64, 144, 160, 2, 32, 3, 1),
+    "dgrad_full": ("dgrad", 64, 144, 160, 32, 32, 3, 1),
+    "wgrad_half": ("wgrad", 64, 72, 80, 64, 64, 3, 1),
+    "fprop_half": ("fprop", 64, 72, 80, 64, 64, 3, 1),
 }
 
 
-def run(which, reps=3):
+def run(which, reps=int(os.environ.get("PROF_REPS", "3"))):
     op, N, H, W, Cc, K, k, s = CASES[which]
     P, pt = L.same_pad(H, k, s); Q, pl = L.same_pad(W, k, s)
-    y_ld = 8 if K < 8 else K
-    x = torch.randn(N, H, W, Cc, device="cuda").to(torch.bfloat16)
-    dy = torch.randn(N, P, Q, y_ld, device="cuda").to(torch.bfloat16)
+    y_ld = K
+    xt = torch.float32 if Cc == 2 else torch.bfloat16
+    yt = torch.float32 if K == 2 else torch.bfloat16
+    x = torch.randn(N, H, W, Cc, device="cuda").to(xt)
+    dy = torch.randn(N, P, Q, y_ld, device="cuda").to(yt)
     w_ck = torch.randn(k * k, Cc, K, device="cuda").to(torch.bfloat16)
     w_kc = torch.randn(k * k, K, Cc, device="cuda").to(torch.bfloat16)
     dw = torch.zeros(k, k, Cc, K, device="cuda")
-    d = L.ConvDesc(N, H, W, Cc, K, k, k, s, pt, pl, P, Q, Cc, 0, y_ld, 0, L.BF16, L.BF16, L.IMPL_TC, 0, 0)
+    d = L.ConvDesc(N, H, W, Cc, K, k, k, s, pt, pl, P, Q, Cc, 0, y_ld, 0, L.dtype_code(x), L.dtype_code(dy), L.IMPL_AUTO, 0, 0)
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

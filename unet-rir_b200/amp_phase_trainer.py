@@ -188,7 +188,7 @@ class Trainer:
         b = eng._buffers(B)
         eng._forward_body(B, training=True, dropout=self.dropout)
         L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), n, 1.0 / n, 1.0 / n, 1,
-               eng.losses_dev.data_ptr(), b["g_out"].data_ptr(), b["g_out8"].data_ptr(), 8)
+               eng.losses_dev.data_ptr(), b["g_out"].data_ptr(), None, 0)
         eng._backward_body(B)
         if self.optimizer == 'adam':
             eng.adam_step()

@@ -31,6 +31,11 @@ bool igemm_dgrad_supported(const urir_conv_desc*);
 int conv_fprop_igemm(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
 int conv_dgrad_igemm(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
 bool wgrad_tc_supported(const urir_conv_desc*);
+bool thin_supported(const urir_conv_desc*, int op);
+bool head_fprop_supported(const urir_conv_desc*);
+int head_fprop(const urir_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int thin_gemm(const urir_conv_desc*, const void*, const void*, const float*, void*, bool, cudaStream_t);
+int thin_wgrad(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int conv_wgrad_tc(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int bn_finalize(const float*, double, const float*, const float*, float*, float*, float, float, int, float*, float*, int, cudaStream_t);
 int bn_relu_fwd(const void*, int, int, const float*, void*, int, int, long long, int, int, cudaStream_t);
@@ -91,6 +96,10 @@ int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, 
     int rc = check_conv(d, "conv2d_fprop"); if (rc) return rc;
     URIR_CHECK_ARG(x && y, "conv2d_fprop: null tensor");
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && thin_supported(d, 0))
+        return thin_gemm(d, x, w_ck, bias, y, true, st);                       // the 2-channel stem
+    if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && head_fprop_supported(d))
+        return head_fprop(d, x, w_ck, bias, y, st);                            // the 2-channel head
     const bool tc_ok = igemm_fprop_supported(d) && w_kc != nullptr;
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
@@ -103,6 +112,8 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
     URIR_CHECK_ARG(dy && dx, "conv2d_dgrad: null tensor");
     URIR_CHECK_ARG(d->act == URIR_ACT_NONE, "conv2d_dgrad: activation not supported");
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && !bias && thin_supported(d, 1))
+        return thin_gemm(d, dy, w_ck, nullptr, dx, false, st);                 // the 2-channel head
     const bool tc_ok = igemm_dgrad_supported(d) && w_ck != nullptr;
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
@@ -113,6 +124,7 @@ int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, fl
     int rc = check_conv(d, "conv2d_wgrad"); if (rc) return rc;
     URIR_CHECK_ARG(x && dy && dw, "conv2d_wgrad: null tensor");
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && thin_supported(d, 2)) return thin_wgrad(d, x, dy, dw, st);
     const bool tc_ok = wgrad_tc_supported(d);
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_wgrad: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
@@ -121,6 +133,8 @@ int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, fl
 
 int urir_conv_path(const urir_conv_desc* d, int op) {
     if (!d || d->impl == URIR_IMPL_SIMT || (d->impl == URIR_IMPL_AUTO && env_force_simt())) return 0;
+    if (thin_supported(d, op)) return 1;
+    if (op == 0 && head_fprop_supported(d)) return 1;
     if (op == 0) return igemm_fprop_supported(d) ? 1 : 0;
     if (op == 1) return igemm_dgrad_supported(d) ? 1 : 0;
     return wgrad_tc_supported(d) ? 1 : 0;

@@ -1,0 +1,382 @@
+// Thin-channel convolutions on tcgen05 (sm_100a): the layers where ONE side has 2 channels --
+//   * the stem  enc1.down : Conv2D(2 -> F0, k)            (dl_models/u_net.py:269-276 on the spectrogram)
+//   * the head            : Conv2D(F0 -> 2, 6x6) + sigmoid (dl_models/u_net.py:247-249)
+// A (tap, 2-channel) im2col row of the thin tensor is only 18 / 72 values, so instead of running taps as
+// GEMM-K iterations over re-fetched activation tiles (what conv_igemm.cu does for wide layers), the CTA
+// builds the im2col rows of a 128-pixel tile in shared memory from a halo patch of the fp32 thin tensor
+// (8 bytes per pixel) and the whole layer becomes ONE small GEMM per tile:
+//   thin_gemm  (stem fprop, head dgrad): wide[p, 32] = im2col(thin)[p, J] * Wm[J, 32]   M = pixels, K = J
+//   thin_wgrad (stem wgrad, head wgrad): dW[J, 32]  += im2col(thin)[p, J]^T * wide[p, 32]   K = pixels
+// Both read / write the wide bf16 tensor exactly once (HBM-bound, ~94 MB per launch at B = 64) and share the
+// same shared-memory image of the im2col tile: 128 rows (pixels) of 128 B, 16-byte chunks XOR-swizzled with
+// (row % 8) -- consumed K-major by thin_gemm and MN-major by thin_wgrad.
+// The head's forward (wide -> thin) lives in conv_head.cu.
+#include "urir_common.cuh"
+#include "urir_tc.cuh"
+
+namespace urir {
+
+using namespace tc;
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int swizzle_bytes);
+
+constexpr int TH_BW = 16, TH_BH = 8;            // the 128-pixel tile
+constexpr int TH_MAX_TAPS = 40;
+constexpr int TH_ATOM = 128 * 128;              // 128 rows x 128 B
+constexpr int TH_PATCH_MAX = (TH_BH + 5) * (TH_BW + 5);   // k <= 6
+
+struct ThinParams {
+    int N, H, W;
+    int ntaps;
+    int PH, PW;                 // halo patch extent (pixels)
+    int oh0, ow0;               // patch origin relative to the tile origin
+    int tiles_w, tiles_h, total_tiles;
+    int KS;                     // GEMM-K steps of 16 for thin_gemm = ceil(2 * ntaps / 16)
+    int nchunks;                // 16-byte chunks per im2col row that are (re)written per tile = 2 * KS
+    int CW_total;               // channels of the wide side in the weight tensor
+    int thin_is_x;              // 1: thin tensor is the conv input (stem); 0: it is the conv output side (head)
+    const float* thin; int thin_ld, thin_coff;
+    const __nv_bfloat16* w_ck; const float* bias;
+    __nv_bfloat16* out; int out_ld, out_coff;
+    float* dw;
+    short toff[TH_MAX_TAPS];    // patch pixel index offset of tap t
+};
+
+__device__ __forceinline__ int thin_widx(const ThinParams& p, int tap, int ct, int cw) {
+    // element (tap, ct, cw) in the [tap][C][K] weight layout
+    return p.thin_is_x ? (tap * 2 + ct) * p.CW_total + cw : (tap * p.CW_total + cw) * 2 + ct;
+}
+
+__device__ __forceinline__ void thin_tile_coords(const ThinParams& p, int tile, int& n, int& h0, int& w0) {
+    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+    const int th = tile % p.tiles_h; n = tile / p.tiles_h;
+    h0 = th * TH_BH; w0 = tw * TH_BW;
+}
+
+// this thread's (up to 3) entries of the halo patch of `tile`, zero outside the image (SAME padding)
+__device__ __forceinline__ void thin_load_patch(const ThinParams& p, int tile, float2 (&pr)[3]) {
+    int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+    const int npatch = p.PH * p.PW;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int i = threadIdx.x + 128 * q;
+        pr[q] = make_float2(0.f, 0.f);
+        if (i < npatch) {
+            const int py = i / p.PW, px = i - py * p.PW;
+            const int gh = h0 + p.oh0 + py, gw = w0 + p.ow0 + px;
+            if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W)
+                pr[q] = __ldg(reinterpret_cast<const float2*>(p.thin + ((size_t)(n * p.H + gh) * p.W + gw) * p.thin_ld + p.thin_coff));
+        }
+    }
+}
+__device__ __forceinline__ void thin_store_patch(const ThinParams& p, float2* patch, const float2 (&pr)[3]) {
+    const int npatch = p.PH * p.PW;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const int i = threadIdx.x + 128 * q; if (i < npatch) patch[i] = pr[q]; }
+}
+
+// im2col row of pixel `m` (= threadIdx.x) -> 16-byte chunks c = 0 .. nchunks-1 of the swizzled tile
+__device__ __forceinline__ void thin_build_row(const ThinParams& p, const float2* patch, uint8_t* sA) {
+    const int m = threadIdx.x;
+    const int base = (m / TH_BW) * p.PW + (m % TH_BW);
+#pragma unroll
+    for (int c = 0; c < TH_MAX_TAPS / 4; ++c) {
+        if (c < p.nchunks) {
+            uint32_t wd[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int tap = 4 * c + e;
+                float2 v = make_float2(0.f, 0.f);
+                if (tap < p.ntaps) v = patch[base + p.toff[tap]];
+                wd[e] = pack_bf16x2(v.x, v.y);
+            }
+            *reinterpret_cast<uint4*>(sA + (c >> 3) * TH_ATOM + m * 128 + (((c & 7) ^ (m & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// thin_gemm: out[p, n0 .. n0+32) = im2col(thin)[p, :] * Wm (+ bias)
+// 128 threads: thread = pixel = A row = TMEM lane. Persistent over tiles; 4 CTAs per SM hide each other's
+// global-load / MMA / store latencies. smem: A 2 atoms (32 KB) | B 2 atoms of 32 rows (8 KB) | patch | barrier
+// ---------------------------------------------------------------------------------------------
+constexpr int TG_B_ATOM = 32 * 128;
+constexpr int TG_SMEM = 2 * TH_ATOM + 2 * TG_B_ATOM + TH_PATCH_MAX * 8 + 64 + 1024;
+
+__global__ void __launch_bounds__(128)
+thin_gemm_kernel(const __grid_constant__ ThinParams p) {
+    constexpr uint32_t IDESC = make_idesc_bf16(128, 32, 0, 0);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 2 * TH_ATOM;
+    float2* patch = reinterpret_cast<float2*>(sB + 2 * TG_B_ATOM);
+    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + TH_PATCH_MAX * 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * 32;
+
+    if (threadIdx.x == 0) { mbar_init(mma_bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(tmem_slot, 32);
+    // weights -> swizzled K-major B tile: row n = wide channel, column j = (tap, thin channel)
+    for (int idx = threadIdx.x; idx < 32 * p.nchunks; idx += 128) {
+        const int c = idx >> 5, n = idx & 31;
+        uint32_t wd[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int tap = 4 * c + e;
+            float a = 0.f, b = 0.f;
+            if (tap < p.ntaps) { a = bf2f(p.w_ck[thin_widx(p, tap, 0, n0 + n)]); b = bf2f(p.w_ck[thin_widx(p, tap, 1, n0 + n)]); }
+            wd[e] = pack_bf16x2(a, b);
+        }
+        *reinterpret_cast<uint4*>(sB + (c >> 3) * TG_B_ATOM + n * 128 + (((c & 7) ^ (n & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (SWZ_128B << 29);
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+
+    float bias_v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias_v[j] = p.bias ? __ldg(p.bias + n0 + j) : 0.f;
+
+    float2 pr[3];
+    int tile = blockIdx.x;
+    if (tile < p.total_tiles) thin_load_patch(p, tile, pr);
+    for (int it = 0; tile < p.total_tiles; ++it, tile += gridDim.x) {
+        thin_store_patch(p, patch, pr);
+        __syncthreads();
+        thin_build_row(p, patch, sA);
+        const int next = tile + gridDim.x;
+        if (next < p.total_tiles) thin_load_patch(p, next, pr);      // in flight across the MMA and the epilogue
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (warp == 0) {
+            fence_after_sync();
+            for (int i = 0; i < p.KS; ++i) {
+                const uint64_t ad = ((uint64_t)d_hi << 32) | ((a_addr + (i >> 2) * TH_ATOM + (i & 3) * 32) >> 4);
+                const uint64_t bd = ((uint64_t)d_hi << 32) | ((b_addr + (i >> 2) * TG_B_ATOM + (i & 3) * 32) >> 4);
+                umma_bf16_elect(tmem_base, ad, bd, IDESC, i != 0);
+            }
+            umma_commit_elect(mma_bar);
+            __syncwarp();
+        }
+        mbar_wait(mma_bar, it & 1);
+        fence_after_sync();
+        int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+        const int m = threadIdx.x;
+        __nv_bfloat16* orow = p.out + ((size_t)(n * p.H + h0 + m / TH_BW) * p.W + w0 + m % TH_BW) * p.out_ld + p.out_coff + n0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t r0[16], r1[16];
+        tmem_ld16(lane_addr, r0);
+        tmem_ld16(lane_addr + 16, r1);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o[j] = pack_bf16x2(__uint_as_float(r0[2 * j]) + bias_v[2 * j], __uint_as_float(r0[2 * j + 1]) + bias_v[2 * j + 1]);
+            o[8 + j] = pack_bf16x2(__uint_as_float(r1[2 * j]) + bias_v[16 + 2 * j], __uint_as_float(r1[2 * j + 1]) + bias_v[16 + 2 * j + 1]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(orow + 8 * q) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 0) { fence_after_sync(); tmem_dealloc(tmem_base, 32); }
+    (void)lane;
+}
+
+// ---------------------------------------------------------------------------------------------
+// thin_wgrad: dW[(tap, ct), n0 .. n0+32) += sum over this CTA's tiles of im2col(thin)^T * wide
+// A = the im2col tile read MN-major (M = J padded to 128 over 2 atoms, K = 128 pixels in 8 steps of 16);
+// B = the wide bf16 tile {32 ch x 16 x 8 pixels} brought by TMA as 128 rows of 64 B (MN-major, 64B swizzle).
+// Two stages of {A, B}; the accumulator stays in TMEM for the CTA's whole pixel range (split-K), then is
+// added into dW with global reductions.
+// ---------------------------------------------------------------------------------------------
+constexpr int TW_A_STAGE = 2 * TH_ATOM, TW_B_STAGE = 128 * 64;
+constexpr int TW_SMEM = 2 * TW_A_STAGE + 2 * TW_B_STAGE + TH_PATCH_MAX * 8 + 128 + 1024;
+
+__global__ void __launch_bounds__(128)
+thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_constant__ ThinParams p) {
+    constexpr uint32_t IDESC = make_idesc_bf16(128, 32, 1, 1);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 2 * TW_A_STAGE;
+    float2* patch = reinterpret_cast<float2*>(sB + 2 * TW_B_STAGE);
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + TH_PATCH_MAX * 8);
+    uint64_t* bar_mma = bar_b + 2;
+    uint64_t* bar_done = bar_mma + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int n0 = blockIdx.y * 32;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_b, 1); mbar_init(bar_b + 1, 1); mbar_init(bar_mma, 1); mbar_init(bar_mma + 1, 1); mbar_init(bar_done, 1);
+        fence_barrier_init();
+        prefetch_tmap(&wide_map);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 32);
+    // chunks the per-tile build never writes (im2col columns >= 16*KS) feed accumulator rows that are never
+    // read back; zero them once so that no NaN patterns circulate
+    for (int s = 0; s < 2; ++s)
+        for (int idx = threadIdx.x; idx < 128 * 16; idx += 128) {
+            const int c = idx >> 7, m = idx & 127;
+            if (c >= p.nchunks)
+                *reinterpret_cast<uint4*>(sA + s * TW_A_STAGE + (c >> 3) * TH_ATOM + m * 128 + (((c & 7) ^ (m & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+        }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (SWZ_128B << 29);
+    const uint32_t b_hi = (512u >> 4) | (1u << 14) | (SWZ_64B << 29);
+    const uint32_t a_lo0 = ((uint32_t)(TH_ATOM >> 4) << 16) | (smem_u32(sA) >> 4);
+    const uint32_t b_lo0 = ((uint32_t)(TW_B_STAGE >> 4) << 16) | (smem_u32(sB) >> 4);
+
+    float2 pr[3];
+    int tile = blockIdx.x;
+    int n_iters = 0;
+    if (tile < p.total_tiles) thin_load_patch(p, tile, pr);
+    for (int it = 0; tile < p.total_tiles; ++it, tile += gridDim.x) {
+        const int s = it & 1;
+        if (it >= 2) mbar_wait(bar_mma + s, ((it >> 1) - 1) & 1);       // the MMAs that read stage s are done
+        if (warp == 0) {
+            int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+            mbar_expect_tx_elect(bar_b + s, TW_B_STAGE);
+            tma_load_4d_elect(&wide_map, bar_b + s, sB + s * TW_B_STAGE, n0, w0, h0, n);
+        }
+        thin_store_patch(p, patch, pr);
+        __syncthreads();
+        thin_build_row(p, patch, sA + s * TW_A_STAGE);
+        const int next = tile + gridDim.x;
+        if (next < p.total_tiles) thin_load_patch(p, next, pr);
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            mbar_wait(bar_b + s, (it >> 1) & 1);
+            fence_after_sync();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + ((s * TW_A_STAGE + i * 2048) >> 4));
+                const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + ((s * TW_B_STAGE + i * 1024) >> 4));
+                umma_bf16_elect(tmem_base, ad, bd, IDESC, (it | i) != 0);
+            }
+            umma_commit_elect(bar_mma + s);
+            __syncwarp();
+        }
+        n_iters = it + 1;
+    }
+    if (n_iters > 0) {
+        if (warp == 0) { umma_commit_elect(bar_done); __syncwarp(); }
+        mbar_wait(bar_done, 0);
+        fence_after_sync();
+        const int j = threadIdx.x;                       // accumulator row = (tap, thin channel)
+        const int tap = j >> 1, ct = j & 1;
+        const bool valid = tap < p.ntaps;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(lane_addr + c0, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    atomicAdd(p.dw + thin_widx(p, tap, ct, n0 + c0 + q), __uint_as_float(r[q]));
+            }
+        }
+        fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 0) { fence_after_sync(); tmem_dealloc(tmem_base, 32); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool thin_geometry_ok(const urir_conv_desc* d) {
+    return d->stride == 1 && d->P == d->H && d->Q == d->W && d->W % TH_BW == 0 && d->H % TH_BH == 0 &&
+           d->R * d->S <= 36 && d->R <= 6 && d->S <= 6;
+}
+// op: 0 fprop (thin = x), 1 dgrad (thin = dy), 2 wgrad (either)
+bool thin_supported(const urir_conv_desc* d, int op) {
+    if (!thin_geometry_ok(d)) return false;
+    const bool thin_x = d->x_dtype == URIR_F32 && d->C == 2 && d->x_ld % 2 == 0 && d->x_coff % 2 == 0 &&
+                        d->y_dtype == URIR_BF16 && d->K % 32 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0;
+    const bool thin_y = d->y_dtype == URIR_F32 && d->K == 2 && d->y_ld % 2 == 0 && d->y_coff % 2 == 0 &&
+                        d->x_dtype == URIR_BF16 && d->C % 32 == 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0;
+    if (op == 0) return thin_x && d->act == URIR_ACT_NONE && !d->accumulate;
+    if (op == 1) return thin_y && !d->accumulate;
+    return thin_x || thin_y;
+}
+
+static void thin_fill(ThinParams& p, const urir_conv_desc* d, bool thin_is_x) {
+    memset(&p, 0, sizeof(p));
+    p.N = d->N; p.H = d->H; p.W = d->W;
+    p.ntaps = d->R * d->S;
+    p.PH = TH_BH + d->R - 1; p.PW = TH_BW + d->S - 1;
+    p.tiles_w = d->W / TH_BW; p.tiles_h = d->H / TH_BH; p.total_tiles = p.tiles_w * p.tiles_h * d->N;
+    p.KS = (2 * p.ntaps + 15) / 16; p.nchunks = 2 * p.KS;
+    p.thin_is_x = thin_is_x ? 1 : 0;
+    p.CW_total = thin_is_x ? d->K : d->C;
+    if (thin_is_x) { p.oh0 = -d->pad_top; p.ow0 = -d->pad_left; }
+    else { p.oh0 = d->pad_top - (d->R - 1); p.ow0 = d->pad_left - (d->S - 1); }
+    for (int r = 0; r < d->R; ++r)
+        for (int s = 0; s < d->S; ++s)
+            p.toff[r * d->S + s] = (short)(thin_is_x ? r * p.PW + s : (d->R - 1 - r) * p.PW + (d->S - 1 - s));
+}
+
+// stem fprop (thin = x fp32) and head dgrad (thin = dy fp32)
+int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const float* bias, void* wide, bool thin_is_x,
+              cudaStream_t st) {
+    URIR_CHECK_ARG(w_ck != nullptr, "thin conv needs w_ck");
+    ThinParams p; thin_fill(p, d, thin_is_x);
+    p.thin = (const float*)thin; p.w_ck = (const __nv_bfloat16*)w_ck; p.bias = bias; p.out = (__nv_bfloat16*)wide;
+    if (thin_is_x) { p.thin_ld = d->x_ld; p.thin_coff = d->x_coff; p.out_ld = d->y_ld; p.out_coff = d->y_coff; }
+    else { p.thin_ld = d->y_ld; p.thin_coff = d->y_coff; p.out_ld = d->x_ld; p.out_coff = d->x_coff; }
+    static bool attr_set = false;
+    if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(thin_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM)); attr_set = true; }
+    int gx = p.total_tiles < 148 * 4 ? p.total_tiles : 148 * 4;
+    dim3 grid(gx, p.CW_total / 32);
+    thin_gemm_kernel<<<grid, 128, TG_SMEM, st>>>(p);
+    URIR_LAUNCH_OK(1);
+    return URIR_OK;
+}
+
+// stem wgrad (thin = x fp32, wide = dy) and head wgrad (thin = dy fp32, wide = x); dw fp32 [tap][C][K], overwritten
+int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    const bool thin_is_x = d->x_dtype == URIR_F32;
+    ThinParams p; thin_fill(p, d, thin_is_x);
+    const void* wide; int wide_ld, wide_coff, wide_c;
+    if (thin_is_x) { p.thin = (const float*)x; p.thin_ld = d->x_ld; p.thin_coff = d->x_coff; wide = dy; wide_ld = d->y_ld; wide_coff = d->y_coff; wide_c = d->K; }
+    else { p.thin = (const float*)dy; p.thin_ld = d->y_ld; p.thin_coff = d->y_coff; wide = x; wide_ld = d->x_ld; wide_coff = d->x_coff; wide_c = d->C; }
+    p.dw = dw;
+    CUtensorMap map;
+    {
+        const uint64_t dims[4] = {(uint64_t)wide_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)wide_ld * 2, (uint64_t)d->W * wide_ld * 2, (uint64_t)d->H * d->W * wide_ld * 2};
+        const uint32_t box[4] = {32, TH_BW, TH_BH, 1};
+        int rc = encode_map(&map, (const char*)wide + (size_t)wide_coff * 2, 4, dims, strides, box, 64);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM)); attr_set = true; }
+    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.ntaps * d->C * d->K, st));
+    int gx = p.total_tiles < 148 * 2 ? p.total_tiles : 148 * 2;
+    dim3 grid(gx, p.CW_total / 32);
+    thin_wgrad_kernel<<<grid, 128, TW_SMEM, st>>>(map, p);
+    URIR_LAUNCH_OK(1);
+    return URIR_OK;
+}
+
+}  // namespace urir

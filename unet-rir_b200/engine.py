@@ -174,11 +174,9 @@ class UNetEngine:
             return torch.zeros(B, h, w, c, dtype=dtype, device=dev)
 
         b["x_in"] = act(H, W, Cin, torch.float32)
-        b["x_in8"] = act(H, W, 8)        # bf16 copy of x_in, 16-byte pixel pitch: TMA operand of the stem's wgrad
         b["emb"] = torch.zeros(B, self.T, dtype=torch.int32, device=dev)
         b["out"] = act(H, W, 2, torch.float32)
         b["g_out"] = act(H, W, 2, torch.float32)
-        b["g_out8"] = act(H, W, 8)       # bf16 copy of g_out, 16-byte pixel pitch: TMA operand of the head's wgrad
         b["y_true"] = act(H, W, 2, torch.float32)
         for i in range(1, 6):
             n = self.F0 * 2 ** (i - 1)
@@ -338,7 +336,6 @@ class UNetEngine:
         b = self._buffers(B)
         if g_head.data_ptr() != b["g_out"].data_ptr():
             b["g_out"].copy_(g_head)
-            b["g_out8"][..., :2].copy_(g_head)
         self._backward_body(B)
 
     def _bstat(self, key, c):
@@ -361,7 +358,7 @@ class UNetEngine:
             g_out = View(b["g_out"])
             d1 = View(b["d1"])
             # head
-            self._conv_wgrad("head", d1, View(b["g_out8"], 0, 2), 6, 1)
+            self._conv_wgrad("head", d1, g_out, 6, 1)
             L.call("channel_sum", g_out.ptr(), L.F32, g_out.npix, 2, 2, 0, self.grad["head.b"].data_ptr())
             self._conv_dgrad("head", g_out, View(b["g_d1"]), 6, 1)
             # decoder, top (level 1) down to level 4
@@ -412,12 +409,7 @@ class UNetEngine:
                     self._conv_dgrad(f"enc{i}.down", g_t, g_e_prev, k, 2, accumulate=1)
                     g_e = g_e_prev
                 else:
-                    if self.input_shape[2] <= 8:
-                        L.call("cast_pad_bf16", b["x_in"].data_ptr(), b["x_in8"].data_ptr(), b["x_in"].numel() // self.input_shape[2],
-                               self.input_shape[2], 8)
-                        self._conv_wgrad("enc1.down", View(b["x_in8"], 0, self.input_shape[2]), g_t, k, 1)
-                    else:
-                        self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
+                    self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
 
     # ------------------------------------------------------------------ loss + optimiser
     def loss_and_grad(self, y_true, w_amp, w_ph, need_grad=True):
@@ -427,8 +419,7 @@ class UNetEngine:
         b["y_true"].copy_(y_true.reshape(b["y_true"].shape))
         npix = b["out"].numel() // 2
         L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), npix, float(w_amp), float(w_ph), 1,
-               self.losses_dev.data_ptr(), b["g_out"].data_ptr() if need_grad else None,
-               b["g_out8"].data_ptr() if need_grad else None, 8)
+               self.losses_dev.data_ptr(), b["g_out"].data_ptr() if need_grad else None, None, 0)
         return self.losses_dev
 
     def l2_loss_and_grad(self, scale):
