@@ -43,6 +43,8 @@ extern "C" {
 #define URIR_IMPL_AUTO   0    /* tcgen05 implicit GEMM when the shape qualifies, else SIMT */
 #define URIR_IMPL_SIMT   1    /* CUDA-core direct convolution                              */
 #define URIR_IMPL_TC     2    /* tcgen05 implicit GEMM or URIR_ERR_UNSUP                   */
+#define URIR_IMPL_HALO   3    /* persistent halo-tile tcgen05 kernel (stride-1 fprop/dgrad)
+                                 or URIR_ERR_UNSUP; AUTO picks it for the wide resolutions  */
 
 #define URIR_ACT_NONE    0
 #define URIR_ACT_SIGMOID 1

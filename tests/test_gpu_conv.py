@@ -300,3 +300,45 @@ def test_thin_channel_tensor_core_kernels(case):
     assert L.load().urir_conv_path(dhf, 0) == 1
     U.run_fprop(dhf, xh.cuda().to(torch.bfloat16), w_ck, w_kc, bh.cuda(), out)
     assert U.max_abs(out, torch.sigmoid(_oracle_fprop(xh, wh, bh, 1))) < 1e-5
+
+
+HALO_CASES = [
+    (2, 16, 32, 32, 32, 3),      # E1b / D5b class: 64-byte rows (swizzle-64), SBO 640
+    (2, 16, 32, 64, 32, 3),      # D5a class: 128-byte rows, SBO 1280
+    (3, 24, 48, 64, 64, 3),      # E2b / D4b class
+    (2, 24, 32, 128, 64, 3),     # D4a class: two channel chunks per tile
+    (2, 20, 40, 32, 64, 3),      # ragged tiles (H % 8 != 0, W % 16 != 0)
+    (2, 16, 16, 32, 32, 6),      # kernels=6 (pad 2,3): 13 x 21 halo box
+    (5, 72, 80, 64, 64, 3),      # more tiles than SMs: several tiles per persistent CTA, both TMEM stages
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[str(c) for c in HALO_CASES])
+def test_halo_tile_fprop_dgrad(case):
+    """conv_halo.cu: persistent CTAs, one TMA halo box per tile, taps as UMMA descriptor offsets, resident
+    weights. Forced through URIR_IMPL_HALO at small shapes (AUTO only picks it for >= 4 tiles per SM)."""
+    N, H, W, Cc, K, k = case
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, k, 1, seed=5)
+    xg, dyg = x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16)
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    d = U.conv_desc(N, H, W, Cc, K, k, 1, impl=L.IMPL_HALO)
+    y = torch.empty(N, H, W, K, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2 * K, device="cuda")
+    U.run_fprop(d, xg, w_ck, w_kc, bias.cuda(), y, stats)
+    ref = _oracle_fprop(x, w, bias, 1)
+    assert U.rel_l2(y.float(), ref) < BF16_TOL
+    assert U.max_abs(stats[:K], ref.sum(dim=(0, 1, 2))) < 2e-3 * float(ref.abs().sum(dim=(0, 1, 2)).max())
+    assert U.rel_l2(stats[K:], (ref ** 2).sum(dim=(0, 1, 2))) < F32_TOL * 10
+    # output into the right half of a concat buffer
+    cat = torch.zeros(N, H, W, 2 * K, dtype=torch.bfloat16, device="cuda")
+    d2 = U.conv_desc(N, H, W, Cc, K, k, 1, y_ld=2 * K, y_coff=K, impl=L.IMPL_HALO)
+    U.run_fprop(d2, xg, w_ck, w_kc, bias.cuda(), cat, None)
+    assert torch.equal(cat[..., K:], y) and float(cat[..., :K].float().abs().max()) == 0.0
+    # dgrad
+    xr = x.clone().requires_grad_(True)
+    gx, = torch.autograd.grad(_oracle_fprop(xr, w, None, 1), [xr], dy)
+    dx = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    dstats = torch.zeros(2 * Cc, device="cuda")
+    U.run_dgrad(d, dyg, w_ck, w_kc, None, dx, dstats)
+    assert U.rel_l2(dx.float(), gx) < BF16_TOL
+    assert U.max_abs(dstats[:Cc], gx.sum(dim=(0, 1, 2))) < 2e-3 * float(gx.abs().sum(dim=(0, 1, 2)).max())

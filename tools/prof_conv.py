@@ -23,6 +23,10 @@ CASES = {
     "dgrad_full": ("dgrad", 64, 144, 160, 32, 32, 3, 1),
     "wgrad_half": ("wgrad", 64, 72, 80, 64, 64, 3, 1),
     "fprop_half": ("fprop", 64, 72, 80, 64, 64, 3, 1),
+    "dgrad_half": ("dgrad", 64, 72, 80, 64, 64, 3, 1),
+    "fprop_d4a": ("fprop", 64, 72, 80, 128, 64, 3, 1),
+    "dgrad_d4a": ("dgrad", 64, 72, 80, 128, 64, 3, 1),
+    "dgrad_full64": ("dgrad", 64, 144, 160, 64, 32, 3, 1),
 }
 
 
@@ -38,6 +42,8 @@ def run(which, reps=int(os.environ.get("PROF_REPS", "3"))):
     w_kc = torch.randn(k * k, K, Cc, device="cuda").to(torch.bfloat16)
     dw = torch.zeros(k, k, Cc, K, device="cuda")
     d = L.ConvDesc(N, H, W, Cc, K, k, k, s, pt, pl, P, Q, Cc, 0, y_ld, 0, L.dtype_code(x), L.dtype_code(dy), L.IMPL_AUTO, 0, 0)
+    stats = torch.zeros(2 * max(Cc, K), device="cuda") if os.environ.get("PROF_STATS") and Cc > 2 and K > 2 else None
+    sp = stats.data_ptr() if stats is not None else None
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,9 +51,9 @@ def run(which, reps=int(os.environ.get("PROF_REPS", "3"))):
         if op == "wgrad":
             L.call("conv2d_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr())
         elif op == "fprop":
-            L.call("conv2d_fprop", C.byref(d), x.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, dy.data_ptr(), None)
+            L.call("conv2d_fprop", C.byref(d), x.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, dy.data_ptr(), sp)
         else:
-            L.call("conv2d_dgrad", C.byref(d), dy.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, x.data_ptr(), None)
+            L.call("conv2d_dgrad", C.byref(d), dy.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, x.data_ptr(), sp)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     fl = 2.0 * N * P * Q * K * Cc * k * k

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liburir.so")
 
 F32, BF16 = 0, 1
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_HALO = 0, 1, 2, 3
 ACT_NONE, ACT_SIGMOID = 0, 1
 
 

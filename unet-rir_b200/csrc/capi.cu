@@ -32,6 +32,8 @@ int conv_fprop_igemm(const urir_conv_desc*, const void*, const void*, const floa
 int conv_dgrad_igemm(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
 bool wgrad_tc_supported(const urir_conv_desc*);
 bool thin_supported(const urir_conv_desc*, int op);
+bool halo_supported(const urir_conv_desc*, int op, bool forced);
+int conv_halo(const urir_conv_desc*, int op, const void*, const void*, const float*, void*, float*, cudaStream_t);
 bool head_fprop_supported(const urir_conv_desc*);
 int head_fprop(const urir_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int thin_gemm(const urir_conv_desc*, const void*, const void*, const float*, void*, bool, cudaStream_t);
@@ -100,6 +102,10 @@ int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, 
         return thin_gemm(d, x, w_ck, bias, y, true, st);                       // the 2-channel stem
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && head_fprop_supported(d))
         return head_fprop(d, x, w_ck, bias, y, st);                            // the 2-channel head
+    if (d->impl == URIR_IMPL_HALO && !(w_kc && halo_supported(d, 0, true)))
+        return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the halo-tile tcgen05 path");
+    if (w_kc && ((d->impl == URIR_IMPL_HALO) || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && halo_supported(d, 0, false))))
+        return conv_halo(d, 0, x, w_kc, bias, y, stats, st);
     const bool tc_ok = igemm_fprop_supported(d) && w_kc != nullptr;
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
@@ -114,6 +120,10 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
     cudaStream_t st = (cudaStream_t)stream;
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && !bias && thin_supported(d, 1))
         return thin_gemm(d, dy, w_ck, nullptr, dx, false, st);                 // the 2-channel head
+    if (d->impl == URIR_IMPL_HALO && !(w_ck && halo_supported(d, 1, true)))
+        return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the halo-tile tcgen05 path");
+    if (w_ck && ((d->impl == URIR_IMPL_HALO) || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && halo_supported(d, 1, false))))
+        return conv_halo(d, 1, dy, w_ck, bias, dx, stats, st);
     const bool tc_ok = igemm_dgrad_supported(d) && w_ck != nullptr;
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
@@ -134,6 +144,7 @@ int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, fl
 int urir_conv_path(const urir_conv_desc* d, int op) {
     if (!d || d->impl == URIR_IMPL_SIMT || (d->impl == URIR_IMPL_AUTO && env_force_simt())) return 0;
     if (thin_supported(d, op)) return 1;
+    if (op < 2 && halo_supported(d, op, d->impl == URIR_IMPL_HALO)) return 1;
     if (op == 0 && head_fprop_supported(d)) return 1;
     if (op == 0) return igemm_fprop_supported(d) ? 1 : 0;
     if (op == 1) return igemm_dgrad_supported(d) ? 1 : 0;

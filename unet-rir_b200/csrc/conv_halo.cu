@@ -1,0 +1,341 @@
+// Persistent halo-tile implicit GEMM for the stride-1 convolutions at the wide resolutions
+// (convolutional_block_1, dl_models/u_net.py:363-371, and their input gradients under tape.gradient,
+// amp_phase_trainer.py:138): E1b / D5a / D5b at 144x160 and E2b / D4a / D4b at 72x80.
+//
+// conv_igemm.cu runs every tap as a GEMM-K iteration over its own re-fetched activation tile, one tile per
+// CTA. At these resolutions that is bound by TMA latency (the 4-deep ring of a short-lived CTA) and by
+// L2 -> SM bandwidth (9 x the activation bytes). Here:
+//   * ONE TMA box per (tile, channel chunk) brings the tile WITH its halo: {BLOCK_K ch, 8+R-1 rows, 16+S-1
+//     cols}, H fastest in shared memory. Tap (dh, dw) is not another load but another UMMA descriptor: it
+//     starts (dw * PH + dh) rows into the box with SBO = PH rows, which walks the 16 groups of 8 vertically
+//     adjacent pixels of the 8 (H) x 16 (W) output tile. The hardware swizzle is a function of the shared
+//     memory address, so any row offset works (profiles/r01_umma_halo_probe*.txt).
+//   * the whole weight tensor of the layer (all taps, <= 144 KB) is loaded once per CTA and stays resident;
+//   * CTAs are persistent (one per SM): the TMA ring runs ahead across tiles, two TMEM accumulator stages
+//     let the epilogue of tile i overlap the MMAs of tile i+1.
+// Epilogue as in conv_igemm.cu: +bias, per-channel sum / sum of squares (BatchNorm statistics or bias
+// gradients), bf16, 32-byte stores into the (possibly channel-sliced) NHWC destination.
+#include "urir_common.cuh"
+#include "urir_tc.cuh"
+
+namespace urir {
+
+using namespace tc;
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int swizzle_bytes);
+
+constexpr int HL_TH = 8, HL_TW = 16;          // output tile: 8 rows x 16 columns = 128 GEMM rows
+constexpr int HL_MAX_STAGES = 8;
+constexpr int HL_SMEM_BUDGET = 220 * 1024;
+
+struct HaloParams {
+    int N, H, W;
+    int tiles_h, tiles_w, total_tiles;
+    int PH, PW;                 // halo box extent (rows, cols)
+    int oh0, ow0;               // box origin relative to the tile origin
+    int ntaps, nchunks;         // taps, GEMM-K chunks of BLOCK_K channels
+    int stages, a_stage_bytes, a_box_bytes, w_bytes;
+    long long o_sn, o_sh, o_sw; // output element strides
+    long long o_off;
+    const float* bias;
+    float* stats;
+    __nv_bfloat16* out;
+    int n_total;
+    short tap_row[36];          // first box row of tap t = dw * PH + dh
+    short wtap[36];             // weight tap index of tap t
+};
+
+struct HaloMaps { CUtensorMap a; CUtensorMap b; };
+
+// Column sums of a [32 lanes] x [16 columns] block by recursive halving: step h exchanges half of the
+// values with lane ^ (16 >> h) and adds, so after all five steps lanes with (lane & 1) == 0 hold the total of
+// column hl_col_of_lane(lane). The steps are linear, so the epilogue runs only the first HS steps per tile,
+// accumulates the surviving 16 >> HS partial sums per block in registers across all tiles of the CTA, and
+// finishes the remaining steps once at the end (no shared-memory atomics in the tile loop).
+#define URIR_HALVE(V, OFF, CNT, BIT) { const bool up = lane & BIT; _Pragma("unroll") for (int j = 0; j < CNT; ++j) { \
+        const float send = up ? V[j] : V[j + CNT]; const float keep = up ? V[j + CNT] : V[j]; \
+        V[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF); } }
+template <int HS>
+__device__ __forceinline__ void hl_halve_head(float (&v)[16], int lane) {
+    if (HS >= 1) URIR_HALVE(v, 16, 8, 16)
+}
+template <int HS>
+__device__ __forceinline__ float hl_halve_tail(float* v, int lane) {     // v holds 16 >> HS partial sums
+    if (HS < 1) URIR_HALVE(v, 16, 8, 16)
+    URIR_HALVE(v, 8, 4, 8)
+    URIR_HALVE(v, 4, 2, 4)
+    URIR_HALVE(v, 2, 1, 2)
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int hl_col_of_lane(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(192, 1)
+conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
+    constexpr uint32_t SWZ = (BLOCK_K == 64) ? SWZ_128B : SWZ_64B;
+    constexpr uint32_t ROW_BYTES = BLOCK_K * 2;
+    constexpr uint32_t B_BYTES = BLOCK_N * ROW_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N, 0, 0);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + p.w_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + p.stages * p.a_stage_bytes);
+    uint64_t* empty_bar = full_bar + HL_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + HL_MAX_STAGES;     // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                // [2]
+    uint64_t* w_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* sstats = reinterpret_cast<float*>(tmem_slot + 2);     // [2 * BLOCK_N]
+    float* sbias = sstats + 2 * BLOCK_N;                         // [BLOCK_N]
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.y;
+    const int STAGES = p.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4); }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 4 && lane == 0) { prefetch_tmap(&maps.a); prefetch_tmap(&maps.b); }
+    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sstats[i] = 0.f;
+    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x)
+        sbias[i] = (p.bias && n_tile * BLOCK_N + i < p.n_total) ? p.bias[n_tile * BLOCK_N + i] : 0.f;
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        // resident weights: one box {BLOCK_K, BLOCK_N} per (tap, chunk), all on one barrier
+        mbar_expect_tx_elect(w_bar, (uint32_t)(p.ntaps * p.nchunks) * B_BYTES);
+        for (int t = 0; t < p.ntaps; ++t) {
+            const int wt = __shfl_sync(0xffffffffu, (int)p.wtap[t], 0);
+            for (int kc = 0; kc < p.nchunks; ++kc)
+                tma_load_3d_elect(&maps.b, w_bar, sW + (size_t)(t * p.nchunks + kc) * B_BYTES, kc * BLOCK_K, n_tile * BLOCK_N, wt);
+        }
+        int stage = 0; uint32_t phase = 0;
+        uint8_t* dst = sA;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+            const int ch = th * HL_TH + p.oh0, cw = tw * HL_TW + p.ow0;
+            for (int kc = 0; kc < p.nchunks; ++kc) {
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                mbar_expect_tx_elect(full_bar + stage, (uint32_t)p.a_box_bytes);
+                tma_load_4d_elect(&maps.a, full_bar + stage, dst, kc * BLOCK_K, ch, cw, n);
+                dst += p.a_stage_bytes;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; dst = sA; }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t a_hi = (((uint32_t)p.PH * ROW_BYTES) >> 4) | (1u << 14) | (SWZ << 29);   // SBO = PH rows
+        const uint32_t b_hi = ((8 * ROW_BYTES) >> 4) | (1u << 14) | (SWZ << 29);
+        const uint32_t w_lo = smem_u32(sW) >> 4;
+        const uint32_t a_lo0 = smem_u32(sA) >> 4;
+        const uint32_t stage16 = (uint32_t)p.a_stage_bytes >> 4;
+        mbar_wait(w_bar, 0);
+        int stage = 0; uint32_t phase = 0;
+        uint32_t a_lo = a_lo0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(tempty_bar + acc, ((it >> 1) & 1) ^ 1);
+            const uint32_t d_tm = tm0 + acc * BLOCK_N;
+            for (int kc = 0; kc < p.nchunks; ++kc) {
+                mbar_wait(full_bar + stage, phase);
+                fence_after_sync();
+                uint32_t b_lo = w_lo + ((kc * B_BYTES) >> 4);
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const uint32_t a_t = a_lo + (((uint32_t)__shfl_sync(0xffffffffu, (int)p.tap_row[t], 0) * ROW_BYTES) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        const uint64_t ad = ((uint64_t)a_hi << 32) | (a_t + 2 * k);
+                        const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + 2 * k);
+                        umma_bf16_elect(d_tm, ad, bd, IDESC, (kc | t | k) != 0);
+                    }
+                    b_lo += (p.nchunks * B_BYTES) >> 4;
+                }
+                umma_commit_elect(empty_bar + stage);
+                a_lo += stage16;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; }
+            }
+            umma_commit_elect(tfull_bar + acc);
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 0-3) =====================
+        constexpr int HS = BLOCK_N >= 64 ? 1 : 0;            // halving steps per tile (see hl_halve_head)
+        constexpr int PART = 16 >> HS;                       // partial sums kept per 16-column block
+        constexpr int NB = BLOCK_N / 16;
+        float acc1[NB * PART], acc2[NB * PART];
+#pragma unroll
+        for (int i = 0; i < NB * PART; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+        const int row = warp * 32 + lane;
+        const int ih = row & 7, iw = row >> 3;
+        const bool want_stats = p.stats != nullptr;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            int t = tile;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+            const int h = th * HL_TH + ih, w = tw * HL_TW + iw;
+            const bool valid = h < p.H && w < p.W;
+            __nv_bfloat16* orow = p.out + p.o_off + (long long)n * p.o_sn + (long long)h * p.o_sh + (long long)w * p.o_sw + n_tile * BLOCK_N;
+            mbar_wait(tfull_bar + acc, (it >> 1) & 1);
+            fence_after_sync();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                uint32_t r[16];
+                tmem_ld16(lane_addr + b * 16, r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sbias + b * 16 + 4 * j4);
+                    v[4 * j4] = __uint_as_float(r[4 * j4]) + bb.x; v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + bb.y;
+                    v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + bb.z; v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + bb.w;
+                }
+                if (valid) {
+                    *reinterpret_cast<uint4*>(orow + b * 16) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    *reinterpret_cast<uint4*>(orow + b * 16 + 8) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                }
+                if (want_stats) {
+                    float q[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { if (!valid) v[j] = 0.f; q[j] = v[j] * v[j]; }
+                    hl_halve_head<HS>(v, lane);
+                    hl_halve_head<HS>(q, lane);
+#pragma unroll
+                    for (int j = 0; j < PART; ++j) { acc1[b * PART + j] += v[j]; acc2[b * PART + j] += q[j]; }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + acc);
+        }
+        if (want_stats) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float s1 = hl_halve_tail<HS>(acc1 + b * PART, lane);
+                const float s2 = hl_halve_tail<HS>(acc2 + b * PART, lane);
+                if ((lane & 1) == 0) {
+                    const int col = b * 16 + hl_col_of_lane(lane);
+                    atomicAdd(sstats + col, s1);
+                    atomicAdd(sstats + BLOCK_N + col, s2);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (p.stats) {
+        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) {
+            const int which = i / BLOCK_N, col = i % BLOCK_N;
+            if (n_tile * BLOCK_N + col < p.n_total)
+                atomicAdd(p.stats + which * p.n_total + n_tile * BLOCK_N + col, sstats[i]);
+        }
+    }
+    if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int halo_block_k(int kg) { return kg % 64 == 0 ? 64 : 32; }
+static int halo_block_n(int n) { return n % 128 == 0 ? 128 : n % 64 == 0 ? 64 : 32; }
+
+// op 0: fprop (GEMM-K = C, GEMM-N = K), op 1: dgrad (GEMM-K = K, GEMM-N = C)
+bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
+    if (d->stride != 1 || d->P != d->H || d->Q != d->W || d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16) return false;
+    if (d->act != URIR_ACT_NONE || d->accumulate) return false;
+    if (d->R > 6 || d->S > 6 || d->R * d->S > 36) return false;
+    if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
+    const int kg = op == 0 ? d->C : d->K, ng = op == 0 ? d->K : d->C;
+    if (kg % 32 || ng % 32) return false;
+    const int BK = halo_block_k(kg), BN = halo_block_n(ng);
+    const long long w_bytes = (long long)d->R * d->S * kg * BN * 2;
+    const long long a_stage = (((long long)(HL_TH + d->R - 1) * (HL_TW + d->S - 1) * BK * 2) + 1023) / 1024 * 1024;
+    if (w_bytes + 3 * a_stage + 2048 > HL_SMEM_BUDGET) return false;
+    // worth it only where the one-tile-per-CTA kernel is latency / L2 bound: many tiles per SM
+    const long long tiles = (long long)d->N * cdiv(d->H, HL_TH) * cdiv(d->W, HL_TW);
+    return forced || tiles >= 148 * 4;
+}
+
+template <int BN, int BK>
+static int launch_halo(const HaloMaps& maps, const HaloParams& p, int n_tiles, int smem, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = conv_halo_kernel<BN, BK>;
+    if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BUDGET + 4096)); attr_set = true; }
+    int gx = 148 / n_tiles; if (gx < 1) gx = 1;
+    if (gx > p.total_tiles) gx = p.total_tiles;
+    dim3 grid(gx, n_tiles);
+    kern<<<grid, 192, smem, st>>>(maps, p);
+    URIR_LAUNCH_OK(1);
+    return URIR_OK;
+}
+
+// a = activation side read through the halo box (x for fprop, dy for dgrad); w = [tap][GEMM-N][GEMM-K] bf16
+int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, const float* bias, void* out, float* stats,
+              cudaStream_t st) {
+    URIR_CHECK_ARG(w != nullptr, "halo conv needs the [tap][N][K] weight layout");
+    const int kg = op == 0 ? d->C : d->K, ng = op == 0 ? d->K : d->C;
+    const int a_ld = op == 0 ? d->x_ld : d->y_ld, a_coff = op == 0 ? d->x_coff : d->y_coff;
+    const int o_ld = op == 0 ? d->y_ld : d->x_ld, o_coff = op == 0 ? d->y_coff : d->x_coff;
+    const int BK = halo_block_k(kg), BN = halo_block_n(ng);
+    HaloMaps maps; HaloParams p; memset(&p, 0, sizeof(p));
+    p.N = d->N; p.H = d->H; p.W = d->W;
+    p.tiles_h = cdiv(d->H, HL_TH); p.tiles_w = cdiv(d->W, HL_TW); p.total_tiles = p.tiles_h * p.tiles_w * d->N;
+    p.PH = HL_TH + d->R - 1; p.PW = HL_TW + d->S - 1;
+    p.ntaps = d->R * d->S; p.nchunks = kg / BK;
+    p.a_box_bytes = p.PH * p.PW * BK * 2;
+    p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+    p.w_bytes = p.ntaps * kg * BN * 2;
+    p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
+    if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
+    if (p.stages < 2) return fail(URIR_ERR_UNSUP, "halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
+    p.o_sn = (long long)d->H * d->W * o_ld; p.o_sh = (long long)d->W * o_ld; p.o_sw = o_ld; p.o_off = o_coff;
+    p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)out; p.n_total = ng;
+    if (op == 0) { p.oh0 = -d->pad_top; p.ow0 = -d->pad_left; }
+    else { p.oh0 = d->pad_top - (d->R - 1); p.ow0 = d->pad_left - (d->S - 1); }
+    for (int r = 0; r < d->R; ++r)
+        for (int s = 0; s < d->S; ++s) {
+            const int t = r * d->S + s;
+            const int dh = op == 0 ? r : d->R - 1 - r, dw = op == 0 ? s : d->S - 1 - s;
+            p.tap_row[t] = (short)(dw * p.PH + dh);
+            p.wtap[t] = (short)t;
+        }
+    {   // activation: dims (C, H, W, N) so that H is the fastest pixel index of the box in shared memory
+        const uint64_t dims[4] = {(uint64_t)kg, (uint64_t)d->H, (uint64_t)d->W, (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)d->W * a_ld * 2, (uint64_t)a_ld * 2, (uint64_t)d->H * d->W * a_ld * 2};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.PH, (uint32_t)p.PW, 1};
+        int rc = encode_map(&maps.a, (const char*)a + (size_t)a_coff * 2, 4, dims, strides, box, BK * 2);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)kg, (uint64_t)ng, (uint64_t)p.ntaps};
+        const uint64_t strides[2] = {(uint64_t)kg * 2, (uint64_t)kg * ng * 2};
+        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+        int rc = encode_map(&maps.b, w, 3, dims, strides, box, BK * 2);
+        if (rc) return rc;
+    }
+    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 5) * 8 + 16 + 3 * BN * 4 + 1024;
+    const int n_tiles = ng / BN;
+#define URIR_HL(BN_, BK_) if (BN == BN_ && BK == BK_) return launch_halo<BN_, BK_>(maps, p, n_tiles, smem, st);
+    URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
+#undef URIR_HL
+    return fail(URIR_ERR_UNSUP, "halo conv: no kernel for BLOCK_N=%d BLOCK_K=%d", BN, BK);
+}
+
+}  // namespace urir
