@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) bench(Cfg c, int iters, long long* out) {
         for (int k = 0; k < 4; ++k) {
             bd[k] = make_smem_desc(b0 + k * c.b_step, c.b_lbo, c.b_sbo, c.b_swz);
 #pragma unroll
-            for (int j = 0; j < NACC; ++j) ad[k][j] = make_smem_desc(a0 + j * c.a_stride_acc + k * c.a_step, c.a_lbo, c.a_sbo, c.a_swz);
+            for (int j = 0; j < NACC; ++j) ad[k][j] = make_smem_desc(a0 + (NACC == 1 ? c.a_stride_acc : j * c.a_stride_acc) + k * c.a_step, c.a_lbo, c.a_sbo, c.a_swz);
         }
         long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
@@ -60,6 +60,16 @@ static void run(const char* name, Cfg c, int iters = 2000) {
 }
 
 int main() {
+    // halo-style A operands (conv_halo.cu): start rows not aligned to the 8-row swizzle group, SBO = 10 rows
+    for (int N : {32, 64, 128}) {
+        for (int off_rows : {0, 1, 3, 10, 11}) {
+            char nm[96];
+            snprintf(nm, sizeof(nm), "halo K-major SW64  SBO=640  start +%d rows (A), B aligned", off_rows);
+            run(nm, {N, 0, 0, SWZ_64B, SWZ_64B, 0, 640, 0, 512, 32, 32, 1, 8192 + off_rows * 64});
+            snprintf(nm, sizeof(nm), "halo K-major SW128 SBO=1280 start +%d rows (A), B aligned", off_rows);
+            run(nm, {N, 0, 0, SWZ_128B, SWZ_128B, 0, 1280, 0, 1024, 32, 32, 1, 16384 + off_rows * 128});
+        }
+    }
     for (int N : {32, 64, 128, 256}) {
         for (int nacc : {1, 3}) {
             if (N * nacc > 512) continue;

@@ -13,8 +13,11 @@
 //   * the whole weight tensor of the layer (all taps, <= 144 KB) is loaded once per CTA and stays resident;
 //   * CTAs are persistent (one per SM): the TMA ring runs ahead across tiles, two TMEM accumulator stages
 //     let the epilogue of tile i overlap the MMAs of tile i+1.
+// Warp roles (384 threads): warp 4 TMA producer; warps 5-6 MMA issuers alternating tiles; warps 0-3 and 8-11
+// two epilogue groups (TMEM lane quarter = warp % 4), group g draining TMEM stage g = the tiles of issuer g.
 // Epilogue as in conv_igemm.cu: +bias, per-channel sum / sum of squares (BatchNorm statistics or bias
 // gradients), bf16, 32-byte stores into the (possibly channel-sliced) NHWC destination.
+#include <stdlib.h>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -42,6 +45,7 @@ struct HaloParams {
     float* stats;
     __nv_bfloat16* out;
     int n_total;
+    long long* trace;           // debug (URIR_HALO_TRACE): clock64 stamps of CTA 0, 8 per tile, first 128 tiles
     short tap_row[36];          // first box row of tap t = dw * PH + dh
     short wtap[36];             // weight tap index of tap t
 };
@@ -59,24 +63,51 @@ struct HaloMaps { CUtensorMap a; CUtensorMap b; };
 template <int HS>
 __device__ __forceinline__ void hl_halve_head(float (&v)[16], int lane) {
     if (HS >= 1) URIR_HALVE(v, 16, 8, 16)
+    if (HS >= 2) URIR_HALVE(v, 8, 4, 8)
 }
 template <int HS>
 __device__ __forceinline__ float hl_halve_tail(float* v, int lane) {     // v holds 16 >> HS partial sums
     if (HS < 1) URIR_HALVE(v, 16, 8, 16)
-    URIR_HALVE(v, 8, 4, 8)
+    if (HS < 2) URIR_HALVE(v, 8, 4, 8)
     URIR_HALVE(v, 4, 2, 4)
     URIR_HALVE(v, 2, 1, 2)
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
+// 4 x 4 transpose of 16-byte chunks across the 4 lanes of a group: in  pk[4c .. 4c+3] = chunk c of this lane's pixel,
+// out pk[4i .. 4i+3] = chunk (lane & 3) of pixel i of the group.
+__device__ __forceinline__ void hl_transpose4(uint32_t (&pk)[16], int lane) {
+    {   // exchange with lane ^ 1 inside chunk pairs (0,1) and (2,3)
+        const bool odd = lane & 1;
+#pragma unroll
+        for (int c = 0; c < 4; c += 2)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t send = odd ? pk[4 * c + e] : pk[4 * (c + 1) + e];
+                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1);
+                if (odd) pk[4 * c + e] = got; else pk[4 * (c + 1) + e] = got;
+            }
+    }
+    {   // exchange with lane ^ 2 between chunk pairs (0,2) and (1,3)
+        const bool hi = lane & 2;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t send = hi ? pk[4 * c + e] : pk[4 * (c + 2) + e];
+                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 2);
+                if (hi) pk[4 * c + e] = got; else pk[4 * (c + 2) + e] = got;
+            }
+    }
+}
 __device__ __forceinline__ int hl_col_of_lane(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
 
 template <int BLOCK_N, int BLOCK_K>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
     constexpr uint32_t SWZ = (BLOCK_K == 64) ? SWZ_128B : SWZ_64B;
     constexpr uint32_t ROW_BYTES = BLOCK_K * 2;
     constexpr uint32_t B_BYTES = BLOCK_N * ROW_BYTES;
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    constexpr uint32_t TMEM_COLS = 4 * BLOCK_N;             // four accumulator stages (two per issuer / epilogue group)
     constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N, 0, 0);
 
     extern __shared__ uint8_t smem_raw[];
@@ -85,9 +116,9 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     uint8_t* sA = smem + p.w_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + p.stages * p.a_stage_bytes);
     uint64_t* empty_bar = full_bar + HL_MAX_STAGES;
-    uint64_t* tfull_bar = empty_bar + HL_MAX_STAGES;     // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;                // [2]
-    uint64_t* w_bar = tempty_bar + 2;
+    uint64_t* tfull_bar = empty_bar + HL_MAX_STAGES;     // [4]
+    uint64_t* tempty_bar = tfull_bar + 4;                // [4]
+    uint64_t* w_bar = tempty_bar + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* sstats = reinterpret_cast<float*>(tmem_slot + 2);     // [2 * BLOCK_N]
     float* sbias = sstats + 2 * BLOCK_N;                         // [BLOCK_N]
@@ -95,10 +126,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int n_tile = blockIdx.y;
     const int STAGES = p.stages;
+    long long trace_c0 = 0; unsigned long long trace_g0 = 0;
+    if (p.trace && threadIdx.x == 0) { trace_c0 = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(trace_g0)); }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4); }
+        for (int a = 0; a < 4; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
@@ -128,16 +161,25 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; const int n = t / p.tiles_h;
             const int ch = th * HL_TH + p.oh0, cw = tw * HL_TW + p.ow0;
+            const int itp = (tile - blockIdx.x) / gridDim.x;
+            const bool trp = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && itp < 128 && lane == 0;
             for (int kc = 0; kc < p.nchunks; ++kc) {
+                (void)trp;
                 mbar_wait(empty_bar + stage, phase ^ 1);
                 mbar_expect_tx_elect(full_bar + stage, (uint32_t)p.a_box_bytes);
                 tma_load_4d_elect(&maps.a, full_bar + stage, dst, kc * BLOCK_K, ch, cw, n);
+
                 dst += p.a_stage_bytes;
                 if (++stage == STAGES) { stage = 0; phase ^= 1; dst = sA; }
             }
         }
-    } else if (warp == 5) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 5 || warp == 6) {
+        // ===================== MMA issuers (warps 5 and 6) =====================
+        // Two issuing warps alternate tiles (warp 5 + mw owns the tiles with it % 2 == mw and TMEM stage mw).
+        // An mbarrier wait costs ~200 cycles even when the barrier is already complete and the tensor pipe's
+        // issue queue is shallow, so a single issuer leaves the pipe idle ~400 cycles per tile (measured with
+        // URIR_HALO_TRACE); with two, one warp's waits overlap the other's MMAs.
+        const int mw = warp - 5;
         const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t a_hi = (((uint32_t)p.PH * ROW_BYTES) >> 4) | (1u << 14) | (SWZ << 29);   // SBO = PH rows
         const uint32_t b_hi = ((8 * ROW_BYTES) >> 4) | (1u << 14) | (SWZ << 29);
@@ -149,11 +191,19 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         uint32_t a_lo = a_lo0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            mbar_wait(tempty_bar + acc, ((it >> 1) & 1) ^ 1);
+            if ((it & 1) != mw) {           // the other issuer's tile: step over its stages
+                for (int kc = 0; kc < p.nchunks; ++kc) { a_lo += stage16; if (++stage == STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; } }
+                continue;
+            }
+            const int acc = it & 3;                  // stages {mw, mw + 2}
+            const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 128 && lane == 0;
+            if (trm) p.trace[it * 8 + 0] = clock64();
+            mbar_wait(tempty_bar + acc, ((it >> 2) & 1) ^ 1);
+            if (trm) p.trace[it * 8 + 1] = clock64();
             const uint32_t d_tm = tm0 + acc * BLOCK_N;
             for (int kc = 0; kc < p.nchunks; ++kc) {
                 mbar_wait(full_bar + stage, phase);
+                if (trm && kc == p.nchunks - 1) p.trace[it * 8 + 2] = clock64();
                 fence_after_sync();
                 uint32_t b_lo = w_lo + ((kc * B_BYTES) >> 4);
                 for (int t = 0; t < p.ntaps; ++t) {
@@ -172,59 +222,96 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             }
             umma_commit_elect(tfull_bar + acc);
             __syncwarp();
+            if (trm) p.trace[it * 8 + 3] = clock64();
         }
-    } else {
-        // ===================== epilogue (warps 0-3) =====================
-        constexpr int HS = BLOCK_N >= 64 ? 1 : 0;            // halving steps per tile (see hl_halve_head)
+    } else if (warp < 4 || warp >= 8) {
+        // ===================== epilogue: group 0 = warps 0-3 (even tiles), group 1 = warps 8-11 (odd tiles) ====
+        // one tile's epilogue is a ~900-cycle latency chain (barrier wait, TMEM loads, stores); two groups give
+        // each of them two tile times to finish it
+        const int eg = warp >= 8 ? 1 : 0;
+        const int quarter = warp & 3;
+        constexpr int HS = BLOCK_N >= 128 ? 2 : BLOCK_N >= 64 ? 1 : 0;   // halving steps per tile (see hl_halve_head)
         constexpr int PART = 16 >> HS;                       // partial sums kept per 16-column block
         constexpr int NB = BLOCK_N / 16;
         float acc1[NB * PART], acc2[NB * PART];
 #pragma unroll
         for (int i = 0; i < NB * PART; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
-        const int row = warp * 32 + lane;
+        const int row = quarter * 32 + lane;
         const int ih = row & 7, iw = row >> 3;
         const bool want_stats = p.stats != nullptr;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
+        int it = eg;
+        for (int tile = blockIdx.x + eg * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+            const int acc = it & 3;
             int t = tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; const int n = t / p.tiles_h;
             const int h = th * HL_TH + ih, w = tw * HL_TW + iw;
             const bool valid = h < p.H && w < p.W;
-            __nv_bfloat16* orow = p.out + p.o_off + (long long)n * p.o_sn + (long long)h * p.o_sh + (long long)w * p.o_sw + n_tile * BLOCK_N;
-            mbar_wait(tfull_bar + acc, (it >> 1) & 1);
+            // the 4 pixels whose chunks this lane stores after the transpose: rows 4 * (lane / 4) + i of the quarter
+            __nv_bfloat16* gout[4]; bool gvalid[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = quarter * 32 + (lane & ~3) + i;
+                const int hh = th * HL_TH + (m & 7), ww = tw * HL_TW + (m >> 3);
+                gvalid[i] = hh < p.H && ww < p.W;
+                gout[i] = p.out + p.o_off + (long long)n * p.o_sn + (long long)hh * p.o_sh + (long long)ww * p.o_sw + n_tile * BLOCK_N;
+            }
+            uint32_t pk[16];
+            const bool tre = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 128 && quarter == 0 && lane == 0;
+            mbar_wait(tfull_bar + acc, (it >> 2) & 1);
+            if (tre) p.trace[it * 8 + 4] = clock64();
             fence_after_sync();
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+            // TMEM loads have a long latency while the tensor pipe is streaming MMAs (the dominant epilogue stall
+            // in the ncu source view), so all loads of a phase (<= 64 columns) are issued before one wait.
+            constexpr int PH_COLS = BLOCK_N < 64 ? BLOCK_N : 64;
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + b * 16, r);
+            for (int ph = 0; ph < BLOCK_N / PH_COLS; ++ph) {
+                uint32_t r[PH_COLS];
+#pragma unroll
+                for (int c = 0; c < PH_COLS / 32; ++c) tmem_ld32(lane_addr + ph * PH_COLS + c * 32, r + c * 32);
                 tmem_ld_wait();
-                float v[16];
+                if (tre && ph == 0) p.trace[it * 8 + 6] = clock64();
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(sbias + b * 16 + 4 * j4);
-                    v[4 * j4] = __uint_as_float(r[4 * j4]) + bb.x; v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + bb.y;
-                    v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + bb.z; v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + bb.w;
-                }
-                if (valid) {
-                    *reinterpret_cast<uint4*>(orow + b * 16) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                    *reinterpret_cast<uint4*>(orow + b * 16 + 8) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-                }
-                if (want_stats) {
-                    float q[16];
+                for (int bb = 0; bb < PH_COLS / 16; ++bb) {
+                    const int b = ph * (PH_COLS / 16) + bb;
+                    float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { if (!valid) v[j] = 0.f; q[j] = v[j] * v[j]; }
-                    hl_halve_head<HS>(v, lane);
-                    hl_halve_head<HS>(q, lane);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 bs = *reinterpret_cast<const float4*>(sbias + b * 16 + 4 * j4);
+                        v[4 * j4] = __uint_as_float(r[bb * 16 + 4 * j4]) + bs.x; v[4 * j4 + 1] = __uint_as_float(r[bb * 16 + 4 * j4 + 1]) + bs.y;
+                        v[4 * j4 + 2] = __uint_as_float(r[bb * 16 + 4 * j4 + 2]) + bs.z; v[4 * j4 + 3] = __uint_as_float(r[bb * 16 + 4 * j4 + 3]) + bs.w;
+                    }
+                    pk[(b & 1) * 8 + 0] = pack_bf16x2(v[0], v[1]); pk[(b & 1) * 8 + 1] = pack_bf16x2(v[2], v[3]);
+                    pk[(b & 1) * 8 + 2] = pack_bf16x2(v[4], v[5]); pk[(b & 1) * 8 + 3] = pack_bf16x2(v[6], v[7]);
+                    pk[(b & 1) * 8 + 4] = pack_bf16x2(v[8], v[9]); pk[(b & 1) * 8 + 5] = pack_bf16x2(v[10], v[11]);
+                    pk[(b & 1) * 8 + 6] = pack_bf16x2(v[12], v[13]); pk[(b & 1) * 8 + 7] = pack_bf16x2(v[14], v[15]);
+                    if (b & 1) {
+                        // 32 channels = four 16-byte chunks per pixel. Transpose them across the 4 lanes of a group so
+                        // that store i writes chunk (lane & 3) of pixel (group, i): 64 contiguous bytes per lane group
+                        // (full sectors) instead of four scattered 16-byte pieces.
+                        hl_transpose4(pk, lane);
+                        const int c32 = (b >> 1) * 32 + (lane & 3) * 8;
 #pragma unroll
-                    for (int j = 0; j < PART; ++j) { acc1[b * PART + j] += v[j]; acc2[b * PART + j] += q[j]; }
+                        for (int i = 0; i < 4; ++i)
+                            if (gvalid[i]) *reinterpret_cast<uint4*>(gout[i] + c32) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                    }
+                    if (want_stats) {
+                        float q[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { if (!valid) v[j] = 0.f; q[j] = v[j] * v[j]; }
+                        hl_halve_head<HS>(v, lane);
+                        hl_halve_head<HS>(q, lane);
+#pragma unroll
+                        for (int j = 0; j < PART; ++j) { acc1[b * PART + j] += v[j]; acc2[b * PART + j] += q[j]; }
+                    }
                 }
             }
+            if (tre) p.trace[it * 8 + 7] = clock64();
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + acc);
+            if (tre) p.trace[it * 8 + 5] = clock64();
         }
         if (want_stats) {
 #pragma unroll
@@ -248,6 +335,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         }
     }
     if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (p.trace && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 148) {
+        unsigned long long g1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+        p.trace[1024 + 2 * blockIdx.x] = clock64() - trace_c0;
+        p.trace[1024 + 2 * blockIdx.x + 1] = (long long)(g1 - trace_g0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -281,7 +373,7 @@ static int launch_halo(const HaloMaps& maps, const HaloParams& p, int n_tiles, i
     int gx = 148 / n_tiles; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     dim3 grid(gx, n_tiles);
-    kern<<<grid, 192, smem, st>>>(maps, p);
+    kern<<<grid, 384, smem, st>>>(maps, p);
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }
@@ -307,6 +399,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     if (p.stages < 2) return fail(URIR_ERR_UNSUP, "halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
     p.o_sn = (long long)d->H * d->W * o_ld; p.o_sh = (long long)d->W * o_ld; p.o_sw = o_ld; p.o_off = o_coff;
     p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)out; p.n_total = ng;
+    { const char* e = getenv("URIR_HALO_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr; }
     if (op == 0) { p.oh0 = -d->pad_top; p.ow0 = -d->pad_left; }
     else { p.oh0 = d->pad_top - (d->R - 1); p.ow0 = d->pad_left - (d->S - 1); }
     for (int r = 0; r < d->R; ++r)
@@ -330,7 +423,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
         int rc = encode_map(&maps.b, w, 3, dims, strides, box, BK * 2);
         if (rc) return rc;
     }
-    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 5) * 8 + 16 + 3 * BN * 4 + 1024;
+    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
     const int n_tiles = ng / BN;
 #define URIR_HL(BN_, BK_) if (BN == BN_ && BK == BK_) return launch_halo<BN_, BK_>(maps, p, n_tiles, smem, st);
     URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
