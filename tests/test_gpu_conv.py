@@ -342,3 +342,36 @@ def test_halo_tile_fprop_dgrad(case):
     U.run_dgrad(d, dyg, w_ck, w_kc, None, dx, dstats)
     assert U.rel_l2(dx.float(), gx) < BF16_TOL
     assert U.max_abs(dstats[:Cc], gx.sum(dim=(0, 1, 2))) < 2e-3 * float(gx.abs().sum(dim=(0, 1, 2)).max())
+
+
+WGRAD_HALO_CASES = [
+    (2, 16, 32, 32, 32),      # E1b / D5b class: one MMA (M = 4 vertical slots x 32 ch, N = 3 x 32) per 16 pixels
+    (2, 16, 32, 64, 32),      # D5a class: 128-byte x rows, two MMAs (vertical taps {0,1} and {2})
+    (3, 24, 48, 64, 64),      # E2b / D4b class: N = 192
+    (2, 24, 32, 128, 64),     # D4a class: two 64-channel x blocks (grid.y = 2)
+    (5, 72, 80, 64, 64),      # many tiles per persistent CTA (ring wrap-around)
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_HALO_CASES, ids=[str(c) for c in WGRAD_HALO_CASES])
+def test_halo_tile_wgrad(case):
+    """conv_wgrad_halo.cu: all nine taps from one x halo box (vertical taps stacked along GEMM-M) and one dy halo
+    box (horizontal taps stacked along GEMM-N). Also with x and dy living inside wider (concat) buffers."""
+    N, H, W, Cc, K = case
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, 3, 1, seed=11)
+    xr, wr = x.clone(), w.clone().requires_grad_(True)
+    gw, = torch.autograd.grad(_oracle_fprop(xr, wr, None, 1), [wr], dy)
+    d = U.conv_desc(N, H, W, Cc, K, 3, 1, impl=L.IMPL_HALO)
+    assert L.load().urir_conv_path(d, 2) == 1
+    dw = torch.full((3, 3, Cc, K), 3.0, device="cuda")
+    U.run_wgrad(d, x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16), dw)
+    assert U.rel_l2(dw, gw) < F32_TOL
+    # operands as channel slices of wider buffers (skip-concat layout)
+    xw = torch.randn(N, H, W, Cc + 32).to(torch.bfloat16).cuda()
+    xw[..., 32:] = x.cuda().to(torch.bfloat16)
+    dyw = torch.randn(N, H, W, 2 * K).to(torch.bfloat16).cuda()
+    dyw[..., :K] = dy.cuda().to(torch.bfloat16)
+    d2 = U.conv_desc(N, H, W, Cc, K, 3, 1, x_ld=Cc + 32, x_coff=32, y_ld=2 * K, y_coff=0, impl=L.IMPL_HALO)
+    dw2 = torch.zeros(3, 3, Cc, K, device="cuda")
+    U.run_wgrad(d2, xw, dyw, dw2)
+    assert U.rel_l2(dw2, gw) < F32_TOL

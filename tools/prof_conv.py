@@ -27,6 +27,10 @@ CASES = {
     "fprop_d4a": ("fprop", 64, 72, 80, 128, 64, 3, 1),
     "dgrad_d4a": ("dgrad", 64, 72, 80, 128, 64, 3, 1),
     "dgrad_full64": ("dgrad", 64, 144, 160, 64, 32, 3, 1),
+    "wgrad_full64": ("wgrad", 64, 144, 160, 64, 32, 3, 1),
+    "wgrad_d4a": ("wgrad", 64, 72, 80, 128, 64, 3, 1),
+    "dgrad_s2_half": ("dgrad", 64, 72, 80, 64, 128, 3, 2),
+    "fprop_s2": ("fprop", 64, 144, 160, 32, 64, 3, 2),
 }
 
 

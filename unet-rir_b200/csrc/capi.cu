@@ -39,6 +39,8 @@ int head_fprop(const urir_conv_desc*, const void*, const void*, const float*, vo
 int thin_gemm(const urir_conv_desc*, const void*, const void*, const float*, void*, bool, cudaStream_t);
 int thin_wgrad(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int conv_wgrad_tc(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
+bool wgrad_halo_supported(const urir_conv_desc*, bool forced);
+int conv_wgrad_halo(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int bn_finalize(const float*, double, const float*, const float*, float*, float*, float, float, int, float*, float*, int, cudaStream_t);
 int bn_relu_fwd(const void*, int, int, const float*, void*, int, int, long long, int, int, cudaStream_t);
 int bn_relu_bwd_reduce(const void*, int, int, const void*, int, int, const float*, const float*, float*, long long, int, cudaStream_t);
@@ -135,6 +137,10 @@ int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, fl
     URIR_CHECK_ARG(x && dy && dw, "conv2d_wgrad: null tensor");
     cudaStream_t st = (cudaStream_t)stream;
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && thin_supported(d, 2)) return thin_wgrad(d, x, dy, dw, st);
+    if (d->impl == URIR_IMPL_HALO && !wgrad_halo_supported(d, true))
+        return fail(URIR_ERR_UNSUP, "conv2d_wgrad: shape not supported by the halo-tile tcgen05 path");
+    if (d->impl == URIR_IMPL_HALO || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && wgrad_halo_supported(d, false)))
+        return conv_wgrad_halo(d, x, dy, dw, st);
     const bool tc_ok = wgrad_tc_supported(d);
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_wgrad: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
@@ -145,6 +151,7 @@ int urir_conv_path(const urir_conv_desc* d, int op) {
     if (!d || d->impl == URIR_IMPL_SIMT || (d->impl == URIR_IMPL_AUTO && env_force_simt())) return 0;
     if (thin_supported(d, op)) return 1;
     if (op < 2 && halo_supported(d, op, d->impl == URIR_IMPL_HALO)) return 1;
+    if (op == 2 && wgrad_halo_supported(d, d->impl == URIR_IMPL_HALO)) return 1;
     if (op == 0 && head_fprop_supported(d)) return 1;
     if (op == 0) return igemm_fprop_supported(d) ? 1 : 0;
     if (op == 1) return igemm_dgrad_supported(d) ? 1 : 0;

@@ -1,0 +1,245 @@
+// Persistent halo-tile weight-gradient kernel (tcgen05, sm_100a) for the 3x3 stride-1 convolutions at the wide
+// resolutions (convolutional_block_1, dl_models/u_net.py:363-371, under tape.gradient, amp_phase_trainer.py:138):
+//   dw[dh][dw][c][k] = sum over pixels (h, w) of  x[h + dh - 1, w + dw - 1][c] * dy[h, w][k]
+//
+// conv_wgrad_tc.cu stages one shifted x tile per tap (9 x the activation bytes through L2 -> shared memory) and
+// issues one N = 32/64 MMA per 3 taps, which costs 44-48 cycles whatever N is. Here ALL NINE taps come out of two
+// boxes per pixel tile and (for 32-channel layers) ONE instruction per 16 pixels:
+//   * substitute w' = w + dw - 1:  dw[dh][dw] = sum over (h, w') of x[h + dh - 1, w'] * dy[h, w' - dw + 1];
+//     out-of-range x or dy rows are TMA zero fill, which is exactly the SAME padding.
+//   * the pixel tile is 8 (h) x 16 (w'), GEMM-K = pixels, both operands MN-major straight from NHWC, H fastest in
+//     shared memory: x box {Cc ch, 10 rows, 16 cols} (one halo row above/below), dy box {KN ch, 8 rows, 18 cols}
+//     (one halo column left/right). A K-group of 8 pixels = 8 vertically adjacent pixels of one column.
+//   * the vertical taps are stacked along GEMM-M: "atom" j of the A descriptor starts j rows lower (LBO = one row,
+//     SBO = 10 rows = next column), so M = 128 = 4 (or 2) overlapping views of the same x box;
+//   * the horizontal taps are stacked along GEMM-N: atom i of the B descriptor starts i columns further right
+//     (LBO = SBO = 8 rows = one column), so N = 3 * KN overlapping views of the same dy box.
+//   The overlap is legal because the UMMA swizzle is a function of the shared-memory address
+//   (profiles/r01_umma_halo_probe.txt, tools/umma_halo_test2.cu mode 2).
+// Every activation byte is staged once (152 B per pixel instead of 768) and the MMA count drops 3-6 x; the
+// layers become HBM-bound. CTAs are persistent (one per SM, grid.y = blocks of Cc x-channels), accumulate their
+// whole pixel range in TMEM and add it into dw with red.global.add.v4.f32 once at the end.
+// Warp roles (192 threads): warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer.
+#include <stdlib.h>
+#include "urir_common.cuh"
+#include "urir_tc.cuh"
+
+namespace urir {
+
+using namespace tc;
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int swizzle_bytes);
+
+constexpr int WH_TH = 8, WH_TW = 16;         // pixel tile (h, w')
+constexpr int WH_PH = WH_TH + 2;             // x box rows (vertical halo)
+constexpr int WH_PW = WH_TW + 2;             // dy box columns (horizontal halo)
+constexpr int WH_MAX_STAGES = 8;
+constexpr int WH_SMEM_BUDGET = 200 * 1024;
+
+struct WhaloParams {
+    int tiles_w, tiles_h, total_tiles;
+    int C, Cc;                  // x channels in total / per CTA (32 or 64)
+    int n_mma;                  // MMAs per k-step: 1 (Cc = 32: 4 vertical slots) or 2 (Cc = 64: 2 slots each)
+    int stages, stage_bytes, a_bytes, tx_bytes;
+    int tmem_cols;
+    int debug;                  // URIR_WH_DEBUG: 1 = skip the epilogue adds, 2 = do not rotate the epilogue order
+    float* dw;
+};
+
+struct WhaloMaps { CUtensorMap a; CUtensorMap b; };
+
+__device__ __forceinline__ void wh_red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int KN>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ WhaloMaps maps, const __grid_constant__ WhaloParams p) {
+    constexpr int N = 3 * KN;
+    constexpr uint32_t IDESC = make_idesc_bf16(128, N, 1, 1);
+    constexpr uint32_t B_ROW = KN * 2;
+    constexpr uint32_t B_SWZ = KN == 64 ? SWZ_128B : SWZ_64B;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // one spare KB after the ring: the unused 4th vertical slot of the last column reads one row past its box
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes + 1024);
+    uint64_t* empty_bar = full_bar + WH_MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + WH_MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int cblk = blockIdx.y;
+    const int STAGES = p.stages;
+    const int n_iters = blockIdx.x < p.total_tiles ? (p.total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (warp == 4 && lane == 0) { prefetch_tmap(&maps.a); prefetch_tmap(&maps.b); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer: two boxes per pixel tile =====================
+        int stage = 0; uint32_t phase = 0;
+        uint8_t* dst = smem;
+        const int c0 = cblk * p.Cc;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+            const int h0 = th * WH_TH, w0 = tw * WH_TW;
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            mbar_expect_tx_elect(full_bar + stage, (uint32_t)p.tx_bytes);
+            tma_load_4d_elect(&maps.a, full_bar + stage, dst, c0, h0 - 1, w0, n);
+            tma_load_4d_elect(&maps.b, full_bar + stage, dst + p.a_bytes, 0, h0, w0 - 1, n);
+            dst += p.stage_bytes;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; dst = smem; }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t a_row = p.Cc * 2;
+        const uint32_t a_swz = p.Cc == 64 ? SWZ_128B : SWZ_64B;
+        const uint32_t a_col = WH_PH * a_row, b_col = WH_TH * B_ROW;          // bytes per pixel column of the boxes
+        const uint32_t a_hi = (a_col >> 4) | (1u << 14) | (a_swz << 29);       // SBO = next column of the x box
+        const uint32_t b_hi = (b_col >> 4) | (1u << 14) | (B_SWZ << 29);       // SBO = next column of the dy box
+        const uint32_t a_lo0 = ((a_row >> 4) << 16) | (smem_u32(smem) >> 4);   // LBO = one row down  (vertical tap)
+        const uint32_t b_lo0 = ((b_col >> 4) << 16) | ((smem_u32(smem) + p.a_bytes) >> 4);   // LBO = one column right
+        const uint32_t a_k16 = (2 * a_col) >> 4, b_k16 = (2 * b_col) >> 4;     // one k-step = 2 pixel columns
+        const uint32_t a_j16 = (2 * a_row) >> 4;                               // second MMA of a 64-channel block: taps 2,(3)
+        const uint32_t stage16 = p.stage_bytes >> 4;
+        const int n_mma = p.n_mma;
+        int stage = 0; uint32_t phase = 0, soff = 0;
+        for (int it = 0; it < n_iters; ++it) {
+            mbar_wait(full_bar + stage, phase);
+            fence_after_sync();
+#pragma unroll
+            for (int k = 0; k < WH_TW / 2; ++k) {
+                const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + soff + k * b_k16);
+                const uint32_t acc = (it != 0) | (k != 0);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j < n_mma) {
+                        const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + soff + k * a_k16 + j * a_j16);
+                        umma_bf16_elect(tm0 + j * N, ad, bd, IDESC, acc);
+                    }
+                }
+            }
+            umma_commit_elect(empty_bar + stage);
+            if (it == n_iters - 1) umma_commit_elect(tmem_full_bar);
+            __syncwarp();
+            soff += stage16;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; soff = 0; }
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue: TMEM -> red.global.add into dw[tap][c][k] =====================
+        if (n_iters > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            fence_after_sync();
+            const int row = warp * 32 + lane;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const int slot = row / p.Cc, c = row % p.Cc;
+            // all CTAs add into the same 9*C*K floats: start each CTA at a different (accumulator, horizontal tap)
+            // so that concurrent reductions hit different addresses
+            const int n_units = p.n_mma * 3;
+            const int u0 = p.debug == 2 ? 0 : blockIdx.x % n_units;
+#pragma unroll 1
+            for (int uu = 0; uu < n_units; ++uu) {
+                int u = uu + u0; if (u >= n_units) u -= n_units;
+                const int j = u / 3, i = u - 3 * j;
+                const int dh = p.Cc == 32 ? slot : 2 * j + slot;
+                const bool valid = dh < 3 && p.debug != 1;
+                {
+                    const int tap = (valid ? dh : 0) * 3 + (2 - i);              // B atom i <-> horizontal tap 2 - i
+                    float* drow = p.dw + ((size_t)tap * p.C + cblk * p.Cc + c) * KN;
+#pragma unroll
+                    for (int c0 = 0; c0 < KN; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(lane_addr + j * N + i * KN + c0, r);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int q = 0; q < 16; q += 4)
+                                wh_red_add_v4(drow + c0 + q, __uint_as_float(r[q]), __uint_as_float(r[q + 1]),
+                                              __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+                        }
+                    }
+                }
+            }
+            fence_before_sync();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------
+bool wgrad_halo_supported(const urir_conv_desc* d, bool forced) {
+    if (d->stride != 1 || d->R != 3 || d->S != 3 || d->pad_top != 1 || d->pad_left != 1) return false;
+    if (d->P != d->H || d->Q != d->W || d->H % WH_TH || d->W % WH_TW) return false;
+    if (d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16) return false;
+    if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
+    if (!(d->C == 32 || d->C % 64 == 0) || !(d->K == 32 || d->K == 64)) return false;
+    const long long tiles = (long long)d->N * (d->H / WH_TH) * (d->W / WH_TW);
+    return forced || tiles >= 148 * 8;
+}
+
+template <int KN>
+static int launch_wh(const WhaloMaps& maps, const WhaloParams& p, dim3 grid, int smem, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = conv_wgrad_halo_kernel<KN>;
+    if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM_BUDGET + 8192)); attr_set = true; }
+    kern<<<grid, 192, smem, st>>>(maps, p);
+    URIR_LAUNCH_OK(1);
+    return URIR_OK;
+}
+
+int conv_wgrad_halo(const urir_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    WhaloMaps maps; WhaloParams p; memset(&p, 0, sizeof(p));
+    const int KN = d->K;
+    p.C = d->C; p.Cc = d->C == 32 ? 32 : 64;
+    p.n_mma = p.Cc == 32 ? 1 : 2;
+    p.tiles_w = d->W / WH_TW; p.tiles_h = d->H / WH_TH; p.total_tiles = p.tiles_w * p.tiles_h * d->N;
+    const int a_box = WH_PH * WH_TW * p.Cc * 2, b_box = WH_TH * WH_PW * KN * 2;
+    p.a_bytes = (a_box + 1023) / 1024 * 1024;
+    p.stage_bytes = p.a_bytes + (b_box + 1023) / 1024 * 1024;
+    p.tx_bytes = a_box + b_box;
+    p.stages = WH_SMEM_BUDGET / p.stage_bytes;
+    if (p.stages > WH_MAX_STAGES) p.stages = WH_MAX_STAGES;
+    { const int cols = p.n_mma * 3 * KN; p.tmem_cols = cols <= 128 ? 128 : cols <= 256 ? 256 : 512; }
+    p.dw = dw;
+    { const char* e = getenv("URIR_WH_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    {   // x: dims (C, H, W, N), H the fastest pixel index of the box
+        const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->H, (uint64_t)d->W, (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)d->W * d->x_ld * 2, (uint64_t)d->x_ld * 2, (uint64_t)d->H * d->W * d->x_ld * 2};
+        const uint32_t box[4] = {(uint32_t)p.Cc, (uint32_t)WH_PH, (uint32_t)WH_TW, 1};
+        int rc = encode_map(&maps.a, (const char*)x + (size_t)d->x_coff * 2, 4, dims, strides, box, p.Cc * 2);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->P, (uint64_t)d->Q, (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)d->Q * d->y_ld * 2, (uint64_t)d->y_ld * 2, (uint64_t)d->P * d->Q * d->y_ld * 2};
+        const uint32_t box[4] = {(uint32_t)KN, (uint32_t)WH_TH, (uint32_t)WH_PW, 1};
+        int rc = encode_map(&maps.b, (const char*)dy + (size_t)d->y_coff * 2, 4, dims, strides, box, KN * 2);
+        if (rc) return rc;
+    }
+    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->C * d->K, st));
+    const int n_cblk = d->C / p.Cc;
+    int gx = 148 / n_cblk; if (gx < 1) gx = 1;
+    if (gx > p.total_tiles) gx = p.total_tiles;
+    dim3 grid(gx, n_cblk);
+    const int smem = p.stages * p.stage_bytes + 1024 + (2 * WH_MAX_STAGES + 2) * 8 + 16 + 1024;
+    if (KN == 32) return launch_wh<32>(maps, p, grid, smem, st);
+    if (KN == 64) return launch_wh<64>(maps, p, grid, smem, st);
+    return fail(URIR_ERR_UNSUP, "wgrad(halo): K = %d not supported", KN);
+}
+
+}  // namespace urir
