@@ -208,6 +208,185 @@ bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy
     }
 }
 
+
+// -----------------------------------------------------------------------------------------
+// Fast paths for power-of-two channel counts (every layer of the canonical net). A thread keeps ONE 8-channel
+// group for its whole life (256 % (C/8) == 0), so the per-channel coefficients sit in registers instead of
+// being re-read from shared memory for every element, the pixel index advances by a constant (no 64-bit
+// divisions in the loop) and UNROLL independent 128-bit loads per tensor are in flight per thread.
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+bn_relu_fwd_pow2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
+                        const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ y, int y_ld,
+                        int y_coff, long long npix, int C, int g_shift, int relu) {
+    const int G = C >> 3, lanes = 256 >> g_shift;
+    const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
+    float sc[8], sh[8];
+    ld8(scale_shift + c, sc); ld8(scale_shift + C + c, sh);
+    const __nv_bfloat16* xp = x + x_coff + c;
+    __nv_bfloat16* yp = y + y_coff + c;
+    const long long pstride = (long long)gridDim.x * lanes;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += UNROLL * pstride) {
+        uint4 u[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+            if (p0 + q * pstride < npix) u[q] = ld_nc_v4(xp + (p0 + q * pstride) * x_ld);
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            if (p0 + q * pstride >= npix) break;
+            float v[8];
+            unpack8(u[q], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = fmaf(v[j], sc[j], sh[j]); if (relu) v[j] = fmaxf(v[j], 0.f); }
+            *reinterpret_cast<uint4*>(yp + (p0 + q * pstride) * y_ld) = pack8(v);
+        }
+    }
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_reduce_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff,
+                               const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
+                               const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
+                               float* __restrict__ sums, long long npix, int C, int g_shift) {
+    extern __shared__ float red[];             // [256][17]
+    const int G = C >> 3, lanes = 256 >> g_shift;
+    const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
+    float sc[8], sh[8], mu[8], rs[8], a1[8], a2[8];
+    ld8(scale_shift + c, sc); ld8(scale_shift + C + c, sh); ld8(mean_rstd + c, mu); ld8(mean_rstd + C + c, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+    const __nv_bfloat16* dp = dy + dy_coff + c;
+    const __nv_bfloat16* xp = x + x_coff + c;
+    const long long pstride = (long long)gridDim.x * lanes;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += UNROLL * pstride) {
+        uint4 ud[UNROLL], ux[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+            if (p0 + q * pstride < npix) { ud[q] = ld_nc_v4(dp + (p0 + q * pstride) * dy_ld); ux[q] = ld_nc_v4(xp + (p0 + q * pstride) * x_ld); }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            if (p0 + q * pstride >= npix) break;
+            float dv[8], xv[8];
+            unpack8(ud[q], dv); unpack8(ux[q], xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float g = fmaf(xv[j], sc[j], sh[j]) > 0.f ? dv[j] : 0.f;
+                a1[j] += g;
+                a2[j] = fmaf(g, (xv[j] - mu[j]) * rs[j], a2[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 17 + j] = a1[j]; red[threadIdx.x * 17 + 8 + j] = a2[j]; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * C; t += blockDim.x) {
+        const int which = t / C, ch = t % C;
+        const int gg = ch >> 3, j = ch & 7;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(l * G + gg) * 17 + which * 8 + j];
+        atomicAdd(sums + t, s);
+    }
+}
+
+// dx = a*g + k1*x + k0 with a = gamma*rstd, k1 = -a*rstd*mean(g*xhat), k0 = -k1*mean - a*mean(g)
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff,
+                              const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
+                              const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
+                              const float* __restrict__ gamma, const float* __restrict__ sums,
+                              __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                              long long npix, int C, int g_shift) {
+    extern __shared__ float red[];             // [256][9]
+    const int G = C >> 3, lanes = 256 >> g_shift;
+    const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
+    const float inv_n = 1.f / (float)npix;
+    float sc[8], sh[8], a[8], k1[8], k0[8], bsum[8];
+    {
+        float mu[8], rs[8], sg[8], sgx[8], gm[8];
+        ld8(scale_shift + c, sc); ld8(scale_shift + C + c, sh); ld8(mean_rstd + c, mu); ld8(mean_rstd + C + c, rs);
+        ld8(sums + c, sg); ld8(sums + C + c, sgx);
+        if (gamma) ld8(gamma + c, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = (gamma ? gm[j] : 1.f) * rs[j];
+            k1[j] = -a[j] * rs[j] * (sgx[j] * inv_n);
+            k0[j] = -k1[j] * mu[j] - a[j] * (sg[j] * inv_n);
+            bsum[j] = 0.f;
+        }
+        if (blockIdx.x == 0 && lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { if (dgamma) dgamma[c + j] = sgx[j]; if (dbeta) dbeta[c + j] = sg[j]; }
+        }
+    }
+    const __nv_bfloat16* dp = dy + dy_coff + c;
+    const __nv_bfloat16* xp = x + x_coff + c;
+    __nv_bfloat16* op = dx + dx_coff + c;
+    const long long pstride = (long long)gridDim.x * lanes;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += UNROLL * pstride) {
+        uint4 ud[UNROLL], ux[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+            if (p0 + q * pstride < npix) { ud[q] = ld_nc_v4(dp + (p0 + q * pstride) * dy_ld); ux[q] = ld_nc_v4(xp + (p0 + q * pstride) * x_ld); }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            if (p0 + q * pstride >= npix) break;
+            float dv[8], xv[8], r[8];
+            unpack8(ud[q], dv); unpack8(ux[q], xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float g = fmaf(xv[j], sc[j], sh[j]) > 0.f ? dv[j] : 0.f;
+                r[j] = fmaf(a[j], g, fmaf(k1[j], xv[j], k0[j]));
+                bsum[j] += r[j];
+            }
+            *reinterpret_cast<uint4*>(op + (p0 + q * pstride) * dx_ld) = pack8(r);
+        }
+    }
+    if (dbias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = bsum[j];
+        __syncthreads();
+        for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+            const int gg = ch >> 3, j = ch & 7;
+            float s = 0.f;
+            for (int l = 0; l < lanes; ++l) s += red[(l * G + gg) * 9 + j];
+            atomicAdd(dbias + ch, s);
+        }
+    }
+}
+
+// C/8 a power of two <= 256 -> log2(C/8), else -1
+static int pow2_shift(int C) {
+    if (C % 8) return -1;
+    const int G = C / 8;
+    if (G < 1 || G > 256 || (G & (G - 1))) return -1;
+    int s = 0; while ((1 << s) < G) ++s;
+    return s;
+}
+// enough blocks to fill the machine, few enough that the per-block tail (atomics) stays small
+static int pow2_grid(long long npix, int lanes, int unroll, int max_per_sm) {
+    long long b = (npix + (long long)lanes * unroll - 1) / ((long long)lanes * unroll);
+    const long long cap = 148LL * max_per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
 static int grid_for(long long work_items, int threads) {
     long long b = (work_items + threads - 1) / threads;
     const long long cap = 148LL * 8;
@@ -232,6 +411,13 @@ int bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* ss, void* y, i
                 long long npix, int C, int relu, cudaStream_t st) {
     URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, y_ld, y_coff), "bn_relu_fwd: C/ld/coff must be multiples of 8");
     URIR_CHECK_ARG(C <= 2048, "bn_relu_fwd: C too large");
+    if (const int gs = pow2_shift(C); gs >= 0) {
+        const int lanes = 256 >> gs;
+        bn_relu_fwd_pow2_kernel<4><<<pow2_grid(npix, lanes, 4, 4), 256, 0, st>>>(
+            (const __nv_bfloat16*)x, x_ld, x_coff, ss, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, gs, relu);
+        URIR_LAUNCH_OK(0);
+        return URIR_OK;
+    }
     bn_relu_fwd_kernel<<<grid_for(npix * (C / 8), 256), 256, 2 * C * sizeof(float), st>>>(
         (const __nv_bfloat16*)x, x_ld, x_coff, ss, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, relu);
     URIR_LAUNCH_OK(0);
@@ -243,6 +429,13 @@ int bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, in
     URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, dy_ld, dy_coff), "bn_bwd_reduce: C/ld/coff must be multiples of 8");
     URIR_CHECK_ARG(C <= 2048 && (C / 8) <= 256, "bn_bwd_reduce: C too large");
     URIR_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st));
+    if (const int gs = pow2_shift(C); gs >= 0) {
+        const int ln = 256 >> gs;
+        bn_relu_bwd_reduce_pow2_kernel<4><<<pow2_grid(npix, ln, 8, 2), 256, 256 * 17 * sizeof(float), st>>>(
+            (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C, gs);
+        URIR_LAUNCH_OK(0);
+        return URIR_OK;
+    }
     const int lanes = 256 / (C / 8);
     long long blocks = (npix + lanes - 1) / lanes;
     if (blocks > 148 * 4) blocks = 148 * 4;
@@ -261,6 +454,14 @@ int bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int
     URIR_CHECK_ARG(C <= 1024, "bn_bwd_apply: C too large");
     URIR_CHECK_ARG(!dbias || (256 % (C / 8) == 0), "bn_bwd_apply: dbias needs C/8 to divide 256");
     if (dbias) URIR_CUDA_OK(cudaMemsetAsync(dbias, 0, C * sizeof(float), st));
+    if (const int gs = pow2_shift(C); gs >= 0) {
+        const int ln = 256 >> gs;
+        bn_relu_bwd_apply_pow2_kernel<4><<<pow2_grid(npix, ln, 8, 2), 256, 256 * 9 * sizeof(float), st>>>(
+            (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, gamma, sums,
+            (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C, gs);
+        URIR_LAUNCH_OK(0);
+        return URIR_OK;
+    }
     bn_relu_bwd_apply_kernel<<<grid_for(npix * (C / 8), 256), 256, (7 * C + 256 * 9) * sizeof(float), st>>>(
         (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, gamma, sums,
         (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C);
