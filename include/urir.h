@@ -138,17 +138,20 @@ int urir_bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x
 /* Embedding(2000,256) + Flatten: out bf16 [B, T*D] */
 int urir_embedding_fwd(const int32_t* idx, const float* table, void* out, int B, int T, int D,
                        int vocab, void* stream);
-/* dtable fp32 [vocab, D] (overwritten) += scatter of dx fp32 [B, T*D] */
-int urir_embedding_bwd(const int32_t* idx, const float* dx, float* dtable, int B, int T, int D,
-                       int vocab, void* stream);
-/* Dense + Dropout: out bf16 [B,N] = (x bf16 [B,Kd] @ w bf16 [Kd,N] + bias) * mask (mask may be
- * NULL); ws = caller-provided fp32 [B,N] split-K scratch (zeroed by the call). */
-int urir_dense_fwd(const void* x, const void* w, const float* bias, const float* mask, void* out,
-                   float* ws, int B, int Kd, int N, void* stream);
-/* dy_eff = dy (bf16 [B,N]) * mask;  dw fp32 [Kd,N] = x^T dy_eff;  db fp32 [N];
- * dx fp32 [B,Kd] = dy_eff @ w^T.  All outputs overwritten. */
-int urir_dense_bwd(const void* x, const void* w, const void* dy, const float* mask, float* dw,
-                   float* db, float* dx, int B, int Kd, int N, void* stream);
+/* dtable fp32 [vocab, D] (overwritten) += scatter of dx (fp32 or bf16, URIR_F32 | URIR_BF16) [B, T*D] */
+int urir_embedding_bwd(const int32_t* idx, const void* dx, int dx_dtype, float* dtable, int B, int T,
+                       int D, int vocab, void* stream);
+/* Dense + Dropout on the tensor cores (a 1x1 convolution over B "pixels"):
+ * out bf16 [B,N] = bf16(x bf16 [B,Kd] @ w + bias) * mask (mask fp32 [B,N] or NULL).
+ * The kernel is passed in both bf16 layouts: w_kn [Kd][N] (Keras Dense kernel order) and w_nk [N][Kd]
+ * (urir_weight_prep with taps = 1, C = Kd, K = N produces both). */
+int urir_dense_fwd(const void* x, const void* w_kn, const void* w_nk, const float* bias,
+                   const float* mask, void* out, int B, int Kd, int N, void* stream);
+/* dy_eff = dy (bf16 [B,N]) * mask (written to the caller's bf16 [B,N] scratch `dy_eff`; unused when mask is NULL);
+ * dw fp32 [Kd,N] = x^T dy_eff;  db fp32 [N];  dx bf16 [B,Kd] = dy_eff @ w^T.  dw / db / dx may each be NULL;
+ * outputs are overwritten. */
+int urir_dense_bwd(const void* x, const void* w_kn, const void* w_nk, const void* dy, const float* mask,
+                   void* dy_eff, float* dw, float* db, void* dx, int B, int Kd, int N, void* stream);
 /* inverted-dropout mask {0, 1/(1-rate)} from a counter-based generator; the stream position is
  * (seed, *step_dev) so CUDA-graph replays draw fresh masks. */
 int urir_dropout_mask(float* mask, long long n, float rate, uint64_t seed,

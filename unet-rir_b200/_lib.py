@@ -53,9 +53,9 @@ _PROTOS = {
     "urir_bn_relu_bwd_apply": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
                                     _vp, _ll, _i, _vp]),
     "urir_embedding_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "urir_embedding_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "urir_embedding_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "urir_dense_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "urir_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "urir_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "urir_dropout_mask": (_i, [_vp, _ll, _f, _u64, _vp, _vp]),
     "urir_ampphase_loss": (_i, [_vp, _vp, _ll, _f, _f, _i, _vp, _vp, _vp, _i, _vp]),
     "urir_adam": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _f, _f, _vp]),

@@ -57,9 +57,9 @@ int add_bf16(const void*, const void*, void*, long long, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
 int cast_pad_bf16(const float*, void*, long long, int, int, cudaStream_t);
 int embedding_fwd(const int*, const float*, void*, int, int, int, int, cudaStream_t);
-int embedding_bwd(const int*, const float*, float*, int, int, int, int, cudaStream_t);
-int dense_fwd(const void*, const void*, const float*, const float*, void*, float*, int, int, int, cudaStream_t);
-int dense_bwd(const void*, const void*, const void*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
+int embedding_bwd(const int*, const void*, int, float*, int, int, int, int, cudaStream_t);
+int dense_fwd(const void*, const void*, const void*, const float*, const float*, void*, int, int, int, cudaStream_t);
+int dense_bwd(const void*, const void*, const void*, const void*, const float*, void*, float*, float*, void*, int, int, int, cudaStream_t);
 int dropout_mask(float*, long long, float, uint64_t, const int*, cudaStream_t);
 int stft_ampphase(const float*, int, const urir_stft_desc*, float*, cudaStream_t);
 int istft_from_ampphase(const float*, int, const urir_stft_desc*, float*, cudaStream_t);
@@ -199,19 +199,21 @@ int urir_embedding_fwd(const int32_t* idx, const float* table, void* out, int B,
     URIR_CHECK_ARG(idx && table && out && B > 0 && T > 0, "embedding_fwd: bad args");
     return embedding_fwd(idx, table, out, B, T, D, vocab, (cudaStream_t)stream);
 }
-int urir_embedding_bwd(const int32_t* idx, const float* dx, float* dtable, int B, int T, int D, int vocab, void* stream) {
+int urir_embedding_bwd(const int32_t* idx, const void* dx, int dx_dtype, float* dtable, int B, int T, int D, int vocab,
+                       void* stream) {
     URIR_CHECK_ARG(idx && dx && dtable && B > 0 && T > 0, "embedding_bwd: bad args");
-    return embedding_bwd(idx, dx, dtable, B, T, D, vocab, (cudaStream_t)stream);
+    URIR_CHECK_ARG(dx_dtype == URIR_F32 || dx_dtype == URIR_BF16, "embedding_bwd: bad dtype");
+    return embedding_bwd(idx, dx, dx_dtype, dtable, B, T, D, vocab, (cudaStream_t)stream);
 }
-int urir_dense_fwd(const void* x, const void* w, const float* bias, const float* mask, void* out, float* ws, int B,
-                   int Kd, int N, void* stream) {
-    URIR_CHECK_ARG(x && w && out && B > 0 && Kd > 0 && N > 0, "dense_fwd: bad args");
-    return dense_fwd(x, w, bias, mask, out, ws, B, Kd, N, (cudaStream_t)stream);
-}
-int urir_dense_bwd(const void* x, const void* w, const void* dy, const float* mask, float* dw, float* db, float* dx,
+int urir_dense_fwd(const void* x, const void* w_kn, const void* w_nk, const float* bias, const float* mask, void* out,
                    int B, int Kd, int N, void* stream) {
-    URIR_CHECK_ARG(x && w && dy && B > 0 && Kd > 0 && N > 0, "dense_bwd: bad args");
-    return dense_bwd(x, w, dy, mask, dw, db, dx, B, Kd, N, (cudaStream_t)stream);
+    URIR_CHECK_ARG(x && w_kn && w_nk && out && B > 0 && Kd > 0 && N > 0, "dense_fwd: bad args");
+    return dense_fwd(x, w_kn, w_nk, bias, mask, out, B, Kd, N, (cudaStream_t)stream);
+}
+int urir_dense_bwd(const void* x, const void* w_kn, const void* w_nk, const void* dy, const float* mask, void* dy_eff,
+                   float* dw, float* db, void* dx, int B, int Kd, int N, void* stream) {
+    URIR_CHECK_ARG(x && w_kn && w_nk && dy && B > 0 && Kd > 0 && N > 0, "dense_bwd: bad args");
+    return dense_bwd(x, w_kn, w_nk, dy, mask, dy_eff, dw, db, dx, B, Kd, N, (cudaStream_t)stream);
 }
 int urir_dropout_mask(float* mask, long long n, float rate, uint64_t seed, const int32_t* step_dev, void* stream) {
     URIR_CHECK_ARG(mask && n > 0, "dropout_mask: bad args");

@@ -281,26 +281,65 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
-// all kernels of the model in one launch: table[e] = {w fp32 ptr, w_ck ptr, w_kc ptr, taps, C, K} (int64 each)
-__global__ void weight_prep_batched_kernel(const long long* __restrict__ table) {
-    const long long* e = table + 6 * blockIdx.y;
-    const float* w = reinterpret_cast<const float*>(e[0]);
-    __nv_bfloat16* w_ck = reinterpret_cast<__nv_bfloat16*>(e[1]);
-    __nv_bfloat16* w_kc = reinterpret_cast<__nv_bfloat16*>(e[2]);
-    const int C = (int)e[4], K = (int)e[5];
-    const long long n = e[3] * C * K;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K), c = (int)((i / K) % C);
-        const long long t = i / ((long long)K * C);
-        const __nv_bfloat16 v = f2bf(w[i]);
-        if (w_ck) w_ck[i] = v;
-        if (w_kc) w_kc[((size_t)t * K + k) * C + c] = v;
+// all kernels of the model in one launch: table[e] = {w fp32 ptr, w_ck ptr, w_kc ptr, taps, C, K} (int64 each).
+// Work unit = one 64 (c) x 64 (k) tile of one tap: fp32 rows are read coalesced, w_ck is written coalesced,
+// and the transposed w_kc goes through a padded shared-memory tile so that it is written coalesced as well
+// (the earlier element-per-thread version scattered 2-byte stores C*2 bytes apart).
+constexpr int WP_MAX_ENTRIES = 64;
+__global__ void __launch_bounds__(256) weight_prep_batched_kernel(const long long* __restrict__ table, int n_entries) {
+    __shared__ long long tile_start[WP_MAX_ENTRIES + 1];
+    __shared__ float tile[64][65];
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        for (int e = 0; e < n_entries; ++e) {
+            tile_start[e] = acc;
+            const long long* t = table + 6 * e;
+            acc += t[3] * ((t[4] + 63) / 64) * ((t[5] + 63) / 64);
+        }
+        tile_start[n_entries] = acc;
+    }
+    __syncthreads();
+    const long long total = tile_start[n_entries];
+    int e = 0;
+    for (long long tl = blockIdx.x; tl < total; tl += gridDim.x) {
+        while (tl >= tile_start[e + 1]) ++e;
+        const long long* t = table + 6 * e;
+        const float* w = reinterpret_cast<const float*>(t[0]);
+        __nv_bfloat16* w_ck = reinterpret_cast<__nv_bfloat16*>(t[1]);
+        __nv_bfloat16* w_kc = reinterpret_cast<__nv_bfloat16*>(t[2]);
+        const int C = (int)t[4], K = (int)t[5];
+        const int tiles_k = (K + 63) / 64, tiles_c = (C + 63) / 64;
+        long long r = tl - tile_start[e];
+        const int tk = (int)(r % tiles_k); r /= tiles_k;
+        const int tc = (int)(r % tiles_c); const long long tap = r / tiles_c;
+        const int c0 = tc * 64, k0 = tk * 64;
+        const size_t base = (size_t)tap * C * K;
+        const int col = threadIdx.x & 63, row0 = threadIdx.x >> 6;
+        __syncthreads();                                   // previous tile's transposed reads are done
+#pragma unroll 4
+        for (int rr = row0; rr < 64; rr += 4) {
+            const int c = c0 + rr, k = k0 + col;
+            float v = 0.f;
+            if (c < C && k < K) {
+                v = w[base + (size_t)c * K + k];
+                if (w_ck) w_ck[base + (size_t)c * K + k] = f2bf(v);
+            }
+            tile[rr][col] = v;
+        }
+        __syncthreads();
+        if (w_kc) {
+#pragma unroll 4
+            for (int rr = row0; rr < 64; rr += 4) {
+                const int k = k0 + rr, c = c0 + col;
+                if (k < K && c < C) w_kc[base + (size_t)k * C + c] = f2bf(tile[col][rr]);
+            }
+        }
     }
 }
 
 int weight_prep_batched(const long long* table_dev, int n_entries, cudaStream_t st) {
-    dim3 grid(64, n_entries);
-    weight_prep_batched_kernel<<<grid, 256, 0, st>>>(table_dev);
+    URIR_CHECK_ARG(n_entries <= WP_MAX_ENTRIES, "weight_prep_batched: at most %d entries", WP_MAX_ENTRIES);
+    weight_prep_batched_kernel<<<148 * 8, 256, 0, st>>>(table_dev, n_entries);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }

@@ -37,6 +37,7 @@ struct WgradParams {
     int tmem_cols;
     int ntaps, n_mtiles;
     float* dw;
+    int direct;                     // 1: a single CTA owns each dw element (no pixel split) -> plain stores, no memset
     long long* trace;               // debug: per-iteration clock64 stamps of CTA (0,0,0) when non-null
     WgradTap taps[36];
 };
@@ -207,7 +208,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
                     tmem_ld_wait();
                     if (valid) {
                         const int n_left = p.K - n_tile * BLOCK_N - c0;      // valid columns from c0 on
-                        if (n_left >= 16 && (p.K & 3) == 0) {
+                        if (p.direct && n_left >= 16 && (p.K & 3) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 16; q += 4)
+                                *reinterpret_cast<float4*>(drow + c0 + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
+                                                                                      __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+                        } else if (n_left >= 16 && (p.K & 3) == 0) {
 #pragma unroll
                             for (int q = 0; q < 16; q += 4)
                                 red_add_v4(drow + c0 + q, __uint_as_float(r[q]), __uint_as_float(r[q + 1]),
@@ -340,7 +346,9 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
         int rc = encode_map(&maps.b, (const char*)dy + (size_t)d->y_coff * 2, 4, dims, strides, bbox, p.b_atom * 2);
         if (rc) return rc;
     }
-    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps * d->C * d->K, st));
+    // without a pixel split every dw element has exactly one producer (all channel tiles exact): store, do not add
+    p.direct = splits == 1 && d->K % BN == 0 && (d->K & 3) == 0 && (d->C % 128 == 0 || d->C == m_valid) ? 1 : 0;
+    if (!p.direct) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps * d->C * d->K, st));
     dim3 grid(splits, p.n_mtiles * n_ntiles, tap_groups);
     if (BN == 128) return launch_wg<128>(maps, p, grid, smem_bytes, st);
     if (BN == 64) return launch_wg<64>(maps, p, grid, smem_bytes, st);

@@ -116,8 +116,10 @@ class UNetEngine:
                 kh, kw, a, b = shape
                 self.wops[name] = (torch.empty(kh * kw, a, b, dtype=torch.bfloat16, device=dev),
                                    torch.empty(kh * kw, b, a, dtype=torch.bfloat16, device=dev))
-        self.dense_w16 = torch.empty(self.shapes["vec.dense.w"], dtype=torch.bfloat16, device=dev)
-        rows = []
+        kd, dn = self.shapes["vec.dense.w"]
+        self.dense_w16 = torch.empty(kd, dn, dtype=torch.bfloat16, device=dev)       # [Kd][N]
+        self.dense_w16_t = torch.empty(dn, kd, dtype=torch.bfloat16, device=dev)     # [N][Kd]
+        rows = [[self.param["vec.dense.w"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(), 1, kd, dn]]
         for name, (w_ck, w_kc) in self.wops.items():
             taps, a, b = w_ck.shape
             rows.append([self.param[name].data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), taps, a, b])
@@ -159,8 +161,6 @@ class UNetEngine:
     def refresh_operands(self):
         """fp32 masters -> bf16 operand layouts (after load / after every optimiser step)."""
         L.call("weight_prep_batched", self.wprep_table.data_ptr(), self.wprep_table.shape[0])
-        L.call("cast_f32_to_bf16", self.param["vec.dense.w"].data_ptr(), self.dense_w16.data_ptr(),
-               self.dense_w16.numel())
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, B):
@@ -190,9 +190,9 @@ class UNetEngine:
             else:
                 b["z"] = act(h, w, n); b["g_z"] = act(h, w, n)
         b["embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=bf, device=dev)
-        b["g_embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=torch.float32, device=dev)
+        b["g_embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=bf, device=dev)
         b["v16"] = act(self.H5, self.W5, PL.VEC_CH); b["g_v16"] = act(self.H5, self.W5, PL.VEC_CH)
-        b["dense_ws"] = torch.zeros(B, self.dense_n, dtype=torch.float32, device=dev)
+        b["g_v16_eff"] = torch.zeros(B, self.dense_n, dtype=bf, device=dev)
         b["mask"] = torch.ones(B, self.dense_n, dtype=torch.float32, device=dev)
         self._bufs[B] = b
         return b
@@ -308,8 +308,9 @@ class UNetEngine:
                        self.dropout_seed, self.step_dev.data_ptr())
                 mask = b["mask"]
         self._fwd_mask = mask
-        L.call("dense_fwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.param["vec.dense.b"].data_ptr(),
-               L.ptr(mask), b["v16"].data_ptr(), b["dense_ws"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
+        L.call("dense_fwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
+               self.param["vec.dense.b"].data_ptr(), L.ptr(mask), b["v16"].data_ptr(), B, self.T * PL.EMB_DIM,
+               self.dense_n)
         z = View(b["z"])
         self._conv_fprop("vec.proj", View(b["v16"]), z, 1, 1, accumulate=1)
         # ---- decoder (decoding_block, u_net.py:291-321)
@@ -386,11 +387,12 @@ class UNetEngine:
             g_z = View(b["g_z"])
             self._conv_wgrad("vec.proj", View(b["v16"]), g_z, 1, 1)
             self._conv_dgrad("vec.proj", g_z, View(b["g_v16"]), 1, 1)
-            L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), b["g_v16"].data_ptr(),
-                   L.ptr(self._fwd_mask), self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
+            L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
+                   b["g_v16"].data_ptr(), L.ptr(self._fwd_mask), b["g_v16_eff"].data_ptr(),
+                   self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
                    b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
-            L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), self.grad["vec.emb"].data_ptr(),
-                   B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+            L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), L.BF16,
+                   self.grad["vec.emb"].data_ptr(), B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
         if segment in (None, 2):
             # encoder, level 5 up to level 1
             g_e = View(b["g_z"])
