@@ -99,8 +99,19 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
  * For a Conv2DTranspose layer pass x = gradient of its output, dy = its input. */
 int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw,
                       void* stream);
+/* The same operation for a 3x3 stride-2 layer on an even input (every Conv2DTranspose forward and every
+ * stride-2 Conv2D input-gradient of the net) as ONE 2x2 stride-1 problem on the half-resolution grid with
+ * GEMM-N = (row parity, column parity, channel): persistent halo-tile tcgen05 kernel, dy read once, the four
+ * parity classes scattered by the epilogue. Weights in the w_up2 layout (urir_weight_prep_up2). Honours
+ * d->accumulate (dx += ...). Returns URIR_ERR_UNSUP when urir_conv_path(d, 3) == 0. */
+int urir_conv2d_dgrad_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, const float* bias,
+                          void* dx, void* stream);
+/* fp32 HWIO [3][3][C][K] -> bf16 w_up2 [a*2+b][(ph, pw, c)][K] = w[2a+ph][2b+pw][c][k], zero where that tap
+ * does not exist (16*C*K elements). */
+int urir_weight_prep_up2(const float* w_hwio, void* w_up2, int C, int K, void* stream);
 /* which kernel family URIR_IMPL_AUTO picks for this descriptor: op 0 = fprop, 1 = dgrad, 2 = wgrad;
- * returns 1 = tcgen05 implicit GEMM, 0 = CUDA-core direct convolution. Pure host query. */
+ * returns 1 = tcgen05 implicit GEMM, 0 = CUDA-core direct convolution. op 3: 1 when urir_conv2d_dgrad_up2
+ * supports the descriptor. Pure host query. */
 int urir_conv_path(const urir_conv_desc* d, int op);
 /* fp32 HWIO master weights -> the two bf16 operand layouts. */
 int urir_weight_prep(const float* w_hwio, void* w_ck, void* w_kc, int taps, int C, int K,

@@ -2,6 +2,8 @@
 the CUDA-core path) against the CPU oracle's TF-SAME convolutions on the same seeded bf16-rounded
 inputs. Tolerances: bf16 outputs rel-L2 <= 4e-3 (one bf16 rounding of an fp32-accumulated result);
 fp32 outputs (wgrad, stats) rel-L2 <= 2e-4 (summation order only)."""
+import ctypes as C
+
 import pytest
 import torch
 
@@ -375,3 +377,41 @@ def test_halo_tile_wgrad(case):
     dw2 = torch.zeros(3, 3, Cc, K, device="cuda")
     U.run_wgrad(d2, xw, dyw, dw2)
     assert U.rel_l2(dw2, gw) < F32_TOL
+
+
+UP2_CASES = [
+    (2, 16, 32, 32, 64),      # D5t / E2a-dgrad class: N = 4C = 128, K = 64
+    (3, 24, 40, 64, 128),     # D4t / E3a-dgrad class: two GEMM-N tiles, two K chunks, ragged half-resolution tiles
+    (5, 144, 160, 32, 64),    # many tiles per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", UP2_CASES, ids=[str(c) for c in UP2_CASES])
+def test_stride2_dgrad_as_2x2_on_half_grid(case):
+    """urir_conv2d_dgrad_up2: the input gradient of a 3x3 stride-2 SAME conv (= Conv2DTranspose forward) as one
+    2x2 stride-1 problem with GEMM-N = (parity, channel); with bias, into a concat slice, and accumulating."""
+    N, H, W, Cc, K = case
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, 3, 2, seed=13)
+    xr = x.clone().requires_grad_(True)
+    gx, = torch.autograd.grad(_oracle_fprop(xr, w, None, 2), [xr], dy)
+    dyg = dy.cuda().to(torch.bfloat16)
+    w_up2 = torch.empty(4, 4 * Cc, K, dtype=torch.bfloat16, device="cuda")
+    L.call("weight_prep_up2", w.cuda().contiguous().data_ptr(), w_up2.data_ptr(), Cc, K)
+    d = U.conv_desc(N, H, W, Cc, K, 3, 2)
+    assert L.load().urir_conv_path(d, 3) == 1
+    cbias = torch.randn(Cc, generator=torch.Generator().manual_seed(7))
+    dx = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    L.call("conv2d_dgrad_up2", C.byref(d), dyg.data_ptr(), w_up2.data_ptr(), cbias.cuda().data_ptr(), dx.data_ptr())
+    assert U.rel_l2(dx.float(), gx + cbias) < BF16_TOL
+    # right half of a concat buffer (Conv2DTranspose forward writes next to the skip connection)
+    cat = torch.zeros(N, H, W, 2 * Cc, dtype=torch.bfloat16, device="cuda")
+    d2 = U.conv_desc(N, H, W, Cc, K, 3, 2, x_ld=2 * Cc, x_coff=Cc)
+    L.call("conv2d_dgrad_up2", C.byref(d2), dyg.data_ptr(), w_up2.data_ptr(), cbias.cuda().data_ptr(), cat.data_ptr())
+    assert torch.equal(cat[..., Cc:], dx) and float(cat[..., :Cc].float().abs().max()) == 0.0
+    # accumulate into the left half (encoder dgrad adds to the skip gradient)
+    base = U.bf16_round(torch.randn(N, H, W, 2 * Cc, generator=torch.Generator().manual_seed(9)))
+    acc = base.cuda().to(torch.bfloat16)
+    d3 = U.conv_desc(N, H, W, Cc, K, 3, 2, x_ld=2 * Cc, x_coff=0, accumulate=1)
+    L.call("conv2d_dgrad_up2", C.byref(d3), dyg.data_ptr(), w_up2.data_ptr(), None, acc.data_ptr())
+    assert U.rel_l2(acc[..., :Cc].float(), gx + base[..., :Cc]) < BF16_TOL
+    assert torch.equal(acc[..., Cc:].cpu().float(), base[..., Cc:])

@@ -54,8 +54,11 @@ def run(which, reps=int(os.environ.get("PROF_REPS", "3"))):
         t_end = __import__("time").time() + 0.3
         while __import__("time").time() < t_end:
             (a @ a); torch.cuda.synchronize()
+    w_up2 = torch.randn(4, 4 * Cc, K, device="cuda").to(torch.bfloat16) if (op == "dgrad" and s == 2 and k == 3) else None
     def launch():
-        if op == "wgrad":
+        if w_up2 is not None and not os.environ.get("PROF_NO_UP2"):
+            L.call("conv2d_dgrad_up2", C.byref(d), dy.data_ptr(), w_up2.data_ptr(), None, x.data_ptr())
+        elif op == "wgrad":
             L.call("conv2d_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr())
         elif op == "fprop":
             L.call("conv2d_fprop", C.byref(d), x.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, dy.data_ptr(), sp)

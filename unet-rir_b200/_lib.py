@@ -45,6 +45,8 @@ _PROTOS = {
     "urir_conv2d_wgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "urir_conv_path": (_i, [C.POINTER(ConvDesc), _i]),
     "urir_weight_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "urir_weight_prep_up2": (_i, [_vp, _vp, _i, _i, _vp]),
+    "urir_conv2d_dgrad_up2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_weight_prep_batched": (_i, [_vp, _i, _vp]),
     "urir_channel_sum": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp]),
     "urir_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _i, _vp]),
@@ -134,7 +136,7 @@ def _conv_info(name, args):
     d = args[0]._obj if hasattr(args[0], "_obj") else None
     if not isinstance(d, ConvDesc):
         return {}
-    op = {"conv2d_fprop": 0, "conv2d_dgrad": 1, "conv2d_wgrad": 2}[name]
+    op = {"conv2d_fprop": 0, "conv2d_dgrad": 1, "conv2d_wgrad": 2, "conv2d_dgrad_up2": 3}[name]
     tc = int(load().urir_conv_path(C.byref(d), op))
     return dict(tc=tc, N=d.N, H=d.H, W=d.W, C=d.C, K=d.K, R=d.R, S=d.S, stride=d.stride, P=d.P, Q=d.Q,
                 x_ld=d.x_ld, y_ld=d.y_ld, x_dtype=d.x_dtype, y_dtype=d.y_dtype, impl=d.impl,

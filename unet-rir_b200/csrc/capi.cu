@@ -34,6 +34,9 @@ bool wgrad_tc_supported(const urir_conv_desc*);
 bool thin_supported(const urir_conv_desc*, int op);
 bool halo_supported(const urir_conv_desc*, int op, bool forced);
 int conv_halo(const urir_conv_desc*, int op, const void*, const void*, const float*, void*, float*, cudaStream_t);
+bool halo_up2_supported(const urir_conv_desc*);
+int conv_halo_up2(const urir_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int weight_prep_up2(const float*, void*, int, int, cudaStream_t);
 bool head_fprop_supported(const urir_conv_desc*);
 int head_fprop(const urir_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int thin_gemm(const urir_conv_desc*, const void*, const void*, const float*, void*, bool, cudaStream_t);
@@ -147,7 +150,19 @@ int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, fl
     return use_tc ? conv_wgrad_tc(d, x, dy, dw, st) : conv_wgrad_simt_dispatch(d, x, dy, dw, st);
 }
 
+int urir_conv2d_dgrad_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, const float* bias, void* dx, void* stream) {
+    int rc = check_conv(d, "conv2d_dgrad_up2"); if (rc) return rc;
+    URIR_CHECK_ARG(dy && dx && w_up2, "conv2d_dgrad_up2: null tensor");
+    if (!halo_up2_supported(d)) return fail(URIR_ERR_UNSUP, "conv2d_dgrad_up2: shape not supported (3x3 stride 2 on an even input, 4C <= 512, resident weights)");
+    return conv_halo_up2(d, dy, w_up2, bias, dx, (cudaStream_t)stream);
+}
+int urir_weight_prep_up2(const float* w_hwio, void* w_up2, int C, int K, void* stream) {
+    URIR_CHECK_ARG(w_hwio && w_up2 && C > 0 && K > 0, "weight_prep_up2: bad args");
+    return weight_prep_up2(w_hwio, w_up2, C, K, (cudaStream_t)stream);
+}
+
 int urir_conv_path(const urir_conv_desc* d, int op) {
+    if (op == 3) return (d && d->impl != URIR_IMPL_SIMT && !(d->impl == URIR_IMPL_AUTO && env_force_simt()) && halo_up2_supported(d)) ? 1 : 0;
     if (!d || d->impl == URIR_IMPL_SIMT || (d->impl == URIR_IMPL_AUTO && env_force_simt())) return 0;
     if (thin_supported(d, op)) return 1;
     if (op < 2 && halo_supported(d, op, d->impl == URIR_IMPL_HALO)) return 1;

@@ -45,6 +45,9 @@ struct HaloParams {
     float* stats;
     __nv_bfloat16* out;
     int n_total;
+    int bias_mod;               // bias index = GEMM-N column % bias_mod (the 4 parity classes of an up-2 layer share it)
+    int accumulate;             // out += result (fp32 add before the bf16 rounding)
+    int grp_off[16];            // output element offset of every 32-column group of GEMM-N (channel / parity placement)
     long long* trace;           // debug (URIR_HALO_TRACE): clock64 stamps of CTA 0, 8 per tile, first 128 tiles
     short tap_row[36];          // first box row of tap t = dw * PH + dh
     short wtap[36];             // weight tap index of tap t
@@ -139,7 +142,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     if (warp == 4 && lane == 0) { prefetch_tmap(&maps.a); prefetch_tmap(&maps.b); }
     for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sstats[i] = 0.f;
     for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x)
-        sbias[i] = (p.bias && n_tile * BLOCK_N + i < p.n_total) ? p.bias[n_tile * BLOCK_N + i] : 0.f;
+        sbias[i] = (p.bias && n_tile * BLOCK_N + i < p.n_total) ? p.bias[(n_tile * BLOCK_N + i) % p.bias_mod] : 0.f;
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -254,7 +257,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 const int m = quarter * 32 + (lane & ~3) + i;
                 const int hh = th * HL_TH + (m & 7), ww = tw * HL_TW + (m >> 3);
                 gvalid[i] = hh < p.H && ww < p.W;
-                gout[i] = p.out + p.o_off + (long long)n * p.o_sn + (long long)hh * p.o_sh + (long long)ww * p.o_sw + n_tile * BLOCK_N;
+                gout[i] = p.out + p.o_off + (long long)n * p.o_sn + (long long)hh * p.o_sh + (long long)ww * p.o_sw;
             }
             uint32_t pk[16];
             const bool tre = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 128 && quarter == 0 && lane == 0;
@@ -282,6 +285,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                         v[4 * j4] = __uint_as_float(r[bb * 16 + 4 * j4]) + bs.x; v[4 * j4 + 1] = __uint_as_float(r[bb * 16 + 4 * j4 + 1]) + bs.y;
                         v[4 * j4 + 2] = __uint_as_float(r[bb * 16 + 4 * j4 + 2]) + bs.z; v[4 * j4 + 3] = __uint_as_float(r[bb * 16 + 4 * j4 + 3]) + bs.w;
                     }
+                    if (p.accumulate && valid) {      // out += : add the previous contents (this lane's own pixel) in fp32
+                        const __nv_bfloat16* old = p.out + p.o_off + (long long)n * p.o_sn + (long long)h * p.o_sh + (long long)w * p.o_sw +
+                                                   p.grp_off[n_tile * (BLOCK_N / 32) + (b >> 1)] + (b & 1) * 16;
+                        const uint4 o0 = *reinterpret_cast<const uint4*>(old), o1 = *reinterpret_cast<const uint4*>(old + 8);
+                        const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const float2 f = unpack_bf16x2(ow[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                    }
                     pk[(b & 1) * 8 + 0] = pack_bf16x2(v[0], v[1]); pk[(b & 1) * 8 + 1] = pack_bf16x2(v[2], v[3]);
                     pk[(b & 1) * 8 + 2] = pack_bf16x2(v[4], v[5]); pk[(b & 1) * 8 + 3] = pack_bf16x2(v[6], v[7]);
                     pk[(b & 1) * 8 + 4] = pack_bf16x2(v[8], v[9]); pk[(b & 1) * 8 + 5] = pack_bf16x2(v[10], v[11]);
@@ -291,7 +302,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                         // that store i writes chunk (lane & 3) of pixel (group, i): 64 contiguous bytes per lane group
                         // (full sectors) instead of four scattered 16-byte pieces.
                         hl_transpose4(pk, lane);
-                        const int c32 = (b >> 1) * 32 + (lane & 3) * 8;
+                        const int c32 = p.grp_off[n_tile * (BLOCK_N / 32) + (b >> 1)] + (lane & 3) * 8;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             if (gvalid[i]) *reinterpret_cast<uint4*>(gout[i] + c32) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
@@ -399,6 +410,8 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     if (p.stages < 2) return fail(URIR_ERR_UNSUP, "halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
     p.o_sn = (long long)d->H * d->W * o_ld; p.o_sh = (long long)d->W * o_ld; p.o_sw = o_ld; p.o_off = o_coff;
     p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)out; p.n_total = ng;
+    p.bias_mod = ng; p.accumulate = 0;
+    for (int g = 0; g < 16; ++g) p.grp_off[g] = 32 * g;
     { const char* e = getenv("URIR_HALO_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr; }
     if (op == 0) { p.oh0 = -d->pad_top; p.ow0 = -d->pad_left; }
     else { p.oh0 = d->pad_top - (d->R - 1); p.ow0 = d->pad_left - (d->S - 1); }
@@ -429,6 +442,99 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
 #undef URIR_HL
     return fail(URIR_ERR_UNSUP, "halo conv: no kernel for BLOCK_N=%d BLOCK_K=%d", BN, BK);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stride-2 3x3 input gradient / Conv2DTranspose forward (dl_models/u_net.py:297-304) through the same kernel.
+// With TF SAME padding on an even input (pad 0 before, 1 after) the forward conv reads x[2p + r, 2q + s], so
+//   dx[2i + ph, 2j + pw, c] = sum over a, b in {0,1}, k of  dy[i - a, j - b, k] * w[2a + ph, 2b + pw, c, k]
+// (terms with 2a + ph > 2 or 2b + pw > 2 do not exist). That is ONE 2x2 stride-1 input-gradient problem on the
+// half-resolution grid whose GEMM-N index is (ph, pw, c): N = 4C, weights "w_up2" [a*2+b][(ph,pw,c)][K] with
+// zeros for the missing taps (urir_weight_prep_up2). dy is read once through the halo box; the epilogue
+// scatters the four parity classes of a pixel to (2i + ph, 2j + pw) -- 64-byte channel groups, so the
+// transposed full-sector stores still apply. conv_igemm.cu instead launches one short-lived CTA per
+// (128-pixel tile, parity class) with N = C (32 -> a 44-cycle MMA does a quarter of the work).
+bool halo_up2_supported(const urir_conv_desc* d) {
+    if (d->stride != 2 || d->R != 3 || d->S != 3 || d->pad_top != 0 || d->pad_left != 0) return false;
+    if (d->H != 2 * d->P || d->W != 2 * d->Q) return false;
+    if (d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16 || d->act != URIR_ACT_NONE) return false;
+    if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
+    if (d->C % 32 || d->K % 32 || 4 * d->C > 512) return false;
+    const int BK = halo_block_k(d->K), BN = halo_block_n(4 * d->C);
+    const long long w_bytes = 4LL * d->K * BN * 2;
+    const long long a_stage = (((long long)(HL_TH + 1) * (HL_TW + 1) * BK * 2) + 1023) / 1024 * 1024;
+    if (w_bytes + 3 * a_stage + 2048 > HL_SMEM_BUDGET) return false;
+    return true;
+}
+
+int conv_halo_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, const float* bias, void* dx, cudaStream_t st) {
+    URIR_CHECK_ARG(w_up2 != nullptr, "up-2 halo conv needs the w_up2 weight layout");
+    const int kg = d->K, ng = 4 * d->C;
+    const int BK = halo_block_k(kg), BN = halo_block_n(ng);
+    HaloMaps maps; HaloParams p; memset(&p, 0, sizeof(p));
+    p.N = d->N; p.H = d->P; p.W = d->Q;                       // the half-resolution grid
+    p.tiles_h = cdiv(p.H, HL_TH); p.tiles_w = cdiv(p.W, HL_TW); p.total_tiles = p.tiles_h * p.tiles_w * d->N;
+    p.PH = HL_TH + 1; p.PW = HL_TW + 1;
+    p.ntaps = 4; p.nchunks = kg / BK;
+    p.a_box_bytes = p.PH * p.PW * BK * 2;
+    p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+    p.w_bytes = p.ntaps * kg * BN * 2;
+    p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
+    if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
+    if (p.stages < 2) return fail(URIR_ERR_UNSUP, "up-2 halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
+    p.o_sn = (long long)d->H * d->W * d->x_ld; p.o_sh = 2LL * d->W * d->x_ld; p.o_sw = 2LL * d->x_ld; p.o_off = d->x_coff;
+    p.bias = bias; p.stats = nullptr; p.out = (__nv_bfloat16*)dx; p.n_total = ng;
+    p.bias_mod = d->C; p.accumulate = d->accumulate;
+    for (int g = 0; g < ng / 32; ++g) {
+        const int n0 = 32 * g, ph = n0 / (2 * d->C), pw = (n0 / d->C) % 2, c0 = n0 % d->C;
+        p.grp_off[g] = (ph * d->W + pw) * d->x_ld + c0;
+    }
+    p.oh0 = -1; p.ow0 = -1;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const int t = a * 2 + b;
+            p.tap_row[t] = (short)((1 - b) * p.PH + (1 - a));
+            p.wtap[t] = (short)t;
+        }
+    {
+        const uint64_t dims[4] = {(uint64_t)kg, (uint64_t)d->P, (uint64_t)d->Q, (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)d->Q * d->y_ld * 2, (uint64_t)d->y_ld * 2, (uint64_t)d->P * d->Q * d->y_ld * 2};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.PH, (uint32_t)p.PW, 1};
+        int rc = encode_map(&maps.a, (const char*)dy + (size_t)d->y_coff * 2, 4, dims, strides, box, BK * 2);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)kg, (uint64_t)ng, 4};
+        const uint64_t strides[2] = {(uint64_t)kg * 2, (uint64_t)kg * ng * 2};
+        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+        int rc = encode_map(&maps.b, w_up2, 3, dims, strides, box, BK * 2);
+        if (rc) return rc;
+    }
+    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
+    const int n_tiles = ng / BN;
+#define URIR_HL(BN_, BK_) if (BN == BN_ && BK == BK_) return launch_halo<BN_, BK_>(maps, p, n_tiles, smem, st);
+    URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
+#undef URIR_HL
+    return fail(URIR_ERR_UNSUP, "up-2 halo conv: no kernel for BLOCK_N=%d BLOCK_K=%d", BN, BK);
+}
+
+// fp32 HWIO [3][3][C][K] -> bf16 w_up2 [a*2+b][(ph,pw,c)][K], zero where 2a+ph > 2 or 2b+pw > 2
+__global__ void weight_prep_up2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int K) {
+    const long long n = 16LL * C * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K); long long r = i / K;
+        const int c = (int)(r % C); r /= C;
+        const int pw = (int)(r & 1), ph = (int)((r >> 1) & 1), b = (int)((r >> 2) & 1), a = (int)(r >> 3);
+        const int rr = 2 * a + ph, ss = 2 * b + pw;
+        out[i] = f2bf((rr < 3 && ss < 3) ? w[((size_t)(rr * 3 + ss) * C + c) * K + k] : 0.f);
+    }
+}
+int weight_prep_up2(const float* w, void* out, int C, int K, cudaStream_t st) {
+    const long long n = 16LL * C * K;
+    int blocks = cdiv(n, 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    weight_prep_up2_kernel<<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)out, C, K);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
 }
 
 }  // namespace urir

@@ -124,6 +124,19 @@ class UNetEngine:
             taps, a, b = w_ck.shape
             rows.append([self.param[name].data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), taps, a, b])
         self.wprep_table = torch.tensor(rows, dtype=torch.int64, device=dev)
+        # w_up2 operand of the stride-2 layers (3x3 only): Conv2DTranspose forward and strided-conv dgrad as one
+        # 2x2 problem on the half-resolution grid (urir_conv2d_dgrad_up2); allocated where the kernel applies
+        self.wup2 = {}
+        if self.kernels == 3:
+            H, W, _ = self.input_shape
+            for name, shape, kind in self.plan:
+                if kind == "convT_w" or (kind == "conv_w" and name.endswith(".down.w") and not name.startswith("enc1.")):
+                    lvl = int(name[3]) if name.startswith("enc") else 7 - int(name[3])     # level of the LARGE tensor + 1
+                    h, w = H >> (lvl - 2), W >> (lvl - 2)
+                    kh, kw, c, k = shape
+                    d = L.ConvDesc(1, h, w, c, k, 3, 3, 2, 0, 0, h // 2, w // 2, c, 0, k, 0, L.BF16, L.BF16, self.impl, 0, 0)
+                    if h % 2 == 0 and w % 2 == 0 and L.load().urir_conv_path(C.byref(d), 3) == 1:
+                        self.wup2[name[:-2]] = torch.empty(4, 4 * c, k, dtype=torch.bfloat16, device=dev)
         # per-BN scratch: stats (zeroed each forward), scale/shift, mean/rstd, backward sums
         bn_names = [n[:-len(".gamma")] for n in self.offsets if n.endswith(".gamma")]
         tot = sum(2 * self.shapes[b + ".gamma"][0] for b in bn_names)
@@ -161,6 +174,8 @@ class UNetEngine:
     def refresh_operands(self):
         """fp32 masters -> bf16 operand layouts (after load / after every optimiser step)."""
         L.call("weight_prep_batched", self.wprep_table.data_ptr(), self.wprep_table.shape[0])
+        for name, buf in self.wup2.items():
+            L.call("weight_prep_up2", self.param[name + ".w"].data_ptr(), buf.data_ptr(), buf.shape[1] // 4, buf.shape[2])
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, B):
@@ -219,6 +234,10 @@ class UNetEngine:
     def _conv_dgrad(self, name, dy, dx, k, stride, stats=None, accumulate=0, bias=False):
         """dx (the conv's input side) from dy (its output side); desc describes the forward conv."""
         d = self._desc(dx, dy, k, stride, L.ACT_NONE, accumulate)
+        if stride == 2 and stats is None and name in self.wup2:
+            L.call("conv2d_dgrad_up2", C.byref(d), dy.ptr(), self.wup2[name].data_ptr(),
+                   self.param[name + ".b"].data_ptr() if bias else None, dx.ptr())
+            return
         w_ck, w_kc = self._w(name)
         L.call("conv2d_dgrad", C.byref(d), dy.ptr(), w_ck, w_kc,
                self.param[name + ".b"].data_ptr() if bias else None, dx.ptr(),
