@@ -30,6 +30,10 @@ CASES = {
     "wgrad_full64": ("wgrad", 64, 144, 160, 64, 32, 3, 1),
     "wgrad_d4a": ("wgrad", 64, 72, 80, 128, 64, 3, 1),
     "dgrad_s2_half": ("dgrad", 64, 72, 80, 64, 128, 3, 2),
+    "fprop_l3": ("fprop", 64, 36, 40, 128, 128, 3, 1),
+    "dgrad_l3": ("dgrad", 64, 36, 40, 128, 128, 3, 1),
+    "fprop_l3a": ("fprop", 64, 36, 40, 256, 128, 3, 1),
+    "fprop_l4": ("fprop", 64, 18, 20, 256, 256, 3, 1),
     "fprop_s2": ("fprop", 64, 144, 160, 32, 64, 3, 2),
 }
 
@@ -45,7 +49,8 @@ def run(which, reps=int(os.environ.get("PROF_REPS", "3"))):
     w_ck = torch.randn(k * k, Cc, K, device="cuda").to(torch.bfloat16)
     w_kc = torch.randn(k * k, K, Cc, device="cuda").to(torch.bfloat16)
     dw = torch.zeros(k, k, Cc, K, device="cuda")
-    d = L.ConvDesc(N, H, W, Cc, K, k, k, s, pt, pl, P, Q, Cc, 0, y_ld, 0, L.dtype_code(x), L.dtype_code(dy), L.IMPL_AUTO, 0, 0)
+    acc = 1 if os.environ.get("PROF_ACC") else 0
+    d = L.ConvDesc(N, H, W, Cc, K, k, k, s, pt, pl, P, Q, Cc, 0, y_ld, 0, L.dtype_code(x), L.dtype_code(dy), L.IMPL_AUTO, 0, acc)
     stats = torch.zeros(2 * max(Cc, K), device="cuda") if os.environ.get("PROF_STATS") and Cc > 2 and K > 2 else None
     sp = stats.data_ptr() if stats is not None else None
     ts = []

@@ -104,7 +104,7 @@ __device__ __forceinline__ void hl_transpose4(uint32_t (&pk)[16], int lane) {
 }
 __device__ __forceinline__ int hl_col_of_lane(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool ACC>
 __global__ void __launch_bounds__(384, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
     constexpr uint32_t SWZ = (BLOCK_K == 64) ? SWZ_128B : SWZ_64B;
@@ -260,6 +260,20 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 gout[i] = p.out + p.o_off + (long long)n * p.o_sn + (long long)hh * p.o_sh + (long long)ww * p.o_sw;
             }
             uint32_t pk[16];
+            // out += (accumulate): the previous contents of this lane's own pixel are fetched one 64-column phase
+            // ahead (before the accumulator barrier / during the previous phase), so the loads overlap the waits
+            constexpr int PH_COLS = BLOCK_N < 64 ? BLOCK_N : 64;
+            uint4 oldv[ACC ? PH_COLS / 8 : 1];
+            const __nv_bfloat16* orow = p.out + p.o_off + (long long)n * p.o_sn + (long long)h * p.o_sh + (long long)w * p.o_sw;
+            auto load_old = [&](int ph) {
+#pragma unroll
+                for (int q = 0; q < PH_COLS / 8; ++q) {
+                    const int col = ph * PH_COLS + q * 8;
+                    oldv[q] = valid ? *reinterpret_cast<const uint4*>(orow + p.grp_off[n_tile * (BLOCK_N / 32) + (col >> 5)] + (col & 31))
+                                    : make_uint4(0, 0, 0, 0);
+                }
+            };
+            if (ACC) load_old(0);
             const bool tre = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 128 && quarter == 0 && lane == 0;
             mbar_wait(tfull_bar + acc, (it >> 2) & 1);
             if (tre) p.trace[it * 8 + 4] = clock64();
@@ -267,13 +281,25 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
             // TMEM loads have a long latency while the tensor pipe is streaming MMAs (the dominant epilogue stall
             // in the ncu source view), so all loads of a phase (<= 64 columns) are issued before one wait.
-            constexpr int PH_COLS = BLOCK_N < 64 ? BLOCK_N : 64;
 #pragma unroll
             for (int ph = 0; ph < BLOCK_N / PH_COLS; ++ph) {
                 uint32_t r[PH_COLS];
 #pragma unroll
                 for (int c = 0; c < PH_COLS / 32; ++c) tmem_ld32(lane_addr + ph * PH_COLS + c * 32, r + c * 32);
                 tmem_ld_wait();
+                if (ACC) {
+#pragma unroll
+                    for (int q = 0; q < PH_COLS / 8; ++q) {
+                        const uint32_t ow[4] = {oldv[q].x, oldv[q].y, oldv[q].z, oldv[q].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = unpack_bf16x2(ow[j]);
+                            r[q * 8 + 2 * j] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * j]) + f.x);
+                            r[q * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * j + 1]) + f.y);
+                        }
+                    }
+                    if (ph + 1 < BLOCK_N / PH_COLS) load_old(ph + 1);
+                }
                 if (tre && ph == 0) p.trace[it * 8 + 6] = clock64();
 #pragma unroll
                 for (int bb = 0; bb < PH_COLS / 16; ++bb) {
@@ -284,14 +310,6 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                         const float4 bs = *reinterpret_cast<const float4*>(sbias + b * 16 + 4 * j4);
                         v[4 * j4] = __uint_as_float(r[bb * 16 + 4 * j4]) + bs.x; v[4 * j4 + 1] = __uint_as_float(r[bb * 16 + 4 * j4 + 1]) + bs.y;
                         v[4 * j4 + 2] = __uint_as_float(r[bb * 16 + 4 * j4 + 2]) + bs.z; v[4 * j4 + 3] = __uint_as_float(r[bb * 16 + 4 * j4 + 3]) + bs.w;
-                    }
-                    if (p.accumulate && valid) {      // out += : add the previous contents (this lane's own pixel) in fp32
-                        const __nv_bfloat16* old = p.out + p.o_off + (long long)n * p.o_sn + (long long)h * p.o_sh + (long long)w * p.o_sw +
-                                                   p.grp_off[n_tile * (BLOCK_N / 32) + (b >> 1)] + (b & 1) * 16;
-                        const uint4 o0 = *reinterpret_cast<const uint4*>(old), o1 = *reinterpret_cast<const uint4*>(old + 8);
-                        const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float2 f = unpack_bf16x2(ow[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
                     }
                     pk[(b & 1) * 8 + 0] = pack_bf16x2(v[0], v[1]); pk[(b & 1) * 8 + 1] = pack_bf16x2(v[2], v[3]);
                     pk[(b & 1) * 8 + 2] = pack_bf16x2(v[4], v[5]); pk[(b & 1) * 8 + 3] = pack_bf16x2(v[6], v[7]);
@@ -358,6 +376,15 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 static int halo_block_k(int kg) { return kg % 64 == 0 ? 64 : 32; }
 static int halo_block_n(int n) { return n % 128 == 0 ? 128 : n % 64 == 0 ? 64 : 32; }
+// largest GEMM-N tile whose resident weights (all taps, kg channels) leave room for >= 3 activation stages:
+// a narrower tile re-reads the activation once per N tile but keeps the halo reuse and the persistent pipeline
+static int halo_block_n_fit(int ng, int kg, int ntaps, int ph, int pw) {
+    const int BK = halo_block_k(kg);
+    const long long a_stage = (((long long)ph * pw * BK * 2) + 1023) / 1024 * 1024;
+    for (int bn = halo_block_n(ng); bn >= 32; bn >>= 1)
+        if ((long long)ntaps * kg * bn * 2 + 3 * a_stage + 2048 <= HL_SMEM_BUDGET) return bn;
+    return 0;
+}
 
 // op 0: fprop (GEMM-K = C, GEMM-N = K), op 1: dgrad (GEMM-K = K, GEMM-N = C)
 bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
@@ -367,19 +394,18 @@ bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
     if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
     const int kg = op == 0 ? d->C : d->K, ng = op == 0 ? d->K : d->C;
     if (kg % 32 || ng % 32) return false;
-    const int BK = halo_block_k(kg), BN = halo_block_n(ng);
-    const long long w_bytes = (long long)d->R * d->S * kg * BN * 2;
-    const long long a_stage = (((long long)(HL_TH + d->R - 1) * (HL_TW + d->S - 1) * BK * 2) + 1023) / 1024 * 1024;
-    if (w_bytes + 3 * a_stage + 2048 > HL_SMEM_BUDGET) return false;
+    const int BN = halo_block_n_fit(ng, kg, d->R * d->S, HL_TH + d->R - 1, HL_TW + d->S - 1);
+    if (BN == 0) return false;
+    if (BN < 64 && BN < ng && !forced) return false;      // 44-cycle N = 32 MMAs over several N tiles do not pay
     // worth it only where the one-tile-per-CTA kernel is latency / L2 bound: many tiles per SM
     const long long tiles = (long long)d->N * cdiv(d->H, HL_TH) * cdiv(d->W, HL_TW);
     return forced || tiles >= 148 * 4;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool ACC = false>
 static int launch_halo(const HaloMaps& maps, const HaloParams& p, int n_tiles, int smem, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = conv_halo_kernel<BN, BK>;
+    auto kern = conv_halo_kernel<BN, BK, ACC>;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BUDGET + 4096)); attr_set = true; }
     int gx = 148 / n_tiles; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
@@ -396,7 +422,8 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     const int kg = op == 0 ? d->C : d->K, ng = op == 0 ? d->K : d->C;
     const int a_ld = op == 0 ? d->x_ld : d->y_ld, a_coff = op == 0 ? d->x_coff : d->y_coff;
     const int o_ld = op == 0 ? d->y_ld : d->x_ld, o_coff = op == 0 ? d->y_coff : d->x_coff;
-    const int BK = halo_block_k(kg), BN = halo_block_n(ng);
+    const int BK = halo_block_k(kg), BN = halo_block_n_fit(ng, kg, d->R * d->S, HL_TH + d->R - 1, HL_TW + d->S - 1);
+    if (BN == 0) return fail(URIR_ERR_UNSUP, "halo conv: the weights of one 32-column tile do not fit in shared memory");
     HaloMaps maps; HaloParams p; memset(&p, 0, sizeof(p));
     p.N = d->N; p.H = d->H; p.W = d->W;
     p.tiles_h = cdiv(d->H, HL_TH); p.tiles_w = cdiv(d->W, HL_TW); p.total_tiles = p.tiles_h * p.tiles_w * d->N;
@@ -512,6 +539,11 @@ int conv_halo_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, co
     }
     const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
     const int n_tiles = ng / BN;
+    if (p.accumulate) {      // 4C is a multiple of 128: only the BLOCK_N = 128 kernels exist with the accumulate epilogue
+        if (BN == 128 && BK == 32) return launch_halo<128, 32, true>(maps, p, n_tiles, smem, st);
+        if (BN == 128 && BK == 64) return launch_halo<128, 64, true>(maps, p, n_tiles, smem, st);
+        return fail(URIR_ERR_UNSUP, "up-2 halo conv: no accumulate kernel for BLOCK_N=%d BLOCK_K=%d", BN, BK);
+    }
 #define URIR_HL(BN_, BK_) if (BN == BN_ && BK == BK_) return launch_halo<BN_, BK_>(maps, p, n_tiles, smem, st);
     URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
 #undef URIR_HL
