@@ -63,7 +63,9 @@ typedef struct urir_conv_desc {
     int32_t x_dtype, y_dtype;   /* URIR_F32 | URIR_BF16                               */
     int32_t impl;               /* URIR_IMPL_*                                        */
     int32_t act;                /* fprop only: URIR_ACT_* applied after bias          */
-    int32_t accumulate;         /* fprop/dgrad: out += result instead of out = result */
+    int32_t accumulate;         /* fprop/dgrad: out += result instead of out = result;
+                                   wgrad: dw += result (the caller zeroed dw, e.g. one memset of the
+                                   flat gradient buffer) instead of dw = result                        */
 } urir_conv_desc;
 
 typedef struct urir_stft_desc {
@@ -133,17 +135,27 @@ int urir_bn_finalize(const float* stats, double count, const float* gamma, const
 /* y = relu(x*scale + shift); x, y bf16 (y may be a concat slice, or alias x). relu != 0. */
 int urir_bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* scale_shift,
                      void* y, int y_ld, int y_coff, long long npix, int C, int relu, void* stream);
-/* sums[2C] (overwritten) = [sum g, sum g*xhat], g = dy * (x*scale+shift > 0). */
+/* training-mode urir_bn_finalize + urir_bn_relu_fwd in ONE launch: y = relu(BN(x)) with the batch statistics
+ * taken from the conv epilogue's stats = [sum | sumsq]; also writes scale_shift / mean_rstd (for the backward
+ * pass) and updates the moving statistics. */
+int urir_bn_relu_fwd_train(const void* x, int x_ld, int x_coff, const float* stats, double count,
+                           const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                           float momentum, float eps, int unbiased_moving_var, float* scale_shift,
+                           float* mean_rstd, void* y, int y_ld, int y_coff, long long npix, int C,
+                           void* stream);
+/* sums[2C] = [sum g, sum g*xhat], g = dy * (x*scale+shift > 0). Overwritten; with prezeroed != 0 the caller
+ * has zeroed `sums` (one memset for all layers instead of one per call). */
 int urir_bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld,
                             int x_coff, const float* scale_shift, const float* mean_rstd,
-                            float* sums, long long npix, int C, void* stream);
+                            float* sums, long long npix, int C, int prezeroed, void* stream);
 /* dx = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n) (bf16); dgamma = sum_gx; dbeta = sum_g;
- * dbias (optional) = sum over pixels of dx = gradient of the preceding conv's bias. */
+ * dbias (optional) = sum over pixels of dx = gradient of the preceding conv's bias (with prezeroed != 0 the
+ * caller has zeroed it). */
 int urir_bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld,
                            int x_coff, const float* scale_shift, const float* mean_rstd,
                            const float* gamma, const float* sums, void* dx, int dx_ld,
                            int dx_coff, float* dgamma, float* dbeta, float* dbias, long long npix,
-                           int C, void* stream);
+                           int C, int prezeroed, void* stream);
 
 /* ---- vector block (u_net.py:253-263) --------------------------------------------------- */
 /* Embedding(2000,256) + Flatten: out bf16 [B, T*D] */

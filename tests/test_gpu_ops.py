@@ -43,17 +43,26 @@ def test_bn_relu_forward_backward():
     L.call("bn_relu_fwd", xg.data_ptr(), Cc, 0, ss.data_ptr(), ybuf.data_ptr(), ld, coff, npix, Cc, 1)
     assert U.rel_l2(ybuf[..., coff:].float(), yr.detach()) < 4e-3
     assert float(ybuf[..., :coff].float().abs().max()) == 0.0
+    # the fused training-mode launch (finalize + apply) gives the same tensors and moving statistics
+    mm2, mv2 = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    ss2, mr2 = torch.empty(2 * Cc, device="cuda"), torch.empty(2 * Cc, device="cuda")
+    ybuf2 = torch.zeros(N, H, W, ld, dtype=torch.bfloat16, device="cuda")
+    L.call("bn_relu_fwd_train", xg.data_ptr(), Cc, 0, stats.data_ptr(), float(npix), gam_g.data_ptr(), bet_g.data_ptr(),
+           mm2.data_ptr(), mv2.data_ptr(), 0.99, 1e-3, 0, ss2.data_ptr(), mr2.data_ptr(), ybuf2.data_ptr(), ld, coff,
+           npix, Cc)
+    assert torch.equal(ybuf2, ybuf) and torch.equal(ss2, ss) and torch.equal(mr2, mr)
+    assert torch.equal(mm2, mm) and torch.equal(mv2, mv)
 
     dybuf = torch.zeros(N, H, W, ld, dtype=torch.bfloat16, device="cuda")
     dybuf[..., coff:] = dy.cuda().to(torch.bfloat16)
     sums = torch.empty(2 * Cc, device="cuda")
     L.call("bn_relu_bwd_reduce", dybuf.data_ptr(), ld, coff, xg.data_ptr(), Cc, 0, ss.data_ptr(), mr.data_ptr(),
-           sums.data_ptr(), npix, Cc)
+           sums.data_ptr(), npix, Cc, 0)
     dx = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
     dgamma, dbeta, dbias = (torch.empty(Cc, device="cuda") for _ in range(3))
     L.call("bn_relu_bwd_apply", dybuf.data_ptr(), ld, coff, xg.data_ptr(), Cc, 0, ss.data_ptr(), mr.data_ptr(),
            gam_g.data_ptr(), sums.data_ptr(), dx.data_ptr(), Cc, 0, dgamma.data_ptr(), dbeta.data_ptr(),
-           dbias.data_ptr(), npix, Cc)
+           dbias.data_ptr(), npix, Cc, 0)
     assert U.rel_l2(dx.float(), gx) < 6e-3
     assert U.rel_l2(dgamma, gg) < 1e-4
     assert U.rel_l2(dbeta, gb) < 1e-4

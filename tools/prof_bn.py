@@ -36,9 +36,9 @@ def main():
         nb = npix * C * 2
         t = timeit(lambda: L.call("bn_relu_fwd", x.data_ptr(), C, 0, ss.data_ptr(), y.data_ptr(), C, 0, npix, C, 1))
         print(f"C={C:4d} npix={npix:8d} fwd    {t*1e3:7.1f} us {2*nb/t/1e6:7.0f} GB/s")
-        t = timeit(lambda: L.call("bn_relu_bwd_reduce", dy.data_ptr(), C, 0, x.data_ptr(), C, 0, ss.data_ptr(), mr.data_ptr(), sums.data_ptr(), npix, C))
+        t = timeit(lambda: L.call("bn_relu_bwd_reduce", dy.data_ptr(), C, 0, x.data_ptr(), C, 0, ss.data_ptr(), mr.data_ptr(), sums.data_ptr(), npix, C, 0))
         print(f"C={C:4d} npix={npix:8d} reduce {t*1e3:7.1f} us {2*nb/t/1e6:7.0f} GB/s")
-        t = timeit(lambda: L.call("bn_relu_bwd_apply", dy.data_ptr(), C, 0, x.data_ptr(), C, 0, ss.data_ptr(), mr.data_ptr(), gamma.data_ptr(), sums.data_ptr(), y.data_ptr(), C, 0, dg.data_ptr(), db.data_ptr(), dbias.data_ptr(), npix, C))
+        t = timeit(lambda: L.call("bn_relu_bwd_apply", dy.data_ptr(), C, 0, x.data_ptr(), C, 0, ss.data_ptr(), mr.data_ptr(), gamma.data_ptr(), sums.data_ptr(), y.data_ptr(), C, 0, dg.data_ptr(), db.data_ptr(), dbias.data_ptr(), npix, C, 0))
         print(f"C={C:4d} npix={npix:8d} apply  {t*1e3:7.1f} us {3*nb/t/1e6:7.0f} GB/s")
 
 

@@ -51,9 +51,11 @@ _PROTOS = {
     "urir_channel_sum": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp]),
     "urir_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _i, _vp]),
     "urir_bn_relu_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _ll, _i, _i, _vp]),
-    "urir_bn_relu_bwd_reduce": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _ll, _i, _vp]),
+    "urir_bn_relu_fwd_train": (_i, [_vp, _i, _i, _vp, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp,
+                                    _vp, _i, _i, _ll, _i, _vp]),
+    "urir_bn_relu_bwd_reduce": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "urir_bn_relu_bwd_apply": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
-                                    _vp, _ll, _i, _vp]),
+                                    _vp, _ll, _i, _i, _vp]),
     "urir_embedding_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "urir_embedding_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "urir_dense_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -46,9 +46,11 @@ bool wgrad_halo_supported(const urir_conv_desc*, bool forced);
 int conv_wgrad_halo(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int bn_finalize(const float*, double, const float*, const float*, float*, float*, float, float, int, float*, float*, int, cudaStream_t);
 int bn_relu_fwd(const void*, int, int, const float*, void*, int, int, long long, int, int, cudaStream_t);
-int bn_relu_bwd_reduce(const void*, int, int, const void*, int, int, const float*, const float*, float*, long long, int, cudaStream_t);
+int bn_relu_bwd_reduce(const void*, int, int, const void*, int, int, const float*, const float*, float*, long long, int, int, cudaStream_t);
+int bn_relu_fwd_train(const void*, int, int, const float*, double, const float*, const float*, float*, float*, float, float, int,
+                      float*, float*, void*, int, int, long long, int, cudaStream_t);
 int bn_relu_bwd_apply(const void*, int, int, const void*, int, int, const float*, const float*, const float*, const float*,
-                      void*, int, int, float*, float*, float*, long long, int, cudaStream_t);
+                      void*, int, int, float*, float*, float*, long long, int, int, cudaStream_t);
 int channel_sum(const void*, int, long long, int, int, int, float*, cudaStream_t);
 int ampphase_loss(const float*, const float*, long long, float, float, int, float*, float*, void*, int, cudaStream_t);
 int adam(float*, const float*, float*, float*, long long, const float*, const int*, float, float, float, cudaStream_t);
@@ -197,17 +199,24 @@ int urir_bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* ss, void*
     URIR_CHECK_ARG(x && y && ss && npix > 0, "bn_relu_fwd: bad args");
     return bn_relu_fwd(x, x_ld, x_coff, ss, y, y_ld, y_coff, npix, C, relu, (cudaStream_t)stream);
 }
+int urir_bn_relu_fwd_train(const void* x, int x_ld, int x_coff, const float* stats, double count, const float* gamma,
+                           const float* beta, float* moving_mean, float* moving_var, float momentum, float eps,
+                           int unbiased_moving_var, float* scale_shift, float* mean_rstd, void* y, int y_ld, int y_coff,
+                           long long npix, int C, void* stream) {
+    return bn_relu_fwd_train(x, x_ld, x_coff, stats, count, gamma, beta, moving_mean, moving_var, momentum, eps,
+                             unbiased_moving_var, scale_shift, mean_rstd, y, y_ld, y_coff, npix, C, (cudaStream_t)stream);
+}
 int urir_bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
-                            const float* mr, float* sums, long long npix, int C, void* stream) {
+                            const float* mr, float* sums, long long npix, int C, int prezeroed, void* stream) {
     URIR_CHECK_ARG(dy && x && ss && mr && sums && npix > 0, "bn_relu_bwd_reduce: bad args");
-    return bn_relu_bwd_reduce(dy, dy_ld, dy_coff, x, x_ld, x_coff, ss, mr, sums, npix, C, (cudaStream_t)stream);
+    return bn_relu_bwd_reduce(dy, dy_ld, dy_coff, x, x_ld, x_coff, ss, mr, sums, npix, C, prezeroed, (cudaStream_t)stream);
 }
 int urir_bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
                            const float* mr, const float* gamma, const float* sums, void* dx, int dx_ld, int dx_coff,
-                           float* dgamma, float* dbeta, float* dbias, long long npix, int C, void* stream) {
+                           float* dgamma, float* dbeta, float* dbias, long long npix, int C, int prezeroed, void* stream) {
     URIR_CHECK_ARG(dy && x && ss && mr && sums && dx && npix > 0, "bn_relu_bwd_apply: bad args");
     return bn_relu_bwd_apply(dy, dy_ld, dy_coff, x, x_ld, x_coff, ss, mr, gamma, sums, dx, dx_ld, dx_coff, dgamma, dbeta,
-                             dbias, npix, C, (cudaStream_t)stream);
+                             dbias, npix, C, prezeroed, (cudaStream_t)stream);
 }
 
 int urir_embedding_fwd(const int32_t* idx, const float* table, void* out, int B, int T, int D, int vocab, void* stream) {

@@ -223,7 +223,7 @@ static int launch_wgrad(const ConvP& p, const void* x, const void* dy, float* dw
     if (pix < 256) pix = 256;
     if (pix > M) pix = M;
     const int chunks = cdiv(M, pix);
-    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.R * p.S * p.C * p.K, st));
+    if (!p.accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.R * p.S * p.C * p.K, st));
     dim3 grid(tiles, chunks), block(256);
     conv_wgrad_simt<TX, TDY><<<grid, block, 0, st>>>(p, (const TX*)x, (const TDY*)dy, dw, KT, CT, (int)pix);
     URIR_LAUNCH_OK(0);

@@ -229,7 +229,7 @@ int stem_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     StemP p = to_stem(d);
     const long long M = (long long)p.N * p.P * p.Q;
     const int J = p.R * p.S * p.C;
-    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)J * p.K, st));
+    if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)J * p.K, st));
     long long chunks = 148LL * 8 / (p.K / STEM_KT);
     long long pix = (M + chunks - 1) / chunks;
     if (pix < 64) pix = 64;

@@ -371,7 +371,7 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     }
     static bool attr_set = false;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM)); attr_set = true; }
-    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.ntaps * d->C * d->K, st));
+    if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.ntaps * d->C * d->K, st));
     int gx = p.total_tiles < 148 * 2 ? p.total_tiles : 148 * 2;
     dim3 grid(gx, p.CW_total / 32);
     thin_wgrad_kernel<<<grid, 128, TW_SMEM, st>>>(map, p);

@@ -231,7 +231,7 @@ int conv_wgrad_halo(const urir_conv_desc* d, const void* x, const void* dy, floa
         int rc = encode_map(&maps.b, (const char*)dy + (size_t)d->y_coff * 2, 4, dims, strides, box, KN * 2);
         if (rc) return rc;
     }
-    URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->C * d->K, st));
+    if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->C * d->K, st));
     const int n_cblk = d->C / p.Cc;
     int gx = 148 / n_cblk; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;

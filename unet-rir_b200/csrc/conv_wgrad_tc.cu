@@ -347,8 +347,8 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
         if (rc) return rc;
     }
     // without a pixel split every dw element has exactly one producer (all channel tiles exact): store, do not add
-    p.direct = splits == 1 && d->K % BN == 0 && (d->K & 3) == 0 && (d->C % 128 == 0 || d->C == m_valid) ? 1 : 0;
-    if (!p.direct) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps * d->C * d->K, st));
+    p.direct = !d->accumulate && splits == 1 && d->K % BN == 0 && (d->K & 3) == 0 && (d->C % 128 == 0 || d->C == m_valid) ? 1 : 0;
+    if (!p.direct && !d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps * d->C * d->K, st));
     dim3 grid(splits, p.n_mtiles * n_ntiles, tap_groups);
     if (BN == 128) return launch_wg<128>(maps, p, grid, smem_bytes, st);
     if (BN == 64) return launch_wg<64>(maps, p, grid, smem_bytes, st);

@@ -370,6 +370,68 @@ bn_relu_bwd_apply_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, i
     }
 }
 
+
+// training-mode BatchNorm + ReLU in one launch: every thread derives scale / shift of its 8 channels from the
+// conv epilogue's [sum | sumsq] (same arithmetic as bn_finalize_kernel), block 0 also writes scale_shift /
+// mean_rstd for the backward pass and updates the moving statistics.
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+bn_relu_fwd_train_pow2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
+                              const float* __restrict__ stats, double count, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ moving_mean,
+                              float* __restrict__ moving_var, float momentum, float eps, int unbiased,
+                              float* __restrict__ scale_shift, float* __restrict__ mean_rstd,
+                              __nv_bfloat16* __restrict__ y, int y_ld, int y_coff, long long npix, int C, int g_shift) {
+    const int G = C >> 3, lanes = 256 >> g_shift;
+    const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
+    float sc[8], sh[8];
+    {
+        float s1[8], s2[8], gm[8], bt[8];
+        ld8(stats + c, s1); ld8(stats + C + c, s2);
+        if (gamma) ld8(gamma + c, gm);
+        if (beta) ld8(beta + c, bt);
+        const bool writer = blockIdx.x == 0 && lane == 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double m = (double)s1[j] / count;
+            double v = (double)s2[j] / count - m * m;
+            if (v < 0) v = 0;
+            const float mean = (float)m, var = (float)v;
+            const float rstd = rsqrtf(var + eps);
+            const float g = gamma ? gm[j] : 1.f, b = beta ? bt[j] : 0.f;
+            sc[j] = g * rstd;
+            sh[j] = b - mean * g * rstd;
+            if (writer) {
+                if (moving_mean) {
+                    const double mv = unbiased ? v * (count / (count > 1 ? count - 1 : 1)) : v;
+                    moving_mean[c + j] = moving_mean[c + j] * momentum + mean * (1.f - momentum);
+                    moving_var[c + j] = moving_var[c + j] * momentum + (float)mv * (1.f - momentum);
+                }
+                scale_shift[c + j] = sc[j]; scale_shift[C + c + j] = sh[j];
+                if (mean_rstd) { mean_rstd[c + j] = mean; mean_rstd[C + c + j] = rstd; }
+            }
+        }
+    }
+    const __nv_bfloat16* xp = x + x_coff + c;
+    __nv_bfloat16* yp = y + y_coff + c;
+    const long long pstride = (long long)gridDim.x * lanes;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += UNROLL * pstride) {
+        uint4 u[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+            if (p0 + q * pstride < npix) u[q] = ld_nc_v4(xp + (p0 + q * pstride) * x_ld);
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            if (p0 + q * pstride >= npix) break;
+            float v[8];
+            unpack8(u[q], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+            *reinterpret_cast<uint4*>(yp + (p0 + q * pstride) * y_ld) = pack8(v);
+        }
+    }
+}
+
 // C/8 a power of two <= 256 -> log2(C/8), else -1
 static int pow2_shift(int C) {
     if (C % 8) return -1;
@@ -424,11 +486,31 @@ int bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* ss, void* y, i
     return URIR_OK;
 }
 
+int bn_relu_fwd_train(const void* x, int x_ld, int x_coff, const float* stats, double count, const float* gamma,
+                      const float* beta, float* mm, float* mv, float momentum, float eps, int unbiased,
+                      float* scale_shift, float* mean_rstd, void* y, int y_ld, int y_coff, long long npix, int C,
+                      cudaStream_t st) {
+    URIR_CHECK_ARG(x && y && stats && scale_shift && npix > 0 && C > 0, "bn_relu_fwd_train: bad args");
+    URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, y_ld, y_coff), "bn_relu_fwd_train: C/ld/coff must be multiples of 8");
+    const int gs = pow2_shift(C);
+    if (gs < 0) {       // general channel counts: the two-launch path
+        int rc = bn_finalize(stats, count, gamma, beta, mm, mv, momentum, eps, unbiased, scale_shift, mean_rstd, C, st);
+        if (rc) return rc;
+        return bn_relu_fwd(x, x_ld, x_coff, scale_shift, y, y_ld, y_coff, npix, C, 1, st);
+    }
+    const int lanes = 256 >> gs;
+    bn_relu_fwd_train_pow2_kernel<4><<<pow2_grid(npix, lanes, 4, 4), 256, 0, st>>>(
+        (const __nv_bfloat16*)x, x_ld, x_coff, stats, count, gamma, beta, mm, mv, momentum, eps, unbiased, scale_shift,
+        mean_rstd, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, gs);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
 int bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
-                       const float* mr, float* sums, long long npix, int C, cudaStream_t st) {
+                       const float* mr, float* sums, long long npix, int C, int prezeroed, cudaStream_t st) {
     URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, dy_ld, dy_coff), "bn_bwd_reduce: C/ld/coff must be multiples of 8");
     URIR_CHECK_ARG(C <= 2048 && (C / 8) <= 256, "bn_bwd_reduce: C too large");
-    URIR_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st));
+    if (!prezeroed) URIR_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st));
     if (const int gs = pow2_shift(C); gs >= 0) {
         const int ln = 256 >> gs;
         bn_relu_bwd_reduce_pow2_kernel<4><<<pow2_grid(npix, ln, 8, 2), 256, 256 * 17 * sizeof(float), st>>>(
@@ -448,12 +530,12 @@ int bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, in
 
 int bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int x_ld, int x_coff, const float* ss,
                       const float* mr, const float* gamma, const float* sums, void* dx, int dx_ld, int dx_coff,
-                      float* dgamma, float* dbeta, float* dbias, long long npix, int C, cudaStream_t st) {
+                      float* dgamma, float* dbeta, float* dbias, long long npix, int C, int prezeroed, cudaStream_t st) {
     URIR_CHECK_ARG(vec8_ok(C, x_ld, x_coff) && vec8_ok(C, dy_ld, dy_coff) && vec8_ok(C, dx_ld, dx_coff),
                    "bn_bwd_apply: C/ld/coff must be multiples of 8");
     URIR_CHECK_ARG(C <= 1024, "bn_bwd_apply: C too large");
     URIR_CHECK_ARG(!dbias || (256 % (C / 8) == 0), "bn_bwd_apply: dbias needs C/8 to divide 256");
-    if (dbias) URIR_CUDA_OK(cudaMemsetAsync(dbias, 0, C * sizeof(float), st));
+    if (dbias && !prezeroed) URIR_CUDA_OK(cudaMemsetAsync(dbias, 0, C * sizeof(float), st));
     if (const int gs = pow2_shift(C); gs >= 0) {
         const int ln = 256 >> gs;
         bn_relu_bwd_apply_pow2_kernel<4><<<pow2_grid(npix, ln, 8, 2), 256, 256 * 9 * sizeof(float), st>>>(

@@ -244,7 +244,8 @@ class UNetEngine:
                None if stats is None else stats.data_ptr())
 
     def _conv_wgrad(self, name, x, dy, k, stride):
-        d = self._desc(x, dy, k, stride)
+        # accumulate = 1: the flat gradient buffer was zeroed once at the start of backward (no per-layer memset)
+        d = self._desc(x, dy, k, stride, accumulate=1)
         L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
 
     def _slot(self, arena, bn):
@@ -257,6 +258,13 @@ class UNetEngine:
         self._conv_fprop(cname, x, raw, k, 1, stats=stats)
         c = raw.C
         ss, mr = self._slot(self.ss_arena, bname), self._slot(self.mr_arena, bname)
+        if training:
+            L.call("bn_relu_fwd_train", raw.ptr(), raw.ld, raw.coff, stats.data_ptr(), float(raw.npix),
+                   self.param[bname + ".gamma"].data_ptr(), self.param[bname + ".beta"].data_ptr(),
+                   self.state[bname + ".moving_mean"].data_ptr(), self.state[bname + ".moving_var"].data_ptr(),
+                   PL.BN_MOMENTUM, PL.BN_EPS, self.bn_unbiased, ss.data_ptr(), mr.data_ptr(),
+                   out.ptr(), out.ld, out.coff, raw.npix, c)
+            return
         L.call("bn_finalize", None if stats is None else stats.data_ptr(), float(raw.npix),
                self.param[bname + ".gamma"].data_ptr(), self.param[bname + ".beta"].data_ptr(),
                self.state[bname + ".moving_mean"].data_ptr(), self.state[bname + ".moving_var"].data_ptr(),
@@ -269,11 +277,11 @@ class UNetEngine:
         sums = self._slot(self.sums_arena, bname)
         c = raw.C
         L.call("bn_relu_bwd_reduce", g_out.ptr(), g_out.ld, g_out.coff, raw.ptr(), raw.ld, raw.coff,
-               ss.data_ptr(), mr.data_ptr(), sums.data_ptr(), raw.npix, c)
+               ss.data_ptr(), mr.data_ptr(), sums.data_ptr(), raw.npix, c, 1)
         L.call("bn_relu_bwd_apply", g_out.ptr(), g_out.ld, g_out.coff, raw.ptr(), raw.ld, raw.coff,
                ss.data_ptr(), mr.data_ptr(), self.param[bname + ".gamma"].data_ptr(), sums.data_ptr(),
                g_raw.ptr(), g_raw.ld, g_raw.coff, self.grad[bname + ".gamma"].data_ptr(),
-               self.grad[bname + ".beta"].data_ptr(), self.grad[cname + ".b"].data_ptr(), raw.npix, c)
+               self.grad[bname + ".beta"].data_ptr(), self.grad[cname + ".b"].data_ptr(), raw.npix, c, 1)
         self._conv_wgrad(cname, x, g_raw, k, 1)
         if g_x is not None:
             self._conv_dgrad(cname, g_raw, g_x, k, 1, stats=g_x_stats, accumulate=accumulate)
@@ -375,6 +383,12 @@ class UNetEngine:
         k = self.kernels
         if segment in (None, 0):
             self.bstat_arena.zero_()
+            self.sums_arena.zero_()
+            # one zero-fill of the flat gradient buffer replaces a memset per wgrad / bias-gradient launch; the
+            # Dense kernel's gradient (plain stores, 47 MB) is skipped
+            lo, n = self.offsets["vec.dense.w"]
+            self.G[:lo].zero_()
+            self.G[lo + n:].zero_()
             g_out = View(b["g_out"])
             d1 = View(b["d1"])
             # head
