@@ -82,6 +82,9 @@ class UNetEngine:
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.losses_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.side = torch.cuda.Stream(device=self.device)
+        self.overlap_wgrad = True
+        self._side_dirty = False
 
     # ------------------------------------------------------------------ parameters
     def _build_params(self, seed):
@@ -244,9 +247,25 @@ class UNetEngine:
                None if stats is None else stats.data_ptr())
 
     def _conv_wgrad(self, name, x, dy, k, stride):
+        """Weight gradient on the side stream: it only feeds the optimiser, so it runs concurrently with the
+        dgrad / BatchNorm chain of the main stream (fills the SMs the small deep-layer grids leave idle and
+        overlaps tensor-bound with HBM-bound kernels). Joined by _join_side() at the end of a backward segment;
+        captured into the CUDA graph as a parallel branch."""
         # accumulate = 1: the flat gradient buffer was zeroed once at the start of backward (no per-layer memset)
         d = self._desc(x, dy, k, stride, accumulate=1)
-        L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
+        if not self.overlap_wgrad:
+            L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
+            return
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
+        self._side_dirty = True
+
+    def _join_side(self):
+        if self._side_dirty:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_dirty = False
 
     def _slot(self, arena, bn):
         o, n = self.bn_slot[bn]
@@ -415,6 +434,8 @@ class UNetEngine:
                 self._conv_fprop(f"dec{j}.up", g_up, g_x_in, k, 2, stats=st2, bias=False)   # ConvT dgrad
                 if j == 2:
                     self.grad["vec.proj.b"].copy_(st2[:x_in.C])
+            if segment == 0:
+                self._join_side()
         if segment in (None, 1):
             # bottleneck: z = e5 + proj(v16)
             g_z = View(b["g_z"])
@@ -426,6 +447,8 @@ class UNetEngine:
                    b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
             L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), L.BF16,
                    self.grad["vec.emb"].data_ptr(), B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+            if segment == 1:
+                self._join_side()
         if segment in (None, 2):
             # encoder, level 5 up to level 1
             g_e = View(b["g_z"])
@@ -445,6 +468,7 @@ class UNetEngine:
                     g_e = g_e_prev
                 else:
                     self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
+            self._join_side()
 
     # ------------------------------------------------------------------ loss + optimiser
     def loss_and_grad(self, y_true, w_amp, w_ph, need_grad=True):
