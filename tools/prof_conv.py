@@ -34,6 +34,14 @@ CASES = {
     "dgrad_l3": ("dgrad", 64, 36, 40, 128, 128, 3, 1),
     "fprop_l3a": ("fprop", 64, 36, 40, 256, 128, 3, 1),
     "fprop_l4": ("fprop", 64, 18, 20, 256, 256, 3, 1),
+    "wgrad_l3a": ("wgrad", 64, 36, 40, 256, 128, 3, 1),
+    "wgrad_l3": ("wgrad", 64, 36, 40, 128, 128, 3, 1),
+    "wgrad_l4a": ("wgrad", 64, 18, 20, 512, 256, 3, 1),
+    "wgrad_l4": ("wgrad", 64, 18, 20, 256, 256, 3, 1),
+    "wgrad_l5": ("wgrad", 64, 9, 10, 512, 512, 3, 1),
+    "wgrad_s2_l4": ("wgrad", 64, 18, 20, 256, 512, 3, 2),
+    "wgrad_s2_l3": ("wgrad", 64, 36, 40, 128, 256, 3, 2),
+    "wgrad_s2_full": ("wgrad", 64, 144, 160, 32, 64, 3, 2),
     "fprop_s2": ("fprop", 64, 144, 160, 32, 64, 3, 2),
 }
 

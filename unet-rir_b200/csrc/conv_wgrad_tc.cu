@@ -307,7 +307,10 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
     const int smem_bytes = p.stages * p.stage_bytes + (2 * WG_MAX_STAGES + 2) * 8 + 16 + 1024;
     const int n_ntiles = (d->K + BN - 1) / BN, tap_groups = ntaps / T;
     const int units = p.n_mtiles * n_ntiles * tap_groups;
-    int splits = (148 * 2 + units - 1) / units;
+    // One wave: as many pixel splits as fit on the machine at once (CTAs per SM follow from the shared-memory
+    // footprint). A grid slightly above a whole number of waves (300 CTAs on 296 slots) costs a full extra wave.
+    const int ctas_per_sm = smem_bytes <= 113 * 1024 ? 2 : 1;
+    int splits = (148 * ctas_per_sm) / units;
     if (splits > p.total_tiles) splits = p.total_tiles;
     if (splits < 1) splits = 1;
     p.tiles_per_cta = cdiv(p.total_tiles, splits);
