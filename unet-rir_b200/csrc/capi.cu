@@ -18,6 +18,11 @@ int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("URIR_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
 void count_launch(int kind) { g_launches_all++; if (kind == 1) g_launches_tc++; }
 
 // implemented in the other translation units

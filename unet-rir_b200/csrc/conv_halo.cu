@@ -147,6 +147,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();          // everything above overlapped the previous kernel's tail
 
     if (warp == 4) {
         // ===================== TMA producer =====================
@@ -410,7 +411,7 @@ static int launch_halo(const HaloMaps& maps, const HaloParams& p, int n_tiles, i
     int gx = 148 / n_tiles; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     dim3 grid(gx, n_tiles);
-    kern<<<grid, 384, smem, st>>>(maps, p);
+    URIR_CUDA_OK(launch_pdl(kern, grid, dim3(384), smem, st, maps, p));
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }

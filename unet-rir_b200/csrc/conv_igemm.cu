@@ -123,6 +123,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
 
     const int total_iters = tile_live ? ntaps * p.kchunks : 0;
 
@@ -321,7 +322,7 @@ static int launch_cfg(const IgemmMaps& maps, const IgemmParams& p, int n_tiles, 
         attr_set = true;
     }
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, n_tiles, p.n_classes);
-    kern<<<grid, 192, L::TOTAL, st>>>(maps, p);
+    URIR_CUDA_OK(launch_pdl(kern, grid, dim3(192), L::TOTAL, st, maps, p));
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }

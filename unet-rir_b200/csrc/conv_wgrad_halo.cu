@@ -85,6 +85,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhaloMaps maps, const __grid_cons
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
 
     if (warp == 4) {
         // ===================== TMA producer: two boxes per pixel tile =====================
@@ -197,7 +198,7 @@ static int launch_wh(const WhaloMaps& maps, const WhaloParams& p, dim3 grid, int
     static bool attr_set = false;
     auto kern = conv_wgrad_halo_kernel<KN>;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM_BUDGET + 8192)); attr_set = true; }
-    kern<<<grid, 192, smem, st>>>(maps, p);
+    URIR_CUDA_OK(launch_pdl(kern, grid, dim3(192), smem, st, maps, p));
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }

@@ -92,6 +92,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
 
     if (warp == 4) {
         // ===================== TMA producer =====================
@@ -261,7 +262,7 @@ static int launch_wg(const WgradMaps& maps, const WgradParams& p, dim3 grid, int
         URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BUDGET + 4096));
         attr_set = true;
     }
-    kern<<<grid, 192, smem_bytes, st>>>(maps, p);
+    URIR_CUDA_OK(launch_pdl(kern, grid, dim3(192), smem_bytes, st, maps, p));
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }

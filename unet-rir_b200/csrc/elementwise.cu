@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_fwd_pow2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
                         const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ y, int y_ld,
                         int y_coff, long long npix, int C, int g_shift, int relu) {
+    pdl_sync();
     const int G = C >> 3, lanes = 256 >> g_shift;
     const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
     float sc[8], sh[8];
@@ -262,6 +263,7 @@ bn_relu_bwd_reduce_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, 
                                const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
                                const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
                                float* __restrict__ sums, long long npix, int C, int g_shift) {
+    pdl_sync();
     extern __shared__ float red[];             // [256][17]
     const int G = C >> 3, lanes = 256 >> g_shift;
     const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
@@ -312,6 +314,7 @@ bn_relu_bwd_apply_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, i
                               __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                               long long npix, int C, int g_shift) {
+    pdl_sync();
     extern __shared__ float red[];             // [256][9]
     const int G = C >> 3, lanes = 256 >> g_shift;
     const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
@@ -382,6 +385,7 @@ bn_relu_fwd_train_pow2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int
                               float* __restrict__ moving_var, float momentum, float eps, int unbiased,
                               float* __restrict__ scale_shift, float* __restrict__ mean_rstd,
                               __nv_bfloat16* __restrict__ y, int y_ld, int y_coff, long long npix, int C, int g_shift) {
+    pdl_sync();
     const int G = C >> 3, lanes = 256 >> g_shift;
     const int c = (threadIdx.x & (G - 1)) << 3, lane = threadIdx.x >> g_shift;
     float sc[8], sh[8];
@@ -475,8 +479,8 @@ int bn_relu_fwd(const void* x, int x_ld, int x_coff, const float* ss, void* y, i
     URIR_CHECK_ARG(C <= 2048, "bn_relu_fwd: C too large");
     if (const int gs = pow2_shift(C); gs >= 0) {
         const int lanes = 256 >> gs;
-        bn_relu_fwd_pow2_kernel<4><<<pow2_grid(npix, lanes, 4, 4), 256, 0, st>>>(
-            (const __nv_bfloat16*)x, x_ld, x_coff, ss, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, gs, relu);
+        URIR_CUDA_OK(launch_pdl(bn_relu_fwd_pow2_kernel<4>, dim3(pow2_grid(npix, lanes, 4, 4)), dim3(256), 0, st,
+            (const __nv_bfloat16*)x, x_ld, x_coff, ss, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, gs, relu));
         URIR_LAUNCH_OK(0);
         return URIR_OK;
     }
@@ -499,9 +503,9 @@ int bn_relu_fwd_train(const void* x, int x_ld, int x_coff, const float* stats, d
         return bn_relu_fwd(x, x_ld, x_coff, scale_shift, y, y_ld, y_coff, npix, C, 1, st);
     }
     const int lanes = 256 >> gs;
-    bn_relu_fwd_train_pow2_kernel<4><<<pow2_grid(npix, lanes, 4, 4), 256, 0, st>>>(
+    URIR_CUDA_OK(launch_pdl(bn_relu_fwd_train_pow2_kernel<4>, dim3(pow2_grid(npix, lanes, 4, 4)), dim3(256), 0, st,
         (const __nv_bfloat16*)x, x_ld, x_coff, stats, count, gamma, beta, mm, mv, momentum, eps, unbiased, scale_shift,
-        mean_rstd, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, gs);
+        mean_rstd, (__nv_bfloat16*)y, y_ld, y_coff, npix, C, gs));
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
@@ -513,8 +517,8 @@ int bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, in
     if (!prezeroed) URIR_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st));
     if (const int gs = pow2_shift(C); gs >= 0) {
         const int ln = 256 >> gs;
-        bn_relu_bwd_reduce_pow2_kernel<4><<<pow2_grid(npix, ln, 8, 2), 256, 256 * 17 * sizeof(float), st>>>(
-            (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C, gs);
+        URIR_CUDA_OK(launch_pdl(bn_relu_bwd_reduce_pow2_kernel<4>, dim3(pow2_grid(npix, ln, 8, 2)), dim3(256), 256 * 17 * sizeof(float), st,
+            (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C, gs));
         URIR_LAUNCH_OK(0);
         return URIR_OK;
     }
@@ -538,9 +542,9 @@ int bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int
     if (dbias && !prezeroed) URIR_CUDA_OK(cudaMemsetAsync(dbias, 0, C * sizeof(float), st));
     if (const int gs = pow2_shift(C); gs >= 0) {
         const int ln = 256 >> gs;
-        bn_relu_bwd_apply_pow2_kernel<4><<<pow2_grid(npix, ln, 8, 2), 256, 256 * 9 * sizeof(float), st>>>(
+        URIR_CUDA_OK(launch_pdl(bn_relu_bwd_apply_pow2_kernel<4>, dim3(pow2_grid(npix, ln, 8, 2)), dim3(256), 256 * 9 * sizeof(float), st,
             (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, gamma, sums,
-            (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C, gs);
+            (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C, gs));
         URIR_LAUNCH_OK(0);
         return URIR_OK;
     }

@@ -27,7 +27,30 @@ void count_launch(int kind);   // kind: 0 = SIMT/bandwidth kernel, 1 = tcgen05 k
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Kernels launched through launch_pdl() may become resident while their predecessor in the stream is still
+// running: their prologue (barrier init, TMEM allocation, tensor-map prefetch, CTA scheduling) overlaps the
+// predecessor's tail. Such a kernel MUST execute pdl_wait() before it touches global memory a predecessor may
+// write (and before it writes anything); pdl_trigger() lets ITS successor start early in turn. Completion
+// order stays transitive because every kernel waits before it finishes. Captured into CUDA graphs as
+// programmatic dependency edges. URIR_NO_PDL=1 turns the attribute off (plain stream order).
+bool pdl_enabled();
+template <typename... KA, typename... A>
+static inline cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+
 // ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
 
