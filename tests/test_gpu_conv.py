@@ -352,6 +352,7 @@ WGRAD_HALO_CASES = [
     (3, 24, 48, 64, 64),      # E2b / D4b class: N = 192
     (2, 24, 32, 128, 64),     # D4a class: two 64-channel x blocks (grid.y = 2)
     (5, 72, 80, 64, 64),      # many tiles per persistent CTA (ring wrap-around)
+    (2, 20, 40, 32, 64),      # ragged tiles (H % 8 != 0, W % 16 != 0): TMA zero fill
 ]
 
 
@@ -415,3 +416,54 @@ def test_stride2_dgrad_as_2x2_on_half_grid(case):
     L.call("conv2d_dgrad_up2", C.byref(d3), dyg.data_ptr(), w_up2.data_ptr(), None, acc.data_ptr())
     assert U.rel_l2(acc[..., :Cc].float(), gx + base[..., :Cc]) < BF16_TOL
     assert torch.equal(acc[..., Cc:].cpu().float(), base[..., Cc:])
+
+
+S2_FPROP_CASES = [
+    (2, 16, 32, 32, 64),      # E2a class: one channel chunk, N = 64
+    (3, 24, 40, 64, 128),     # E3a class: two chunks, ragged half-resolution tiles
+    (5, 144, 160, 32, 64),    # many tiles per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", S2_FPROP_CASES, ids=[str(c) for c in S2_FPROP_CASES])
+def test_stride2_fprop_through_parity_planes(case):
+    """conv_halo_s2_fprop: the four parity planes of x as halo boxes, taps as descriptor offsets (forced through
+    URIR_IMPL_HALO); input read from a concat slice, with the fused channel statistics."""
+    N, H, W, Cc, K = case
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, 3, 2, seed=17)
+    ref = _oracle_fprop(x, w, bias, 2)
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    xw = torch.randn(N, H, W, 2 * Cc).to(torch.bfloat16).cuda()
+    xw[..., Cc:] = x.cuda().to(torch.bfloat16)
+    d = U.conv_desc(N, H, W, Cc, K, 3, 2, x_ld=2 * Cc, x_coff=Cc, impl=L.IMPL_HALO)
+    assert L.load().urir_conv_path(d, 0) == 1
+    y = torch.empty(N, P, Q, K, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2 * K, device="cuda")
+    U.run_fprop(d, xw, w_ck, w_kc, bias.cuda(), y, stats)
+    assert U.rel_l2(y.float(), ref) < BF16_TOL
+    assert U.max_abs(stats[:K], ref.sum(dim=(0, 1, 2))) < 2e-3 * float(ref.abs().sum(dim=(0, 1, 2)).max())
+    assert U.rel_l2(stats[K:], (ref ** 2).sum(dim=(0, 1, 2))) < F32_TOL * 10
+
+
+WGRAD_S2_CASES = [
+    (2, 16, 32, 32, 64),      # E2a / D5t class: dy has one 64-channel half
+    (3, 24, 40, 64, 128),     # E3a / D4t class: two x channel blocks, two dy halves, ragged tiles
+    (5, 144, 160, 32, 64),    # many tiles per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_S2_CASES, ids=[str(c) for c in WGRAD_S2_CASES])
+def test_stride2_wgrad_through_parity_planes(case):
+    """conv_wgrad_halo_s2: nine taps of a stride-2 kernel gradient from the four parity planes of x (stacked along
+    GEMM-M) and a dy box with one halo column (column shift stacked along GEMM-N); operands inside concat buffers."""
+    N, H, W, Cc, K = case
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, 3, 2, seed=19)
+    wr = w.clone().requires_grad_(True)
+    gw, = torch.autograd.grad(_oracle_fprop(x, wr, None, 2), [wr], dy)
+    xw = torch.randn(N, H, W, 2 * Cc).to(torch.bfloat16).cuda()
+    xw[..., :Cc] = x.cuda().to(torch.bfloat16)
+    d = U.conv_desc(N, H, W, Cc, K, 3, 2, x_ld=2 * Cc, x_coff=0, impl=L.IMPL_HALO)
+    assert L.load().urir_conv_path(d, 2) == 1
+    dw = torch.full((3, 3, Cc, K), 3.0, device="cuda")
+    U.run_wgrad(d, xw, dy.cuda().to(torch.bfloat16), dw)
+    assert U.rel_l2(dw, gw) < F32_TOL

@@ -40,6 +40,8 @@ bool thin_supported(const urir_conv_desc*, int op);
 bool halo_supported(const urir_conv_desc*, int op, bool forced);
 int conv_halo(const urir_conv_desc*, int op, const void*, const void*, const float*, void*, float*, cudaStream_t);
 bool halo_up2_supported(const urir_conv_desc*);
+bool halo_s2_fprop_supported(const urir_conv_desc*, bool forced);
+int conv_halo_s2_fprop(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
 int conv_halo_up2(const urir_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int weight_prep_up2(const float*, void*, int, int, cudaStream_t);
 bool head_fprop_supported(const urir_conv_desc*);
@@ -48,6 +50,8 @@ int thin_gemm(const urir_conv_desc*, const void*, const void*, const float*, voi
 int thin_wgrad(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int conv_wgrad_tc(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 bool wgrad_halo_supported(const urir_conv_desc*, bool forced);
+bool wgrad_halo_s2_supported(const urir_conv_desc*, bool forced);
+int conv_wgrad_halo_s2(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int conv_wgrad_halo(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int bn_finalize(const float*, double, const float*, const float*, float*, float*, float, float, int, float*, float*, int, cudaStream_t);
 int bn_relu_fwd(const void*, int, int, const float*, void*, int, int, long long, int, int, cudaStream_t);
@@ -114,6 +118,9 @@ int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, 
         return thin_gemm(d, x, w_ck, bias, y, true, st);                       // the 2-channel stem
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && head_fprop_supported(d))
         return head_fprop(d, x, w_ck, bias, y, st);                            // the 2-channel head
+    if (w_kc && d->stride == 2 && d->impl != URIR_IMPL_SIMT && d->impl != URIR_IMPL_TC && !env_force_simt() &&
+        halo_s2_fprop_supported(d, d->impl == URIR_IMPL_HALO))
+        return conv_halo_s2_fprop(d, x, w_kc, bias, y, stats, st);
     if (d->impl == URIR_IMPL_HALO && !(w_kc && halo_supported(d, 0, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the halo-tile tcgen05 path");
     if (w_kc && ((d->impl == URIR_IMPL_HALO) || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && halo_supported(d, 0, false))))
@@ -147,6 +154,9 @@ int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, fl
     URIR_CHECK_ARG(x && dy && dw, "conv2d_wgrad: null tensor");
     cudaStream_t st = (cudaStream_t)stream;
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && thin_supported(d, 2)) return thin_wgrad(d, x, dy, dw, st);
+    if (d->stride == 2 && (d->impl == URIR_IMPL_HALO || (d->impl == URIR_IMPL_AUTO && !env_force_simt())) &&
+        wgrad_halo_s2_supported(d, d->impl == URIR_IMPL_HALO))
+        return conv_wgrad_halo_s2(d, x, dy, dw, st);
     if (d->impl == URIR_IMPL_HALO && !wgrad_halo_supported(d, true))
         return fail(URIR_ERR_UNSUP, "conv2d_wgrad: shape not supported by the halo-tile tcgen05 path");
     if (d->impl == URIR_IMPL_HALO || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && wgrad_halo_supported(d, false)))
@@ -173,7 +183,9 @@ int urir_conv_path(const urir_conv_desc* d, int op) {
     if (!d || d->impl == URIR_IMPL_SIMT || (d->impl == URIR_IMPL_AUTO && env_force_simt())) return 0;
     if (thin_supported(d, op)) return 1;
     if (op < 2 && halo_supported(d, op, d->impl == URIR_IMPL_HALO)) return 1;
+    if (op == 0 && halo_s2_fprop_supported(d, d->impl == URIR_IMPL_HALO)) return 1;
     if (op == 2 && wgrad_halo_supported(d, d->impl == URIR_IMPL_HALO)) return 1;
+    if (op == 2 && wgrad_halo_s2_supported(d, d->impl == URIR_IMPL_HALO)) return 1;
     if (op == 0 && head_fprop_supported(d)) return 1;
     if (op == 0) return igemm_fprop_supported(d) ? 1 : 0;
     if (op == 1) return igemm_dgrad_supported(d) ? 1 : 0;

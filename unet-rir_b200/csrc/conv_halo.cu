@@ -39,6 +39,7 @@ struct HaloParams {
     int oh0, ow0;               // box origin relative to the tile origin
     int ntaps, nchunks;         // taps, GEMM-K chunks of BLOCK_K channels
     int stages, a_stage_bytes, a_box_bytes, w_bytes;
+    int nplanes, plane_bytes;   // boxes per stage (1, or the 4 parity planes of a stride-2 input) and their spacing
     long long o_sn, o_sh, o_sw; // output element strides
     long long o_off;
     const float* bias;
@@ -53,7 +54,7 @@ struct HaloParams {
     short wtap[36];             // weight tap index of tap t
 };
 
-struct HaloMaps { CUtensorMap a; CUtensorMap b; };
+struct HaloMaps { CUtensorMap a[4]; CUtensorMap b; };
 
 // Column sums of a [32 lanes] x [16 columns] block by recursive halving: step h exchanges half of the
 // values with lane ^ (16 >> h) and adds, so after all five steps lanes with (lane & 1) == 0 hold the total of
@@ -139,7 +140,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-    if (warp == 4 && lane == 0) { prefetch_tmap(&maps.a); prefetch_tmap(&maps.b); }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); }
     for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sstats[i] = 0.f;
     for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x)
         sbias[i] = (p.bias && n_tile * BLOCK_N + i < p.n_total) ? p.bias[(n_tile * BLOCK_N + i) % p.bias_mod] : 0.f;
@@ -170,8 +171,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             for (int kc = 0; kc < p.nchunks; ++kc) {
                 (void)trp;
                 mbar_wait(empty_bar + stage, phase ^ 1);
-                mbar_expect_tx_elect(full_bar + stage, (uint32_t)p.a_box_bytes);
-                tma_load_4d_elect(&maps.a, full_bar + stage, dst, kc * BLOCK_K, ch, cw, n);
+                mbar_expect_tx_elect(full_bar + stage, (uint32_t)(p.nplanes * p.a_box_bytes));
+                tma_load_4d_elect(&maps.a[0], full_bar + stage, dst, kc * BLOCK_K, ch, cw, n);
+                if (p.nplanes > 1) {
+#pragma unroll
+                    for (int pl = 1; pl < 4; ++pl)
+                        tma_load_4d_elect(&maps.a[pl], full_bar + stage, dst + pl * p.plane_bytes, kc * BLOCK_K, ch, cw, n);
+                }
 
                 dst += p.a_stage_bytes;
                 if (++stage == STAGES) { stage = 0; phase ^= 1; dst = sA; }
@@ -432,6 +438,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     p.ntaps = d->R * d->S; p.nchunks = kg / BK;
     p.a_box_bytes = p.PH * p.PW * BK * 2;
     p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+    p.nplanes = 1; p.plane_bytes = p.a_stage_bytes;
     p.w_bytes = p.ntaps * kg * BN * 2;
     p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
     if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
@@ -454,7 +461,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
         const uint64_t dims[4] = {(uint64_t)kg, (uint64_t)d->H, (uint64_t)d->W, (uint64_t)d->N};
         const uint64_t strides[3] = {(uint64_t)d->W * a_ld * 2, (uint64_t)a_ld * 2, (uint64_t)d->H * d->W * a_ld * 2};
         const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.PH, (uint32_t)p.PW, 1};
-        int rc = encode_map(&maps.a, (const char*)a + (size_t)a_coff * 2, 4, dims, strides, box, BK * 2);
+        int rc = encode_map(&maps.a[0], (const char*)a + (size_t)a_coff * 2, 4, dims, strides, box, BK * 2);
         if (rc) return rc;
     }
     {
@@ -506,6 +513,7 @@ int conv_halo_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, co
     p.ntaps = 4; p.nchunks = kg / BK;
     p.a_box_bytes = p.PH * p.PW * BK * 2;
     p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+    p.nplanes = 1; p.plane_bytes = p.a_stage_bytes;
     p.w_bytes = p.ntaps * kg * BN * 2;
     p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
     if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
@@ -528,7 +536,7 @@ int conv_halo_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, co
         const uint64_t dims[4] = {(uint64_t)kg, (uint64_t)d->P, (uint64_t)d->Q, (uint64_t)d->N};
         const uint64_t strides[3] = {(uint64_t)d->Q * d->y_ld * 2, (uint64_t)d->y_ld * 2, (uint64_t)d->P * d->Q * d->y_ld * 2};
         const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.PH, (uint32_t)p.PW, 1};
-        int rc = encode_map(&maps.a, (const char*)dy + (size_t)d->y_coff * 2, 4, dims, strides, box, BK * 2);
+        int rc = encode_map(&maps.a[0], (const char*)dy + (size_t)d->y_coff * 2, 4, dims, strides, box, BK * 2);
         if (rc) return rc;
     }
     {
@@ -549,6 +557,86 @@ int conv_halo_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, co
     URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
 #undef URIR_HL
     return fail(URIR_ERR_UNSUP, "up-2 halo conv: no kernel for BLOCK_N=%d BLOCK_K=%d", BN, BK);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stride-2 3x3 forward (encoding_block's strided Conv2D, dl_models/u_net.py:269-276, and the input gradient of a
+// Conv2DTranspose) through the same kernel. With SAME padding on an even input the conv reads x[2p + r, 2q + s]:
+// tap (r, s) lives in parity plane (r & 1, s & 1) of x at offset (r >> 1, s >> 1). Each stage holds the four
+// parity planes of the tile, every plane a (8+1) x (16+1) halo box fetched through its own strided tensor map
+// (H/2 x W/2 view with doubled strides; the row / column past the end is TMA zero fill = the trailing SAME pad).
+// The nine taps are descriptor offsets into those planes: x is read once per tile instead of once per tap, by a
+// persistent CTA with resident weights.
+bool halo_s2_fprop_supported(const urir_conv_desc* d, bool forced) {
+    if (d->stride != 2 || d->R != 3 || d->S != 3 || d->pad_top != 0 || d->pad_left != 0) return false;
+    if (d->H != 2 * d->P || d->W != 2 * d->Q) return false;
+    if (d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16 || d->act != URIR_ACT_NONE || d->accumulate) return false;
+    if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
+    if (d->C % 32 || d->K % 32) return false;
+    const int BK = 32;
+    const long long stage = 4LL * ((((HL_TH + 1) * (HL_TW + 1) * BK * 2) + 1023) / 1024 * 1024);
+    int BN = 0;
+    for (int bn = halo_block_n(d->K); bn >= 32; bn >>= 1)
+        if (9LL * d->C * bn * 2 + 3 * stage + 2048 <= HL_SMEM_BUDGET) { BN = bn; break; }
+    if (BN == 0 || (BN < 64 && BN < d->K)) return false;
+    const long long tiles = (long long)d->N * cdiv(d->P, HL_TH) * cdiv(d->Q, HL_TW);
+    return forced || tiles >= 148 * 4;
+}
+
+int conv_halo_s2_fprop(const urir_conv_desc* d, const void* x, const void* w_kc, const float* bias, void* y, float* stats,
+                       cudaStream_t st) {
+    URIR_CHECK_ARG(w_kc != nullptr, "stride-2 halo conv needs the [tap][K][C] weight layout");
+    const int kg = d->C, ng = d->K;
+    const int BK = 32;                                   // 4 planes per stage: keep the stages small
+    HaloMaps maps; HaloParams p; memset(&p, 0, sizeof(p));
+    p.N = d->N; p.H = d->P; p.W = d->Q;
+    p.tiles_h = cdiv(p.H, HL_TH); p.tiles_w = cdiv(p.W, HL_TW); p.total_tiles = p.tiles_h * p.tiles_w * d->N;
+    p.PH = HL_TH + 1; p.PW = HL_TW + 1;
+    p.ntaps = 9; p.nchunks = kg / BK;
+    p.a_box_bytes = p.PH * p.PW * BK * 2;
+    p.plane_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+    p.nplanes = 4; p.a_stage_bytes = 4 * p.plane_bytes;
+    int BN = 0;
+    for (int bn = halo_block_n(ng); bn >= 32; bn >>= 1)
+        if (9LL * kg * bn * 2 + 3LL * p.a_stage_bytes + 2048 <= HL_SMEM_BUDGET) { BN = bn; break; }
+    if (BN == 0) return fail(URIR_ERR_UNSUP, "stride-2 halo conv: weights do not fit in shared memory");
+    p.w_bytes = p.ntaps * kg * BN * 2;
+    p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
+    if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
+    p.o_sn = (long long)d->P * d->Q * d->y_ld; p.o_sh = (long long)d->Q * d->y_ld; p.o_sw = d->y_ld; p.o_off = d->y_coff;
+    p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)y; p.n_total = ng;
+    p.bias_mod = ng; p.accumulate = 0;
+    for (int g = 0; g < 16; ++g) p.grp_off[g] = 32 * g;
+    p.oh0 = 0; p.ow0 = 0;
+    const int plane_rows = p.plane_bytes / (BK * 2);
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+            const int t = r * 3 + s, plane = (r & 1) * 2 + (s & 1);
+            p.tap_row[t] = (short)(plane * plane_rows + (s >> 1) * p.PH + (r >> 1));
+            p.wtap[t] = (short)t;
+        }
+    for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+            const uint64_t dims[4] = {(uint64_t)kg, (uint64_t)d->P, (uint64_t)d->Q, (uint64_t)d->N};
+            const uint64_t strides[3] = {2ull * d->W * d->x_ld * 2, 2ull * d->x_ld * 2, (uint64_t)d->H * d->W * d->x_ld * 2};
+            const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.PH, (uint32_t)p.PW, 1};
+            const char* base = (const char*)x + ((size_t)d->x_coff + ((size_t)ph * d->W + pw) * d->x_ld) * 2;
+            int rc = encode_map(&maps.a[ph * 2 + pw], base, 4, dims, strides, box, BK * 2);
+            if (rc) return rc;
+        }
+    {
+        const uint64_t dims[3] = {(uint64_t)kg, (uint64_t)ng, 9};
+        const uint64_t strides[2] = {(uint64_t)kg * 2, (uint64_t)kg * ng * 2};
+        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+        int rc = encode_map(&maps.b, w_kc, 3, dims, strides, box, BK * 2);
+        if (rc) return rc;
+    }
+    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
+    const int n_tiles = ng / BN;
+    if (BN == 32) return launch_halo<32, 32>(maps, p, n_tiles, smem, st);
+    if (BN == 64) return launch_halo<64, 32>(maps, p, n_tiles, smem, st);
+    if (BN == 128) return launch_halo<128, 32>(maps, p, n_tiles, smem, st);
+    return fail(URIR_ERR_UNSUP, "stride-2 halo conv: no kernel for BLOCK_N=%d", BN);
 }
 
 // fp32 HWIO [3][3][C][K] -> bf16 w_up2 [a*2+b][(ph,pw,c)][K], zero where 2a+ph > 2 or 2b+pw > 2
