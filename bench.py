@@ -63,37 +63,70 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock + throttle reasons sampled every ~10 ms through NVML (nvidia_ml_py) while the timed regions run;
+    falls back to a line-buffered `nvidia-smi -lms 50` when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._thread, self.proc, self.source = threading.Event(), None, None, None
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.reasons.update(k for k, b in bits.items() if r & b)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            if r and r[0].replace(".", "").isdigit():
+                self.sm.append(float(r[0]))
+                if len(r) > 1 and r[1].replace(".", "").isdigit():
+                    self.max_mhz = float(r[1])
+                self.reasons.update(self.NAMES[i] for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active"))
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["stdbuf", "-oL", "nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.source = "nvidia-smi"
+            self._thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self._thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop.set()
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock samples"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
@@ -151,9 +184,11 @@ def workload_name(args):
 def per_kernel_profile(step_fn):
     """One eager step with a CUDA-event pair around every liburir launch -> per-family totals."""
     from unet_rir_b200 import _lib as L
+    prev = L.load().urir_set_pdl(0)            # one kernel at a time: no prologue overlap while timing single launches
     L.profile_begin()
     step_fn()
     rec = L.profile_end()
+    L.load().urir_set_pdl(prev)
     fam = {}
     for name, info, ms in rec:
         if name.startswith("conv2d"):
@@ -258,12 +293,16 @@ def run_gpu(args, rank, world, local):
     pk = peaks()
     if world == 1:
         l0 = L.launch_count(0)
+        eng.overlap_wgrad = False              # per-launch timing: keep every kernel on the one timed stream
         rec, fam = per_kernel_profile(body)
+        eng.overlap_wgrad = True
         launches_per_step = L.launch_count(0) - l0
     else:
         l0 = L.launch_count(0)
         save = dt._graphs; dt._graphs = None; w_save = dt.world; dt.world = 1
+        eng.overlap_wgrad = False
         rec, fam = per_kernel_profile(lambda: dt._run(B))
+        eng.overlap_wgrad = True
         dt._graphs, dt.world = save, w_save
         launches_per_step = L.launch_count(0) - l0
     tot_ms = sum(f["ms"] for f in fam.values())

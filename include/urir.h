@@ -84,6 +84,10 @@ int         urir_version(void);
 const char* urir_last_error(void);
 /* number of kernels launched by this library since load; kind 0 = all, 1 = tcgen05 only */
 long long   urir_launch_count(int kind);
+/* programmatic dependent launch of the library's kernels (default on; URIR_NO_PDL=1 starts with it off):
+ * a kernel's prologue may overlap its predecessor's tail. Returns the previous setting. Turn it off to time
+ * kernels one by one with events. */
+int         urir_set_pdl(int enabled);
 
 /* ---- convolutions: replace tf.keras Conv2D / Conv2DTranspose and their autodiff ------- */
 /* Conv2D forward (dl_models/u_net.py:269-276, 366, 248, 262). Also Conv2DTranspose's

@@ -18,9 +18,10 @@ int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
+static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("URIR_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+    int v = g_pdl.load();
+    if (v < 0) { const char* e = getenv("URIR_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; g_pdl.store(v); }
     return v == 1;
 }
 void count_launch(int kind) { g_launches_all++; if (kind == 1) g_launches_tc++; }
@@ -107,6 +108,7 @@ extern "C" {
 
 int urir_version(void) { return URIR_VERSION; }
 const char* urir_last_error(void) { return g_err; }
+int urir_set_pdl(int enabled) { const int prev = pdl_enabled() ? 1 : 0; g_pdl.store(enabled ? 1 : 0); return prev; }
 long long urir_launch_count(int kind) { return kind == 1 ? g_launches_tc.load() : g_launches_all.load(); }
 
 int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, const void* w_kc, const float* bias,

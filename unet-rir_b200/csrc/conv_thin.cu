@@ -109,9 +109,11 @@ thin_gemm_kernel(const __grid_constant__ ThinParams p) {
     constexpr uint32_t IDESC = make_idesc_bf16(128, 32, 0, 0);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // one 128-byte atom row holds 32 taps: the stem (9 / 36 taps) and a 3x3 head need one atom, the 6x6 head two
+    const int atoms = p.nchunks > 8 ? 2 : 1;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + 2 * TH_ATOM;
-    float2* patch = reinterpret_cast<float2*>(sB + 2 * TG_B_ATOM);
+    uint8_t* sB = smem + atoms * TH_ATOM;
+    float2* patch = reinterpret_cast<float2*>(sB + atoms * TG_B_ATOM);
     uint64_t* mma_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + TH_PATCH_MAX * 8);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
@@ -208,8 +210,10 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
     constexpr uint32_t IDESC = make_idesc_bf16(128, 32, 1, 1);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int atoms = p.nchunks > 8 ? 2 : 1;             // A stage = `atoms` 128 x 128 B tiles (see thin_gemm)
+    const int a_stage = atoms * TH_ATOM;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + 2 * TW_A_STAGE;
+    uint8_t* sB = smem + 2 * a_stage;
     float2* patch = reinterpret_cast<float2*>(sB + 2 * TW_B_STAGE);
     uint64_t* bar_b = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + TH_PATCH_MAX * 8);
     uint64_t* bar_mma = bar_b + 2;
@@ -228,10 +232,10 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
     // chunks the per-tile build never writes (im2col columns >= 16*KS) feed accumulator rows that are never
     // read back; zero them once so that no NaN patterns circulate
     for (int s = 0; s < 2; ++s)
-        for (int idx = threadIdx.x; idx < 128 * 16; idx += 128) {
+        for (int idx = threadIdx.x; idx < 128 * 8 * atoms; idx += 128) {
             const int c = idx >> 7, m = idx & 127;
             if (c >= p.nchunks)
-                *reinterpret_cast<uint4*>(sA + s * TW_A_STAGE + (c >> 3) * TH_ATOM + m * 128 + (((c & 7) ^ (m & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(sA + s * a_stage + (c >> 3) * TH_ATOM + m * 128 + (((c & 7) ^ (m & 7)) << 4)) = make_uint4(0, 0, 0, 0);
         }
     fence_proxy_async();
     fence_before_sync();
@@ -257,7 +261,7 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
         }
         thin_store_patch(p, patch, pr);
         __syncthreads();
-        thin_build_row(p, patch, sA + s * TW_A_STAGE);
+        thin_build_row(p, patch, sA + s * a_stage);
         const int next = tile + gridDim.x;
         if (next < p.total_tiles) thin_load_patch(p, next, pr);
         fence_proxy_async();
@@ -267,7 +271,7 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
             fence_after_sync();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + ((s * TW_A_STAGE + i * 2048) >> 4));
+                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + ((s * a_stage + i * 2048) >> 4));
                 const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + ((s * TW_B_STAGE + i * 1024) >> 4));
                 umma_bf16_elect(tmem_base, ad, bd, IDESC, (it | i) != 0);
             }
@@ -346,9 +350,14 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
     else { p.thin_ld = d->y_ld; p.thin_coff = d->y_coff; p.out_ld = d->x_ld; p.out_coff = d->x_coff; }
     static bool attr_set = false;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(thin_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM)); attr_set = true; }
-    int gx = p.total_tiles < 148 * 4 ? p.total_tiles : 148 * 4;
+    // the per-tile phases of a CTA (patch load, im2col build, MMA, store) run back to back, so throughput comes
+    // from co-resident CTAs: as many as the shared memory of the layer's atom count allows
+    const int atoms = p.nchunks > 8 ? 2 : 1;
+    const int smem = atoms * (TH_ATOM + TG_B_ATOM) + TH_PATCH_MAX * 8 + 64 + 1024;
+    const int per_sm = atoms == 1 ? 8 : 4;             // measured: 80 -> 56 us for the stem; no gain beyond 4 with two atoms
+    int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
     dim3 grid(gx, p.CW_total / 32);
-    thin_gemm_kernel<<<grid, 128, TG_SMEM, st>>>(p);
+    thin_gemm_kernel<<<grid, 128, smem, st>>>(p);
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }
@@ -372,9 +381,14 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     static bool attr_set = false;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM)); attr_set = true; }
     if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.ntaps * d->C * d->K, st));
-    int gx = p.total_tiles < 148 * 2 ? p.total_tiles : 148 * 2;
+    const int atoms = p.nchunks > 8 ? 2 : 1;
+    // with one atom the M = 128 instruction also reads the 16 KB after its A stage (the other stage / the B
+    // stages: finite bf16 data inside the allocation); those accumulator rows 64..127 are never read back
+    const int smem = 2 * atoms * TH_ATOM + 2 * TW_B_STAGE + TH_PATCH_MAX * 8 + 128 + 1024;
+    const int per_sm = 2;                              // more CTAs only add dw reductions (measured slower)
+    int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
     dim3 grid(gx, p.CW_total / 32);
-    thin_wgrad_kernel<<<grid, 128, TW_SMEM, st>>>(map, p);
+    thin_wgrad_kernel<<<grid, 128, smem, st>>>(map, p);
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }
