@@ -133,3 +133,25 @@ def test_adam_step_moves_parameters_like_oracle():
         agree = float((torch.sign(du[big]) == torch.sign(du_ref[big])).float().mean())
         assert agree > 0.85, (name, agree)          # fp32 vs bf16 evaluation: sign agreement is statistical
         assert abs(float(du.abs().mean()) - float(du_ref.abs().mean())) < 0.05 * float(du_ref.abs().mean()), name
+
+
+def test_many_graph_replays_stay_healthy():
+    """Soak test: 600 replays of the captured train step. Guards the pipelines' mbarrier protocols against
+    timing-dependent hangs (a two-issuer ring whose stage ownership alternated between fills once aliased mbarrier
+    parities about once per thousand steps: a trapped 'unspecified launch failure') and checks that training moves."""
+    from unet_rir_b200.amp_phase_trainer import EarlyStopping, ModelCheckpoint, Trainer
+    from unet_rir_b200.dl_models.u_net import UNet
+    g = torch.Generator().manual_seed(3)
+    B = 16
+    x = torch.rand(B, 144, 160, 2, generator=g); y = torch.rand(B, 144, 160, 2, generator=g)
+    emb = torch.randint(0, 2000, (B, 2, 16), generator=g, dtype=torch.int32)
+    unet = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+    tr = Trainer(0.9, 1, "adam", [ModelCheckpoint("/tmp/urir_soak", False, 0), EarlyStopping(5)], [False, 0], 1e-4, "soak")
+    first = last = None
+    for i in range(600):
+        l = tr.step(x, y, emb, unet)[0]
+        if i == 0:
+            first = float(l)
+    torch.cuda.synchronize()
+    last = float(l)
+    assert last == last and last < first, (first, last)

@@ -39,6 +39,7 @@ struct HaloParams {
     int oh0, ow0;               // box origin relative to the tile origin
     int ntaps, nchunks;         // taps, GEMM-K chunks of BLOCK_K channels
     int stages, a_stage_bytes, a_box_bytes, w_bytes;
+    int one_issuer;             // 1: warp 5 issues every tile (ring length not a multiple of 2 * nchunks, see kernel)
     int nplanes, plane_bytes;   // boxes per stage (1, or the 4 parity planes of a stride-2 input) and their spacing
     long long o_sn, o_sh, o_sw; // output element strides
     long long o_off;
@@ -190,6 +191,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         // issue queue is shallow, so a single issuer leaves the pipe idle ~400 cycles per tile (measured with
         // URIR_HALO_TRACE); with two, one warp's waits overlap the other's MMAs.
         const int mw = warp - 5;
+        const int issue_end = (p.one_issuer && mw == 1) ? 0 : p.total_tiles;      // the idle second issuer
         const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t a_hi = (((uint32_t)p.PH * ROW_BYTES) >> 4) | (1u << 14) | (SWZ << 29);   // SBO = PH rows
         const uint32_t b_hi = ((8 * ROW_BYTES) >> 4) | (1u << 14) | (SWZ << 29);
@@ -200,8 +202,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         int stage = 0; uint32_t phase = 0;
         uint32_t a_lo = a_lo0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != mw) {           // the other issuer's tile: step over its stages
+        for (int tile = blockIdx.x; tile < issue_end; tile += gridDim.x, ++it) {
+            // An mbarrier parity wait cannot tell "fill k+2 complete" from "fill k complete". With a ring length that
+            // is a multiple of 2 * nchunks every stage always belongs to the same issuer, which therefore observes
+            // every fill of it, and the producer's empty-barrier handshake keeps it from being lapped. With any other
+            // ring length stage ownership alternates between fills, an issuer would see only every other phase of a
+            // barrier and could sail through a wait one ring pass early (observed as a rare hang / stale tile):
+            // those configurations run with ONE issuer (p.one_issuer, warp 6 idles).
+            if (!p.one_issuer && (it & 1) != mw) {           // the other issuer's tile: step over its stages
                 for (int kc = 0; kc < p.nchunks; ++kc) { a_lo += stage16; if (++stage == STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; } }
                 continue;
             }
@@ -393,6 +401,16 @@ static int halo_block_n_fit(int ng, int kg, int ntaps, int ph, int pw) {
     return 0;
 }
 
+// Ring length for the two-issuer scheme: prefer a multiple of 2 * nchunks (static stage ownership, see the kernel's
+// issuer loop) when that costs at most a quarter of the ring; otherwise keep the stages and run with one issuer.
+static void halo_fix_stages(HaloParams& p) {
+    if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
+    const int q = 2 * p.nchunks;
+    const int rounded = p.stages / q * q;
+    if (rounded >= 2 && rounded * 4 >= p.stages * 3) { p.stages = rounded; p.one_issuer = 0; }
+    else p.one_issuer = (p.stages % q) != 0 ? 1 : 0;
+}
+
 // op 0: fprop (GEMM-K = C, GEMM-N = K), op 1: dgrad (GEMM-K = K, GEMM-N = C)
 bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
     if (d->stride != 1 || d->P != d->H || d->Q != d->W || d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16) return false;
@@ -441,7 +459,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     p.nplanes = 1; p.plane_bytes = p.a_stage_bytes;
     p.w_bytes = p.ntaps * kg * BN * 2;
     p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
-    if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
+    halo_fix_stages(p);
     if (p.stages < 2) return fail(URIR_ERR_UNSUP, "halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
     p.o_sn = (long long)d->H * d->W * o_ld; p.o_sh = (long long)d->W * o_ld; p.o_sw = o_ld; p.o_off = o_coff;
     p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)out; p.n_total = ng;
@@ -516,7 +534,7 @@ int conv_halo_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, co
     p.nplanes = 1; p.plane_bytes = p.a_stage_bytes;
     p.w_bytes = p.ntaps * kg * BN * 2;
     p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
-    if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
+    halo_fix_stages(p);
     if (p.stages < 2) return fail(URIR_ERR_UNSUP, "up-2 halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
     p.o_sn = (long long)d->H * d->W * d->x_ld; p.o_sh = 2LL * d->W * d->x_ld; p.o_sw = 2LL * d->x_ld; p.o_off = d->x_coff;
     p.bias = bias; p.stats = nullptr; p.out = (__nv_bfloat16*)dx; p.n_total = ng;
@@ -602,7 +620,7 @@ int conv_halo_s2_fprop(const urir_conv_desc* d, const void* x, const void* w_kc,
     if (BN == 0) return fail(URIR_ERR_UNSUP, "stride-2 halo conv: weights do not fit in shared memory");
     p.w_bytes = p.ntaps * kg * BN * 2;
     p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
-    if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
+    halo_fix_stages(p);
     p.o_sn = (long long)d->P * d->Q * d->y_ld; p.o_sh = (long long)d->Q * d->y_ld; p.o_sw = d->y_ld; p.o_off = d->y_coff;
     p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)y; p.n_total = ng;
     p.bias_mod = ng; p.accumulate = 0;

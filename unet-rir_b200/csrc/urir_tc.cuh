@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace urir {
 namespace tc {
@@ -44,7 +45,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (1ll << 32)) { asm volatile("trap;"); }
+        if (clock64() - t0 > (1ll << 32)) {
+#ifdef URIR_DEBUG_TRAP
+            if ((threadIdx.x & 31) == 0)
+                printf("urir: mbarrier timeout: grid (%d,%d,%d) block (%d,%d,%d) of %d threads, warp %d parity %u smem bar 0x%x\n",
+                       gridDim.x, gridDim.y, gridDim.z, blockIdx.x, blockIdx.y, blockIdx.z, blockDim.x, threadIdx.x >> 5, parity, smem_u32(bar));
+#endif
+            asm volatile("trap;");
+        }
     }
 }
 

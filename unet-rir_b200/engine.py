@@ -19,6 +19,7 @@ Data layout in HBM (all NHWC):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import torch
@@ -83,7 +84,7 @@ class UNetEngine:
         self.losses_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.side = torch.cuda.Stream(device=self.device)
-        self.overlap_wgrad = True
+        self.overlap_wgrad = os.environ.get("URIR_NO_OVERLAP", "0") != "1"
         self._side_dirty = False
 
     # ------------------------------------------------------------------ parameters
