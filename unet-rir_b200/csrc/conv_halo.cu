@@ -30,6 +30,7 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
 
 constexpr int HL_TH = 8, HL_TW = 16;          // output tile: 8 rows x 16 columns = 128 GEMM rows
 constexpr int HL_MAX_STAGES = 8;
+constexpr int HL_MAX_FSETS = 8;            // sets of `full` barriers (see HaloParams::fsets)
 constexpr int HL_SMEM_BUDGET = 220 * 1024;
 
 struct HaloParams {
@@ -39,7 +40,8 @@ struct HaloParams {
     int oh0, ow0;               // box origin relative to the tile origin
     int ntaps, nchunks;         // taps, GEMM-K chunks of BLOCK_K channels
     int stages, a_stage_bytes, a_box_bytes, w_bytes;
-    int one_issuer;             // 1: warp 5 issues every tile (ring length not a multiple of 2 * nchunks, see kernel)
+    int one_issuer;             // 1: warp 5 issues every tile (fallback when fsets would exceed HL_MAX_FSETS)
+    int fsets;                  // `full` barrier sets: fill number `pass` of a stage signals set pass % fsets (see kernel)
     int nplanes, plane_bytes;   // boxes per stage (1, or the 4 parity planes of a stride-2 input) and their spacing
     long long o_sn, o_sh, o_sw; // output element strides
     long long o_off;
@@ -120,7 +122,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     uint8_t* sW = smem;
     uint8_t* sA = smem + p.w_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + p.stages * p.a_stage_bytes);
-    uint64_t* empty_bar = full_bar + HL_MAX_STAGES;
+    uint64_t* empty_bar = full_bar + HL_MAX_FSETS * HL_MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + HL_MAX_STAGES;     // [4]
     uint64_t* tempty_bar = tfull_bar + 4;                // [4]
     uint64_t* w_bar = tempty_bar + 4;
@@ -135,7 +137,10 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     if (p.trace && threadIdx.x == 0) { trace_c0 = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(trace_g0)); }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(empty_bar + s, 1);
+            for (int j = 0; j < p.fsets; ++j) mbar_init(full_bar + j * HL_MAX_STAGES + s, 1);
+        }
         for (int a = 0; a < 4; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
@@ -161,6 +166,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 tma_load_3d_elect(&maps.b, w_bar, sW + (size_t)(t * p.nchunks + kc) * B_BYTES, kc * BLOCK_K, n_tile * BLOCK_N, wt);
         }
         int stage = 0; uint32_t phase = 0;
+        int fj = 0;                          // pass % fsets -> which set of full barriers this pass signals
         uint8_t* dst = sA;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int t = tile;
@@ -172,16 +178,17 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             for (int kc = 0; kc < p.nchunks; ++kc) {
                 (void)trp;
                 mbar_wait(empty_bar + stage, phase ^ 1);
-                mbar_expect_tx_elect(full_bar + stage, (uint32_t)(p.nplanes * p.a_box_bytes));
-                tma_load_4d_elect(&maps.a[0], full_bar + stage, dst, kc * BLOCK_K, ch, cw, n);
+                uint64_t* fb = full_bar + fj * HL_MAX_STAGES + stage;
+                mbar_expect_tx_elect(fb, (uint32_t)(p.nplanes * p.a_box_bytes));
+                tma_load_4d_elect(&maps.a[0], fb, dst, kc * BLOCK_K, ch, cw, n);
                 if (p.nplanes > 1) {
 #pragma unroll
                     for (int pl = 1; pl < 4; ++pl)
-                        tma_load_4d_elect(&maps.a[pl], full_bar + stage, dst + pl * p.plane_bytes, kc * BLOCK_K, ch, cw, n);
+                        tma_load_4d_elect(&maps.a[pl], fb, dst + pl * p.plane_bytes, kc * BLOCK_K, ch, cw, n);
                 }
 
                 dst += p.a_stage_bytes;
-                if (++stage == STAGES) { stage = 0; phase ^= 1; dst = sA; }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; dst = sA; if (++fj == p.fsets) fj = 0; }
             }
         }
     } else if (warp == 5 || warp == 6) {
@@ -199,18 +206,25 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         const uint32_t a_lo0 = smem_u32(sA) >> 4;
         const uint32_t stage16 = (uint32_t)p.a_stage_bytes >> 4;
         mbar_wait(w_bar, 0);
-        int stage = 0; uint32_t phase = 0;
+        int stage = 0;
+        int fj = 0; uint32_t fpar = 0;       // full-barrier set of the current pass, parity within that set
         uint32_t a_lo = a_lo0;
         int it = 0;
         for (int tile = blockIdx.x; tile < issue_end; tile += gridDim.x, ++it) {
-            // An mbarrier parity wait cannot tell "fill k+2 complete" from "fill k complete". With a ring length that
-            // is a multiple of 2 * nchunks every stage always belongs to the same issuer, which therefore observes
-            // every fill of it, and the producer's empty-barrier handshake keeps it from being lapped. With any other
-            // ring length stage ownership alternates between fills, an issuer would see only every other phase of a
-            // barrier and could sail through a wait one ring pass early (observed as a rare hang / stale tile):
-            // those configurations run with ONE issuer (p.one_issuer, warp 6 idles).
+            // An mbarrier parity wait cannot tell "fill k+2 complete" from "fill k complete", so a waiter must observe
+            // EVERY phase of a barrier it waits on. Tiles alternate between the two issuers, and unless the ring length
+            // is a multiple of 2 * nchunks the issuer that consumes a given stage alternates between ring passes: with
+            // one `full` barrier per stage each issuer would see only every other phase and (TMA completions being
+            // unordered) could sail through a wait one pass early -- observed as a hang about once per thousand steps.
+            // Hence `fsets` sets of full barriers: fill number `pass` of stage s signals set pass % fsets, with fsets
+            // the smallest count for which fsets * STAGES is a multiple of 2 * nchunks. Then (stage, set) always
+            // belongs to the same issuer, which sees each of its phases in order, and the empty-barrier handshake
+            // keeps the producer from lapping it.
             if (!p.one_issuer && (it & 1) != mw) {           // the other issuer's tile: step over its stages
-                for (int kc = 0; kc < p.nchunks; ++kc) { a_lo += stage16; if (++stage == STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; } }
+                for (int kc = 0; kc < p.nchunks; ++kc) {
+                    a_lo += stage16;
+                    if (++stage == STAGES) { stage = 0; a_lo = a_lo0; if (++fj == p.fsets) { fj = 0; fpar ^= 1; } }
+                }
                 continue;
             }
             const int acc = it & 3;                  // stages {mw, mw + 2}
@@ -220,7 +234,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             if (trm) p.trace[it * 8 + 1] = clock64();
             const uint32_t d_tm = tm0 + acc * BLOCK_N;
             for (int kc = 0; kc < p.nchunks; ++kc) {
-                mbar_wait(full_bar + stage, phase);
+                mbar_wait(full_bar + fj * HL_MAX_STAGES + stage, fpar);
                 if (trm && kc == p.nchunks - 1) p.trace[it * 8 + 2] = clock64();
                 fence_after_sync();
                 uint32_t b_lo = w_lo + ((kc * B_BYTES) >> 4);
@@ -236,7 +250,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 }
                 umma_commit_elect(empty_bar + stage);
                 a_lo += stage16;
-                if (++stage == STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; }
+                if (++stage == STAGES) { stage = 0; a_lo = a_lo0; if (++fj == p.fsets) { fj = 0; fpar ^= 1; } }
             }
             umma_commit_elect(tfull_bar + acc);
             __syncwarp();
@@ -401,14 +415,15 @@ static int halo_block_n_fit(int ng, int kg, int ntaps, int ph, int pw) {
     return 0;
 }
 
-// Ring length for the two-issuer scheme: prefer a multiple of 2 * nchunks (static stage ownership, see the kernel's
-// issuer loop) when that costs at most a quarter of the ring; otherwise keep the stages and run with one issuer.
+// Number of `full` barrier sets that makes (stage, set) ownership static for the two issuers (see the kernel's
+// issuer loop); a single issuer if that would need more than HL_MAX_FSETS sets.
 static void halo_fix_stages(HaloParams& p) {
     if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
     const int q = 2 * p.nchunks;
-    const int rounded = p.stages / q * q;
-    if (rounded >= 2 && rounded * 4 >= p.stages * 3) { p.stages = rounded; p.one_issuer = 0; }
-    else p.one_issuer = (p.stages % q) != 0 ? 1 : 0;
+    p.fsets = 1;
+    while ((p.fsets * p.stages) % q != 0) ++p.fsets;
+    p.one_issuer = 0;
+    if (p.fsets > HL_MAX_FSETS) { p.fsets = 1; p.one_issuer = 1; }
 }
 
 // op 0: fprop (GEMM-K = C, GEMM-N = K), op 1: dgrad (GEMM-K = K, GEMM-N = C)
@@ -489,7 +504,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
         int rc = encode_map(&maps.b, w, 3, dims, strides, box, BK * 2);
         if (rc) return rc;
     }
-    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
+    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + ((HL_MAX_FSETS + 1) * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
     const int n_tiles = ng / BN;
 #define URIR_HL(BN_, BK_) if (BN == BN_ && BK == BK_) return launch_halo<BN_, BK_>(maps, p, n_tiles, smem, st);
     URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
@@ -564,7 +579,7 @@ int conv_halo_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, co
         int rc = encode_map(&maps.b, w_up2, 3, dims, strides, box, BK * 2);
         if (rc) return rc;
     }
-    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
+    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + ((HL_MAX_FSETS + 1) * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
     const int n_tiles = ng / BN;
     if (p.accumulate) {      // 4C is a multiple of 128: only the BLOCK_N = 128 kernels exist with the accumulate epilogue
         if (BN == 128 && BK == 32) return launch_halo<128, 32, true>(maps, p, n_tiles, smem, st);
@@ -649,7 +664,7 @@ int conv_halo_s2_fprop(const urir_conv_desc* d, const void* x, const void* w_kc,
         int rc = encode_map(&maps.b, w_kc, 3, dims, strides, box, BK * 2);
         if (rc) return rc;
     }
-    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + (2 * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
+    const int smem = p.w_bytes + p.stages * p.a_stage_bytes + ((HL_MAX_FSETS + 1) * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
     const int n_tiles = ng / BN;
     if (BN == 32) return launch_halo<32, 32>(maps, p, n_tiles, smem, st);
     if (BN == 64) return launch_halo<64, 32>(maps, p, n_tiles, smem, st);
