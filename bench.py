@@ -305,6 +305,13 @@ def run_gpu(args, rank, world, local):
         eng.overlap_wgrad = True
         dt._graphs, dt.world = save, w_save
         launches_per_step = L.launch_count(0) - l0
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")     # written by tools/ncu_step_table.py from an ncu capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("families", {})
+        except Exception:
+            traffic = {}
     tot_ms = sum(f["ms"] for f in fam.values())
     dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
     dname, d = dom
@@ -313,7 +320,11 @@ def run_gpu(args, rank, world, local):
     if d["flops"] > 0:
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                "frac": ach / pk["tf_sustained"],
+                "traffic": traffic.get(dname, {}).get("dram_bytes_per_call") if B == 64 else None,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per call, profiles/r01_traffic.json",
+                "algorithmic_flops_per_launch": d["flops"] / d["launches"],
+                "peak_source": pk["source"] + " (sustained)",
                 "share_of_step": d["ms"] / tot_ms, "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                 "all_tcgen05_tflops": (tens_fl / (tens_ms * 1e-3) / 1e12) if tens_ms else None,
                 "all_tcgen05_share": tens_ms / tot_ms}

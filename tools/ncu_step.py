@@ -17,8 +17,24 @@ tr.use_cuda_graph = False
 x, y, e = synthetic_batch(B, 1)
 tr.step(x, y, e, unet)
 torch.cuda.synchronize()
+# record, per C-ABI call of the profiled step, how many liburir kernels it launched (urir_launch_count deltas):
+# tools/ncu_step_table.py uses it to attribute ncu's per-kernel DRAM bytes to bench.py's call families
+import json
+from unet_rir_b200 import _lib as L
+calls = []
+_orig_call = L.call
+def _counting_call(name, *args):
+    n0 = L.launch_count(0)
+    _orig_call(name, *args)
+    info = L._conv_info(name, args) if name.startswith("conv2d") else {}
+    calls.append({"name": name, "tc": info.get("tc"), "kernels": L.launch_count(0) - n0})
+L.call = _counting_call
+import unet_rir_b200.engine as _E, unet_rir_b200.amp_phase_trainer as _T
 torch.cuda.profiler.start()
 tr._device_step(eng, B)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+L.call = _orig_call
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(calls, open("gpurun_out/step_calls.json", "w"))
 print("ok", [float(v) for v in eng.losses_dev[:3]])

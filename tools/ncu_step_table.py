@@ -1,6 +1,9 @@
 """Turns the long-format CSV of `ncu --metrics ... --csv` (tools/ncu_step.py run) into a per-launch table and a
 per-kernel-family summary: time, DRAM bytes, achieved GB/s, tensor-pipe utilisation.
-usage: python tools/ncu_step_table.py gpurun_out/step_metrics_r1.csv > profiles/r01_step_kernels.txt"""
+usage: python tools/ncu_step_table.py gpurun_out/step_metrics_r1.csv [gpurun_out/step_calls.json profiles/r01_traffic.json]
+           > profiles/r01_step_kernels.txt
+With the call list written by tools/ncu_step.py it also writes, per bench.py call family (conv2d_fprop.tcgen05, ...),
+the launches, time and DRAM bytes per call: the `traffic` figure of bench.py's roofline object."""
 import collections
 import csv
 import re
@@ -48,3 +51,25 @@ print()
 print(f"{'kernel family':58s} {'n':>4} {'us':>9} {'share':>6} {'dramR MB':>9} {'dramW MB':>9} {'GB/s':>7} {'tensor%':>7}")
 for k, f in sorted(fam.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:58s} {f[0]:4d} {f[1]:9.1f} {100 * f[1] / tot:5.1f}% {f[2]:9.1f} {f[3]:9.1f} {(f[2] + f[3]) / f[1] * 1e3:7.0f} {f[4] / f[1]:7.1f}")
+
+if len(sys.argv) > 3:
+    import json
+    calls = json.load(open(sys.argv[2]))
+    ours = [d for d in launch.values() if "urir::" in d["name"]]
+    need = sum(c["kernels"] for c in calls)
+    out = {"note": "per C-ABI call of one eager train step (B = 64) under ncu: kernels, us, DRAM read+write bytes",
+           "aligned": need == len(ours), "families": {}}
+    if need == len(ours):
+        i = 0
+        for c in calls:
+            ks = ours[i:i + c["kernels"]]; i += c["kernels"]
+            key = c["name"] + ((".tcgen05" if c.get("tc") else ".simt") if c["name"].startswith("conv2d") else "")
+            f = out["families"].setdefault(key, {"calls": 0, "kernels": 0, "us": 0.0, "dram_bytes": 0.0})
+            f["calls"] += 1; f["kernels"] += len(ks)
+            f["us"] += sum(k["gpu__time_duration.sum"] for k in ks)
+            f["dram_bytes"] += sum(k.get("dram__bytes_read.sum", 0) + k.get("dram__bytes_write.sum", 0) for k in ks)
+        for f in out["families"].values():
+            f["dram_bytes_per_call"] = f["dram_bytes"] / max(f["calls"], 1)
+    else:
+        out["error"] = f"call list expects {need} liburir kernels, ncu saw {len(ours)}"
+    json.dump(out, open(sys.argv[3], "w"), indent=1)

@@ -85,6 +85,7 @@ class DistributedTrainer:
         self.buckets = gradient_buckets(self.eng.offsets, self.eng.n_flat)
         self._graphs = None
         self._calls = 0
+        self.overlap = os.environ.get("URIR_DP_OVERLAP", "1") != "0"
         self.eng.set_lr(lr)
 
     # loss weights: w_amp * sum sq err + w_ph * sum (1 - cos)
@@ -133,13 +134,18 @@ class DistributedTrainer:
         works = []
         for i, s in enumerate(segs):
             if i == 3:
+                if self.world > 1 and not self.overlap:
+                    # one all-reduce of the whole flat gradient after backward: nothing runs beside the persistent
+                    # one-CTA-per-SM conv kernels (an NCCL kernel resident on a few SMs forces their static tile
+                    # schedule into a second wave)
+                    works.append(dist.all_reduce(self.eng.G, op=dist.ReduceOp.SUM, async_op=True))
                 for w in works:
                     w.wait()
             if self._graphs is not None:
                 self._graphs[i].replay()
             else:
                 s(B)
-            if i < 3 and self.world > 1:
+            if i < 3 and self.world > 1 and self.overlap:
                 lo, hi = self.buckets[i]
                 works.append(dist.all_reduce(self.eng.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
         self._calls += 1
