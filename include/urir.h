@@ -206,6 +206,9 @@ int urir_step_increment(int32_t* step_dev, void* stream);
 int urir_axpy(float* y, const float* x, float a, long long n, void* stream);
 /* out[0] (+)= scale * sum(x^2) */
 int urir_sumsq(const float* x, long long n, float scale, float* out, int accumulate, void* stream);
+/* the L2 kernel regulariser of ALL regularised tensors in one launch: table_dev = n_entries x {param fp32 ptr,
+ * grad fp32 ptr, element count} (int64, device memory); out[0] = coef * sum ||W||^2 (overwritten), grad += 2*coef*W. */
+int urir_l2_reg_batched(const int64_t* table_dev, int n_entries, float coef, float* out, void* stream);
 /* elementwise helpers for the alternate block modes (u_net.py:337,359) and casts */
 int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int urir_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);

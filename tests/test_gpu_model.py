@@ -155,3 +155,31 @@ def test_many_graph_replays_stay_healthy():
     torch.cuda.synchronize()
     last = float(l)
     assert last == last and last < first, (first, last)
+
+
+def test_data_parallel_step_world1_matches_oracle_dp_loss():
+    """DistributedTrainer (main_training.py's compute_loss: alpha-weighted amp/phase terms / global batch + the L2
+    kernel regulariser of the nine strided layers) on one replica: loss value against the oracle's dp_loss, and the
+    regulariser's gradient 2 * 0.001 * W present in the flat gradient (one batched launch)."""
+    from unet_rir_b200.dl_models.u_net import UNet
+    from unet_rir_b200.main_training import DistributedTrainer
+    om, params, x, y, emb, mask = _setup(B=2, kernels=3, seed=2)
+    unet = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+    eng = unet.model.engine
+    eng.load_state_dict(params)
+    dt = DistributedTrainer(unet, per_replica_batch=2, alpha=0.9, lr=0.0, loss="dp", world=1, use_cuda_graph=False,
+                            dropout=False)
+    loss = float(dt.train_step(x, emb, y))
+    pred = om.forward(params, x, emb, training=True, dropout_mask=None)
+    ref = float(O.dp_loss(y, pred, 0.9, 2, l2_losses=om.l2_losses(params), num_replicas=1))
+    assert abs(loss - ref) < 3e-3 * abs(ref), (loss, ref)
+    # lr = 0: parameters unchanged, so G = data gradient + 2 * 0.001 * W on the regularised kernels
+    name = "enc3.down.w"
+    g_with = eng.grad[name].clone()
+    eng.forward(x.cuda(), emb.cuda(), training=True, dropout=False)
+    wa, wp = dt._weights(2)
+    eng.loss_and_grad(y.cuda(), wa, wp)
+    eng.backward(eng._buffers(2)["g_out"])
+    diff = (g_with - eng.grad[name]).cpu()
+    want = 2 * O.L2_COEF * params[name]
+    assert U.rel_l2(diff, want) < 2e-2, U.rel_l2(diff, want)      # the two backward passes differ by atomic-order noise

@@ -45,6 +45,7 @@ _PROTOS = {
     "urir_conv2d_wgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "urir_conv_path": (_i, [C.POINTER(ConvDesc), _i]),
     "urir_set_pdl": (_i, [_i]),
+    "urir_l2_reg_batched": (_i, [_vp, _i, _f, _vp, _vp]),
     "urir_weight_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "urir_weight_prep_up2": (_i, [_vp, _vp, _i, _i, _vp]),
     "urir_conv2d_dgrad_up2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -69,6 +69,7 @@ int step_increment(int*, cudaStream_t);
 int axpy(float*, const float*, float, long long, cudaStream_t);
 int sumsq(const float*, long long, float, float*, int, cudaStream_t);
 int add_bf16(const void*, const void*, void*, long long, cudaStream_t);
+int l2_reg_batched(const long long*, int, float, float*, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
 int cast_pad_bf16(const float*, void*, long long, int, int, cudaStream_t);
 int embedding_fwd(const int*, const float*, void*, int, int, int, int, cudaStream_t);
@@ -290,6 +291,10 @@ int urir_axpy(float* y, const float* x, float a, long long n, void* stream) {
 int urir_sumsq(const float* x, long long n, float scale, float* out, int accumulate, void* stream) {
     URIR_CHECK_ARG(x && out && n > 0, "sumsq: bad args");
     return sumsq(x, n, scale, out, accumulate, (cudaStream_t)stream);
+}
+int urir_l2_reg_batched(const int64_t* table_dev, int n_entries, float coef, float* out, void* stream) {
+    URIR_CHECK_ARG(table_dev && out && n_entries > 0, "l2_reg_batched: bad args");
+    return l2_reg_batched(reinterpret_cast<const long long*>(table_dev), n_entries, coef, out, (cudaStream_t)stream);
 }
 int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
     URIR_CHECK_ARG(a && b && out && n > 0, "add_bf16: bad args");

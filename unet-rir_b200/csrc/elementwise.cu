@@ -704,6 +704,27 @@ sumsq_kernel(const float* __restrict__ x, long long n, float scale, float* __res
     if (threadIdx.x == 0) { float a = 0.f; for (int i = 0; i < 8; ++i) a += r[i]; atomicAdd(out, a * scale); }
 }
 
+// L2 kernel regulariser of every regularised tensor in ONE launch (main_training.py:232-233):
+// table[e] = {param fp32 ptr, grad fp32 ptr, n} (int64 each); out[0] += coef * sum p^2 ; grad += 2 * coef * p.
+__global__ void __launch_bounds__(256)
+l2_reg_batched_kernel(const long long* __restrict__ table, float coef, float* __restrict__ out) {
+    const long long* e = table + 3 * blockIdx.y;
+    const float* p = reinterpret_cast<const float*>(e[0]);
+    float* g = reinterpret_cast<float*>(e[1]);
+    const long long n = e[2];
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = p[i];
+        s = fmaf(v, v, s);
+        g[i] = fmaf(2.f * coef, v, g[i]);
+    }
+    __shared__ float r[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float a = 0.f; for (int i = 0; i < 8; ++i) a += r[i]; atomicAdd(out, a * coef); }
+}
+
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long n8) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const uint4 ua = a[i], ub = b[i];
@@ -756,6 +777,12 @@ int axpy(float* y, const float* x, float a, long long n, cudaStream_t st) {
 int sumsq(const float* x, long long n, float scale, float* out, int accumulate, cudaStream_t st) {
     if (!accumulate) URIR_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
     sumsq_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, n, scale, out);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+int l2_reg_batched(const long long* table_dev, int n_entries, float coef, float* out, cudaStream_t st) {
+    URIR_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
+    l2_reg_batched_kernel<<<dim3(64, n_entries), 256, 0, st>>>(table_dev, coef, out);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }

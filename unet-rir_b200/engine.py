@@ -484,14 +484,13 @@ class UNetEngine:
 
     def l2_loss_and_grad(self, scale):
         """DP loss regulariser (main_training.py:232-233): reg = scale * 0.001 * sum ||W||^2 over the
-        strided convs and ConvTs; its gradient 2*scale*0.001*W is added to the flat gradient."""
-        first = True
-        for name in self.offsets:
-            if PL.l2_regularised(name):
-                p, g = self.param[name], self.grad[name]
-                L.call("sumsq", p.data_ptr(), p.numel(), scale * PL.L2_COEF, self.reg_dev.data_ptr(), 0 if first else 1)
-                L.call("axpy", g.data_ptr(), p.data_ptr(), 2.0 * scale * PL.L2_COEF, p.numel())
-                first = False
+        strided convs and ConvTs; its gradient 2*scale*0.001*W is added to the flat gradient. One launch."""
+        if getattr(self, "_l2_table", None) is None:
+            rows = [[self.param[n].data_ptr(), self.grad[n].data_ptr(), self.param[n].numel()]
+                    for n in self.offsets if PL.l2_regularised(n)]
+            self._l2_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        L.call("l2_reg_batched", self._l2_table.data_ptr(), self._l2_table.shape[0], float(scale * PL.L2_COEF),
+               self.reg_dev.data_ptr())
         return self.reg_dev
 
     def adam_step(self, beta1=0.9, beta2=0.999, eps=1e-7):
