@@ -52,6 +52,7 @@ struct HaloParams {
     int bias_mod;               // bias index = GEMM-N column % bias_mod (the 4 parity classes of an up-2 layer share it)
     int accumulate;             // out += result (fp32 add before the bf16 rounding)
     int grp_off[16];            // output element offset of every 32-column group of GEMM-N (channel / parity placement)
+    int debug;                  // URIR_HALO_DEBUG: 1 no global stores, 2 no epilogue math/stores, 3 no MMAs, 4 no TMA loads (timing experiments)
     long long* trace;           // debug (URIR_HALO_TRACE): clock64 stamps of CTA 0, 8 per tile, first 128 tiles
     short tap_row[36];          // first box row of tap t = dw * PH + dh
     short wtap[36];             // weight tap index of tap t
@@ -179,9 +180,9 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 (void)trp;
                 mbar_wait(empty_bar + stage, phase ^ 1);
                 uint64_t* fb = full_bar + fj * HL_MAX_STAGES + stage;
-                mbar_expect_tx_elect(fb, (uint32_t)(p.nplanes * p.a_box_bytes));
-                tma_load_4d_elect(&maps.a[0], fb, dst, kc * BLOCK_K, ch, cw, n);
-                if (p.nplanes > 1) {
+                mbar_expect_tx_elect(fb, p.debug == 4 ? 0u : (uint32_t)(p.nplanes * p.a_box_bytes));
+                if (p.debug != 4) tma_load_4d_elect(&maps.a[0], fb, dst, kc * BLOCK_K, ch, cw, n);
+                if (p.nplanes > 1 && p.debug != 4) {
 #pragma unroll
                     for (int pl = 1; pl < 4; ++pl)
                         tma_load_4d_elect(&maps.a[pl], fb, dst + pl * p.plane_bytes, kc * BLOCK_K, ch, cw, n);
@@ -210,6 +211,15 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         int fj = 0; uint32_t fpar = 0;       // full-barrier set of the current pass, parity within that set
         uint32_t a_lo = a_lo0;
         int it = 0;
+        // Stagger the issuers by half a tile of tensor-pipe time. Started together they fall into lock step: both
+        // stream their MMAs at once (interleaved at the pipe's rate), then both sit in their ~600-cycle between-tile
+        // gap (commits, barrier waits) at once and the pipe idles; URIR_HALO_TRACE showed 1140 cycles per tile
+        // against 800 of MMA time. Half a period apart, one warp's gap hides behind the other's MMAs.
+        if (mw == 1 && !p.one_issuer && p.debug == 7) {          // measured: the issuers fall back into lock step (epilogue-coupled); off
+            const long long t0 = clock64();
+            const long long delay = (long long)p.ntaps * p.nchunks * (BLOCK_K / 16) * (BLOCK_N <= 64 ? 24 : BLOCK_N <= 128 ? 32 : 64);
+            while (clock64() - t0 < delay) { }
+        }
         for (int tile = blockIdx.x; tile < issue_end; tile += gridDim.x, ++it) {
             // An mbarrier parity wait cannot tell "fill k+2 complete" from "fill k complete", so a waiter must observe
             // EVERY phase of a barrier it waits on. Tiles alternate between the two issuers, and unless the ring length
@@ -238,7 +248,9 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 if (trm && kc == p.nchunks - 1) p.trace[it * 8 + 2] = clock64();
                 fence_after_sync();
                 uint32_t b_lo = w_lo + ((kc * B_BYTES) >> 4);
-                for (int t = 0; t < p.ntaps; ++t) {
+                // (a fully unrolled 9-tap variant with register-resident offsets was measured: faster in isolation
+                // for the 64-channel dgrad, no gain at step level, more spills -- kept simple)
+                for (int t = 0; t < (p.debug == 3 ? 0 : p.ntaps); ++t) {
                     const uint32_t a_t = a_lo + (((uint32_t)__shfl_sync(0xffffffffu, (int)p.tap_row[t], 0) * ROW_BYTES) >> 4);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
@@ -311,7 +323,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             // TMEM loads have a long latency while the tensor pipe is streaming MMAs (the dominant epilogue stall
             // in the ncu source view), so all loads of a phase (<= 64 columns) are issued before one wait.
 #pragma unroll
-            for (int ph = 0; ph < BLOCK_N / PH_COLS; ++ph) {
+            for (int ph = 0; ph < (p.debug == 2 ? 0 : BLOCK_N / PH_COLS); ++ph) {
                 uint32_t r[PH_COLS];
 #pragma unroll
                 for (int c = 0; c < PH_COLS / 32; ++c) tmem_ld32(lane_addr + ph * PH_COLS + c * 32, r + c * 32);
@@ -348,11 +360,18 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                         // 32 channels = four 16-byte chunks per pixel. Transpose them across the 4 lanes of a group so
                         // that store i writes chunk (lane & 3) of pixel (group, i): 64 contiguous bytes per lane group
                         // (full sectors) instead of four scattered 16-byte pieces.
+                        if (p.debug == 6) {      // experiment: each lane stores its own pixel's 64 bytes, no transpose
+                            __nv_bfloat16* own = const_cast<__nv_bfloat16*>(orow) + p.grp_off[n_tile * (BLOCK_N / 32) + (b >> 1)];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (valid) *reinterpret_cast<uint4*>(own + 8 * i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                        } else {
                         hl_transpose4(pk, lane);
                         const int c32 = p.grp_off[n_tile * (BLOCK_N / 32) + (b >> 1)] + (lane & 3) * 8;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (gvalid[i]) *reinterpret_cast<uint4*>(gout[i] + c32) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                            if (gvalid[i] && p.debug != 1) *reinterpret_cast<uint4*>(gout[i] + c32) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                        }
                     }
                     if (want_stats) {
                         float q[16];
@@ -481,6 +500,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     p.bias_mod = ng; p.accumulate = 0;
     for (int g = 0; g < 16; ++g) p.grp_off[g] = 32 * g;
     { const char* e = getenv("URIR_HALO_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr; }
+    { const char* e = getenv("URIR_HALO_DEBUG"); p.debug = e ? atoi(e) : 0; }
     if (op == 0) { p.oh0 = -d->pad_top; p.ow0 = -d->pad_left; }
     else { p.oh0 = d->pad_top - (d->R - 1); p.ow0 = d->pad_left - (d->S - 1); }
     for (int r = 0; r < d->R; ++r)
