@@ -187,3 +187,35 @@ def test_data_parallel_step_world1_matches_oracle_dp_loss():
             assert U.rel_l2(g, 2 * O.L2_COEF * params[n]) < 1e-6, n
         else:
             assert float(g.abs().max()) == 0.0, n
+
+
+def test_train_step_with_default_kernel_size_6():
+    """The constructor default kernels=6 (u_net.py:42): 6x6 SAME convs (pad 2,3 / 2,2) take the generic tcgen05 paths
+    (no stride-2 halo / up-2 kernels). One training forward + backward against the oracle on the device's own forward
+    state, same tolerances as the kernels=3 test."""
+    om, params, x, y, emb, mask = _setup(B=2, kernels=6)
+    st = O.new_opt_state(params, om.plan)
+    (loss, lp, ls), grads32, ref_out = O.train_step(om, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    eng = UNetEngine(kernels=6)
+    eng.load_state_dict(params)
+    out = eng.forward(x.cuda(), emb.cuda(), training=True, dropout_mask=mask.cuda())
+    assert U.max_abs(out.float(), ref_out) < 3e-2 and U.rel_l2(out.float(), ref_out) < 1.5e-2
+    n = 2 * 144 * 160
+    losses = eng.loss_and_grad(y.cuda(), 1.0 / n, 1.0 / n)
+    assert abs(float(losses[0]) - float(loss)) < 2e-3 * float(loss)
+    eng.backward(eng._buffers(2)["g_out"])
+    torch.cuda.synchronize()
+    oq = O.UNetOracle(kernels=6, emulate_bf16=True)
+    oq.override = eng.forward_state()
+    _, grads, _ = O.train_step(oq, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    bad = []
+    for name in eng.trainable_names():
+        got, ref = eng.grad[name].cpu(), grads[name]
+        scale = float(ref.abs().max())
+        if name.endswith(".b") and (".blk." in name or ".fuse" in name):
+            ok = U.max_abs(got, ref) < 2e-3
+        else:
+            ok = U.rel_l2(got, ref) < 2.5e-2 or U.max_abs(got, ref) < 1e-7 + 1e-3 * scale
+        if not ok:
+            bad.append((name, U.rel_l2(got, ref), U.max_abs(got, ref), scale))
+    assert not bad, bad

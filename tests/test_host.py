@@ -191,3 +191,21 @@ def test_data_parallel_arithmetic_world2_gloo(tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith("DP_ERR")][0].split()
     assert float(line[1]) < 1e-5            # bucketed all-reduce == sum of per-replica gradients
     assert float(line[2]) > 1e-3            # and is NOT the full-batch-BN gradient (BN is per replica)
+
+
+def test_rt60_and_edc_of_known_decays():
+    """rir_generation.rt60 / edc_db (torch, device-agnostic) against the oracle's numpy version and the analytic value
+    for x[t] = N(0,1) * exp(-6.91 t / (rt60 * sr)) (60 dB of energy decay after rt60 seconds)."""
+    import numpy as np
+    from oracle import signal_oracle as SO
+    from unet_rir_b200 import rir_generation as RG
+    rng = np.random.default_rng(1)
+    want = np.array([0.1, 0.2, 0.35])
+    h = SO.synthetic_rir(3, rng, rt60_s=want, length=9600)
+    got = RG.rt60(torch.as_tensor(h)).numpy()
+    for i in range(3):
+        assert abs(got[i] - SO.rt60(h[i])) < 1e-9 * max(1.0, got[i])
+        assert abs(got[i] - want[i]) < 0.1 * want[i]
+    e = RG.edc_db(torch.as_tensor(h)).numpy()
+    assert np.allclose(e[:, 0], 0.0) and (np.diff(e, axis=1) <= 1e-12).all()
+    assert np.abs(e[0] - SO.edc_db(h[0])).max() < 1e-9
