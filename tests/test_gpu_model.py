@@ -13,6 +13,7 @@ deepest tensors differ by ~30 %; even a 1e-4 perturbation of one BN mean moves d
 percent. Pinning the forward state isolates what the backward kernels compute. Against the pure-fp32 oracle
 the test additionally requires cosine similarity >= 0.9 and a norm ratio within 15 % for every kernel.
 Biases of BN-followed convs (true gradient analytically zero) are checked in absolute terms."""
+import numpy as np
 import pytest
 import torch
 
@@ -219,3 +220,34 @@ def test_train_step_with_default_kernel_size_6():
         if not ok:
             bad.append((name, U.rel_l2(got, ref), U.max_abs(got, ref), scale))
     assert not bad, bad
+
+
+def test_prefetched_inputs_give_the_same_step():
+    """Trainer.prefetch (copy-stream staging of the next batch) + step == step alone; a step called with other
+    objects than the prefetched ones ignores the staged copy."""
+    from unet_rir_b200.amp_phase_trainer import EarlyStopping, ModelCheckpoint, Trainer
+    from unet_rir_b200.dl_models.u_net import UNet
+    g = torch.Generator().manual_seed(5)
+    B = 4
+    batches = [(torch.rand(B, 144, 160, 2, generator=g).pin_memory(), torch.rand(B, 144, 160, 2, generator=g).pin_memory(),
+                torch.randint(0, 2000, (B, 2, 16), generator=g, dtype=torch.int32).pin_memory()) for _ in range(3)]
+    losses = []
+    for use_prefetch in (False, True):
+        unet = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+        tr = Trainer(0.9, 1, "adam", [ModelCheckpoint("/tmp/urir_pf", False, 0), EarlyStopping(5)], [False, 0], 1e-4, "pf")
+        tr.dropout = False
+        out = []
+        if use_prefetch:
+            tr.prefetch(*batches[0], unet)
+        for i, (x, y, e) in enumerate(batches):
+            l = tr.step(x, y, e, unet)[0]
+            if use_prefetch and i + 1 < len(batches):
+                tr.prefetch(*batches[i + 1], unet)
+            out.append(float(l))
+        if use_prefetch:                       # stale prefetch: announce batch 0, then step on batch 1
+            tr.prefetch(*batches[0], unet)
+            l_stale = float(tr.step(*batches[1], unet)[0])
+            assert np.isfinite(l_stale)
+        losses.append(out)
+    for a, b in zip(*losses):
+        assert abs(a - b) < 2e-3 * abs(a), losses      # same data, same init; BN statistics / gradients use atomics

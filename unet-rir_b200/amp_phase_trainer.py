@@ -128,9 +128,13 @@ class Trainer:
                 if epoch >= self.lr_exp_decay_epoch:
                     self.learning_rate = self.lr0 * np.exp(-0.25 * (epoch - self.lr_exp_decay_epoch))
 
+            nxt = self._next_batch(train_generator, 0) if numUpdates > 0 else None
             for i in range(0, numUpdates):
-                spec_in, spec_out, emb = self._next_batch(train_generator, i)
+                spec_in, spec_out, emb = nxt
                 loss, loss_phase, loss_stft = self.step(spec_in, spec_out, emb, model)
+                if i + 1 < numUpdates:        # next batch's H2D copy overlaps this step (enqueued, not waited for)
+                    nxt = self._next_batch(train_generator, i + 1)
+                    self.prefetch(nxt[0], nxt[1], nxt[2], model)
                 train_loss.append(loss)
                 train_loss_phase.append(loss_phase)
                 train_loss_stft.append(loss_stft)
@@ -195,15 +199,22 @@ class Trainer:
         elif self.optimizer == 'sgd':
             eng.sgd_step()
 
+    def prefetch(self, spec_in, spec_out, emb, model):
+        """Optional: start the host -> device copy of the NEXT batch (same argument order as step) on a copy
+        stream while the current step computes; the following step(...) called with the same objects uses it.
+        train() does this for every batch."""
+        model.model.engine.prefetcher.prefetch(spec_in, emb, spec_out)
+
     def step(self, spec_in, spec_out, emb, model):
         eng = model.model.engine
         dev = eng.device
-        spec_in = _dev_tensor(spec_in, torch.float32, dev)
-        spec_out = _dev_tensor(spec_out, torch.float32, dev)
-        emb = _dev_tensor(emb, torch.int32, dev)
-        B = spec_in.shape[0]
+        B = int(spec_in.shape[0])
         eng.set_lr(self.learning_rate)
-        eng.stage(spec_in, emb, spec_out)
+        if not eng.prefetcher.take(spec_in, emb, spec_out):      # not announced with prefetch(): copy now
+            spec_in = _dev_tensor(spec_in, torch.float32, dev)
+            spec_out = _dev_tensor(spec_out, torch.float32, dev)
+            emb = _dev_tensor(emb, torch.int32, dev)
+            eng.stage(spec_in, emb, spec_out)
         if self.optimizer == 'nadam':
             self._device_step(eng, B)
             if self._nadam is None:

@@ -22,6 +22,7 @@ import ctypes as C
 import os
 from collections import OrderedDict
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -51,6 +52,62 @@ class View:
 
 def _align(n, a=4):
     return (n + a - 1) // a * a
+
+
+class InputPrefetcher:
+    """Double-buffered host -> device staging of a batch on a copy stream, so the H2D copy of batch i+1 overlaps the
+    train step of batch i (the reference's tf.data pipeline does the same for MirroredStrategy,
+    main_training.py:114). `prefetch` enqueues the copies; `take` hands the staged device tensors to the step that
+    is called with the SAME host objects (identity match), after making the compute stream wait for the copy."""
+
+    def __init__(self, eng):
+        self.eng, self.stream, self.sets, self.pending, self.k = eng, None, {}, None, 0
+
+    def _set(self, B, k):
+        key = (B, k)
+        if key not in self.sets:
+            H, W, Cin = self.eng.input_shape
+            dev = self.eng.device
+            self.sets[key] = {"x": torch.empty(B, H, W, Cin, dtype=torch.float32, device=dev),
+                              "y": torch.empty(B, H, W, 2, dtype=torch.float32, device=dev),
+                              "emb": torch.empty(B, self.eng.T, dtype=torch.int32, device=dev),
+                              "ready": None, "consumed": None}
+        return self.sets[key]
+
+    @staticmethod
+    def _host(t, dtype):
+        t = t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t))
+        return t if t.dtype == dtype else t.to(dtype)
+
+    def prefetch(self, spec_in, emb, spec_out):
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=self.eng.device)
+        B = int(spec_in.shape[0])
+        s = self._set(B, self.k)
+        self.k ^= 1
+        if s["consumed"] is not None:
+            self.stream.wait_event(s["consumed"])          # the step that last read this set has copied it out
+        with torch.cuda.stream(self.stream):
+            s["x"].copy_(self._host(spec_in, torch.float32).reshape(s["x"].shape), non_blocking=True)
+            s["y"].copy_(self._host(spec_out, torch.float32).reshape(s["y"].shape), non_blocking=True)
+            s["emb"].copy_(self._host(emb, torch.int32).reshape(s["emb"].shape), non_blocking=True)
+            s["ready"] = torch.cuda.Event()
+            s["ready"].record(self.stream)
+        self.pending = (id(spec_in), id(emb), id(spec_out), s)
+
+    def take(self, spec_in, emb, spec_out):
+        """Stages a prefetched batch into the engine's static input buffers; False when nothing matches."""
+        pd = self.pending
+        if pd is None or pd[:3] != (id(spec_in), id(emb), id(spec_out)):
+            return False
+        self.pending = None
+        s = pd[3]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(s["ready"])
+        self.eng.stage(s["x"], s["emb"], s["y"])           # device -> device into the buffers the CUDA graph reads
+        s["consumed"] = torch.cuda.Event()
+        s["consumed"].record(cur)
+        return True
 
 
 class UNetEngine:
@@ -84,6 +141,7 @@ class UNetEngine:
         self.losses_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.side = torch.cuda.Stream(device=self.device)
+        self.prefetcher = InputPrefetcher(self)
         self.overlap_wgrad = os.environ.get("URIR_NO_OVERLAP", "0") != "1"
         self._side_dirty = False
 

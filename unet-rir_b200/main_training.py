@@ -150,17 +150,23 @@ class DistributedTrainer:
                 works.append(dist.all_reduce(self.eng.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
         self._calls += 1
 
+    def prefetch(self, spec_in, emb, spec_out):
+        """Start the host -> device copy of the next shard on a copy stream (same argument order as train_step)."""
+        self.eng.prefetcher.prefetch(spec_in, emb, spec_out)
+
     def train_step(self, spec_in, emb, spec_out):
         """inputs = this replica's shard (spec_in, emb, spec_out), the tuple order of the reference's
         train_step (main_training.py:254). Returns the replica's loss contribution as a 0-d tensor;
         `strategy.reduce(SUM)` of those (:326) is the global loss."""
         e = self.eng
         dev = e.device
-        spec_in = torch.as_tensor(spec_in).to(dev, torch.float32, non_blocking=True)
-        spec_out = torch.as_tensor(spec_out).to(dev, torch.float32, non_blocking=True)
-        emb = torch.as_tensor(emb).to(dev, torch.int32, non_blocking=True)
-        e.stage(spec_in, emb, spec_out)
-        self._run(spec_in.shape[0])
+        B = int(spec_in.shape[0])
+        if not e.prefetcher.take(spec_in, emb, spec_out):
+            spec_in = torch.as_tensor(spec_in).to(dev, torch.float32, non_blocking=True)
+            spec_out = torch.as_tensor(spec_out).to(dev, torch.float32, non_blocking=True)
+            emb = torch.as_tensor(emb).to(dev, torch.int32, non_blocking=True)
+            e.stage(spec_in, emb, spec_out)
+        self._run(B)
         loss = e.losses_dev[0].clone()
         if self.loss == "dp":
             loss = loss + e.reg_dev[0] / self.world      # reg_dev = sum(l2); each replica's share is 1/replicas
