@@ -211,6 +211,10 @@ int urir_sumsq(const float* x, long long n, float scale, float* out, int accumul
 int urir_l2_reg_batched(const int64_t* table_dev, int n_entries, float coef, float* out, void* stream);
 /* elementwise helpers for the alternate block modes (u_net.py:337,359) and casts */
 int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+/* the same for C-channel slices of NHWC buffers (residual_block_1 / residual_block_2 Adds, u_net.py:337,359, and
+ * their gradient fan-in); out may alias an input */
+int urir_add_bf16_strided(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff,
+                          void* out, int out_ld, int out_coff, long long npix, int C, void* stream);
 int urir_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 /* fp32 [npix][C] -> bf16 [npix][ld], ld >= C: the 16-byte-pitch bf16 copy of the 2-channel input
  * spectrogram that the stem's tensor-core weight-gradient reads through TMA (u_net.py:269-276). */

@@ -251,3 +251,57 @@ def test_prefetched_inputs_give_the_same_step():
         losses.append(out)
     for a, b in zip(*losses):
         assert abs(a - b) < 2e-3 * abs(a), losses      # same data, same init; BN statistics / gradients use atomics
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_alternate_block_modes(mode):
+    """mode 1 convolutional_block_2, 2 residual_block_1, 3 residual_block_2 (u_net.py:280-287, 324-386): eval forward
+    against the fp32 oracle, then a training forward + backward against the oracle evaluated on the device's own
+    forward state (same method and tolerances as the mode-0 test)."""
+    g = torch.Generator().manual_seed(mode)
+    om = O.UNetOracle(kernels=3, mode=mode)
+    params = O.init_params(om.plan, seed=500)
+    for n, _, kind in om.plan:
+        if kind == "gamma":
+            params[n] = 1 + 0.2 * torch.randn(params[n].shape, generator=g)
+        elif kind in ("beta", "bias"):
+            params[n] = 0.1 * torch.randn(params[n].shape, generator=g)
+    x = torch.rand(2, 144, 160, 2, generator=g); y = torch.rand(2, 144, 160, 2, generator=g)
+    emb = torch.randint(0, 2000, (2, 2, 16), generator=g, dtype=torch.int32)
+    mask = (torch.rand(2, 1440, generator=g) > 0.3).float() / 0.7
+    eng = UNetEngine(kernels=3, mode=mode)
+    assert eng.trainable_names() == O.trainable_names(om.plan)
+    eng.load_state_dict(params)
+    out = eng.forward(x.cuda(), emb.cuda(), training=False).float().cpu()
+    ref = om.forward(params, x, emb, training=False)
+    assert U.max_abs(out, ref) < 2e-2 and U.rel_l2(out, ref) < 1e-2
+
+    st = O.new_opt_state(params, om.plan)
+    (loss, lp, ls), _, ref_out = O.train_step(om, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    out = eng.forward(x.cuda(), emb.cuda(), training=True, dropout_mask=mask.cuda())
+    assert U.rel_l2(out.float(), ref_out) < 2.5e-2
+    n = 2 * 144 * 160
+    losses = eng.loss_and_grad(y.cuda(), 1.0 / n, 1.0 / n)
+    assert abs(float(losses[0]) - float(loss)) < 5e-3 * float(loss)
+    eng.backward(eng._buffers(2)["g_out"])
+    torch.cuda.synchronize()
+    oq = O.UNetOracle(kernels=3, mode=mode, emulate_bf16=True)
+    oq.override = eng.forward_state()
+    _, grads, _ = O.train_step(oq, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    bad = []
+    for name in eng.trainable_names():
+        got, refg = eng.grad[name].cpu(), grads[name]
+        scale = float(refg.abs().max())
+        if name.endswith(".b") and (".blk." in name or ".fuse" in name):
+            ok = U.max_abs(got, refg) < 3e-3
+        elif name.endswith(".down.b") or name.endswith(".up.b") or name == "vec.proj.b":
+            # sums over all pixels of a gradient that just left a BatchNorm backward (zero mean per channel):
+            # cancellation-dominated, and these nets double / triple the number of BN layers -- direction and size
+            got_d, ref_d = got.double().flatten(), refg.double().flatten()
+            cos = float((got_d @ ref_d) / (got_d.norm() * ref_d.norm() + 1e-300))
+            ok = U.rel_l2(got, refg) < 0.3 and cos > 0.95
+        else:
+            ok = U.rel_l2(got, refg) < 3e-2 or U.max_abs(got, refg) < 1e-7 + 1e-3 * scale
+        if not ok:
+            bad.append((name, U.rel_l2(got, refg), U.max_abs(got, refg), scale))
+    assert not bad, bad

@@ -70,6 +70,7 @@ _PROTOS = {
     "urir_axpy": (_i, [_vp, _vp, _f, _ll, _vp]),
     "urir_sumsq": (_i, [_vp, _ll, _f, _vp, _i, _vp]),
     "urir_add_bf16": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "urir_add_bf16_strided": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _ll, _i, _vp]),
     "urir_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "urir_cast_pad_bf16": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "urir_stft_ampphase": (_i, [_vp, _i, C.POINTER(StftDesc), _vp, _vp]),

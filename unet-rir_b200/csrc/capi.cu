@@ -69,6 +69,7 @@ int step_increment(int*, cudaStream_t);
 int axpy(float*, const float*, float, long long, cudaStream_t);
 int sumsq(const float*, long long, float, float*, int, cudaStream_t);
 int add_bf16(const void*, const void*, void*, long long, cudaStream_t);
+int add_bf16_strided(const void*, int, int, const void*, int, int, void*, int, int, long long, int, cudaStream_t);
 int l2_reg_batched(const long long*, int, float, float*, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, long long, cudaStream_t);
 int cast_pad_bf16(const float*, void*, long long, int, int, cudaStream_t);
@@ -295,6 +296,11 @@ int urir_sumsq(const float* x, long long n, float scale, float* out, int accumul
 int urir_l2_reg_batched(const int64_t* table_dev, int n_entries, float coef, float* out, void* stream) {
     URIR_CHECK_ARG(table_dev && out && n_entries > 0, "l2_reg_batched: bad args");
     return l2_reg_batched(reinterpret_cast<const long long*>(table_dev), n_entries, coef, out, (cudaStream_t)stream);
+}
+int urir_add_bf16_strided(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, void* out, int out_ld,
+                          int out_coff, long long npix, int C, void* stream) {
+    URIR_CHECK_ARG(a && b && out && npix > 0 && C > 0, "add_bf16_strided: bad args");
+    return add_bf16_strided(a, a_ld, a_coff, b, b_ld, b_coff, out, out_ld, out_coff, npix, C, (cudaStream_t)stream);
 }
 int urir_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
     URIR_CHECK_ARG(a && b && out && n > 0, "add_bf16: bad args");

@@ -109,8 +109,9 @@ __device__ __forceinline__ void hl_transpose4(uint32_t (&pk)[16], int lane) {
 }
 __device__ __forceinline__ int hl_col_of_lane(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
 
-template <int BLOCK_N, int BLOCK_K, bool ACC>
-__global__ void __launch_bounds__(384, 1)
+// NG = epilogue groups (2: warps 0-3, 8-11; 4: additionally warps 12-15, 16-19 -- 640 threads, <= 96 registers)
+template <int BLOCK_N, int BLOCK_K, bool ACC, int NG>
+__global__ void __launch_bounds__(NG == 4 ? 640 : 384, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
     constexpr uint32_t SWZ = (BLOCK_K == 64) ? SWZ_128B : SWZ_64B;
     constexpr uint32_t ROW_BYTES = BLOCK_K * 2;
@@ -272,7 +273,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         // ===================== epilogue: group 0 = warps 0-3 (even tiles), group 1 = warps 8-11 (odd tiles) ====
         // one tile's epilogue is a ~900-cycle latency chain (barrier wait, TMEM loads, stores); two groups give
         // each of them two tile times to finish it
-        const int eg = warp >= 8 ? 1 : 0;
+        const int eg = warp >= 8 ? ((warp - 8) >> 2) + 1 : 0;      // group eg drains the tiles with it % NG == eg
         const int quarter = warp & 3;
         constexpr int HS = BLOCK_N >= 128 ? 2 : BLOCK_N >= 64 ? 1 : 0;   // halving steps per tile (see hl_halve_head)
         constexpr int PART = 16 >> HS;                       // partial sums kept per 16-column block
@@ -284,7 +285,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         const int ih = row & 7, iw = row >> 3;
         const bool want_stats = p.stats != nullptr;
         int it = eg;
-        for (int tile = blockIdx.x + eg * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+        for (int tile = blockIdx.x + eg * gridDim.x; tile < p.total_tiles; tile += NG * gridDim.x, it += NG) {
             const int acc = it & 3;
             int t = tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -461,15 +462,15 @@ bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
     return forced || tiles >= 148 * 4;
 }
 
-template <int BN, int BK, bool ACC = false>
+template <int BN, int BK, bool ACC = false, int NG = 2>
 static int launch_halo(const HaloMaps& maps, const HaloParams& p, int n_tiles, int smem, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = conv_halo_kernel<BN, BK, ACC>;
+    auto kern = conv_halo_kernel<BN, BK, ACC, NG>;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BUDGET + 4096)); attr_set = true; }
     int gx = 148 / n_tiles; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     dim3 grid(gx, n_tiles);
-    URIR_CUDA_OK(launch_pdl(kern, grid, dim3(384), smem, st, maps, p));
+    URIR_CUDA_OK(launch_pdl(kern, grid, dim3(NG == 4 ? 640 : 384), smem, st, maps, p));
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }
@@ -526,6 +527,9 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     }
     const int smem = p.w_bytes + p.stages * p.a_stage_bytes + ((HL_MAX_FSETS + 1) * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
     const int n_tiles = ng / BN;
+    { static int ng4 = -1; if (ng4 < 0) { const char* e = getenv("URIR_HALO_NG4"); ng4 = (e && e[0] == '1') ? 1 : 0; }
+      if (ng4 && BN == 32 && BK == 32) return launch_halo<32, 32, false, 4>(maps, p, n_tiles, smem, st);
+      if (ng4 && BN == 32 && BK == 64) return launch_halo<32, 64, false, 4>(maps, p, n_tiles, smem, st); }
 #define URIR_HL(BN_, BK_) if (BN == BN_ && BK == BK_) return launch_halo<BN_, BK_>(maps, p, n_tiles, smem, st);
     URIR_HL(32, 32) URIR_HL(32, 64) URIR_HL(64, 32) URIR_HL(64, 64) URIR_HL(128, 32) URIR_HL(128, 64)
 #undef URIR_HL

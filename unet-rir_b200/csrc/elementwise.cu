@@ -786,6 +786,37 @@ int l2_reg_batched(const long long* table_dev, int n_entries, float coef, float*
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
+// out[p, c] = a[p, c] + b[p, c] for channel slices of NHWC buffers (the residual Adds of block modes 2 / 3 and their
+// gradient fan-in); out may alias a or b. 8 channels (128 bits) per thread.
+__global__ void __launch_bounds__(256)
+add_bf16_strided_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, int a_coff, const __nv_bfloat16* __restrict__ b,
+                        int b_ld, int b_coff, __nv_bfloat16* __restrict__ o, int o_ld, int o_coff, long long npix, int C) {
+    const int G = C >> 3;
+    const long long total = npix * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / G;
+        const int c = (int)(i - pix * G) << 3;
+        const uint4 ua = *reinterpret_cast<const uint4*>(a + pix * a_ld + a_coff + c);
+        const uint4 ub = *reinterpret_cast<const uint4*>(b + pix * b_ld + b_coff + c);
+        const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w}, bb[4] = {ub.x, ub.y, ub.z, ub.w};
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 x = unpack_bf16x2(aa[j]), y = unpack_bf16x2(bb[j]);
+            r[j] = pack_bf16x2(x.x + y.x, x.y + y.y);
+        }
+        *reinterpret_cast<uint4*>(o + pix * o_ld + o_coff + c) = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+}
+int add_bf16_strided(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, void* o, int o_ld, int o_coff,
+                     long long npix, int C, cudaStream_t st) {
+    URIR_CHECK_ARG(vec8_ok(C, a_ld, a_coff) && vec8_ok(C, b_ld, b_coff) && vec8_ok(C, o_ld, o_coff),
+                   "add_bf16_strided: C/ld/coff must be multiples of 8");
+    add_bf16_strided_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, st>>>((const __nv_bfloat16*)a, a_ld, a_coff,
+        (const __nv_bfloat16*)b, b_ld, b_coff, (__nv_bfloat16*)o, o_ld, o_coff, npix, C);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
 int add_bf16(const void* a, const void* b, void* o, long long n, cudaStream_t st) {
     URIR_CHECK_ARG(n % 8 == 0, "add_bf16: n must be a multiple of 8");
     add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)o, n / 8);

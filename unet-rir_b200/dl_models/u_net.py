@@ -13,8 +13,8 @@ Deviations, all deliberate and visible:
   * weights are saved as a torch state dict (`weights.pt`); h5py / Keras `weights.h5` do not exist here.
   * `_save_parameters` also stores `kernels`. The reference omits it (u_net.py:180-187), so its own
     `UNet.load` rebuilds with `BatchNorm` shifted into the `kernels` slot -- a latent bug we do not copy.
-  * only `mode=0` with `BatchNorm=True` is wired on the device (the only configuration any reference
-    call site uses); other modes raise NotImplementedError at construction.
+  * all four block modes (0 convolutional_block_1 ... 3 residual_block_2) are wired on the device with
+    `BatchNorm=True`; every reference call site uses mode 0. `BatchNorm=False` raises NotImplementedError.
 """
 from __future__ import annotations
 

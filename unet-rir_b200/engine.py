@@ -114,10 +114,9 @@ class UNetEngine:
     def __init__(self, input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0,
                  number_filters_0=32, kernels=6, BatchNorm=True, device="cuda", seed=500,
                  impl=L.IMPL_AUTO, bn_unbiased_moving_var=False):
-        if mode != 0:
-            raise NotImplementedError(
-                "the CUDA engine wires mode=0 (convolutional_block_1), the only mode any reference call "
-                "site uses (u_net.py:392, main_training.py:157, rir_generation.py:119)")
+        if mode not in (0, 1, 2, 3):
+            raise ValueError("mode must be 0 (convolutional_block_1), 1 (convolutional_block_2), 2 (residual_block_1) "
+                             "or 3 (residual_block_2)  (u_net.py:280-287)")
         if not BatchNorm:
             raise NotImplementedError("BatchNorm=False is not wired in the CUDA engine")
         H, W, Cin = input_shape
@@ -266,6 +265,18 @@ class UNetEngine:
                     b[f"{nm}{i}"] = act(h, w, n); b[f"g_{nm}{i}"] = act(h, w, n)
             else:
                 b["z"] = act(h, w, n); b["g_z"] = act(h, w, n)
+        if self.mode != 0:
+            # block modes 1-3 (u_net.py:324-386): activation after c1, raw c2 output, (2/3) activation after c2,
+            # (3) raw / activated shortcut conv -- and the matching gradients, per block
+            for i in range(1, 6):
+                n = self.F0 * 2 ** (i - 1)
+                h, w = (H, W) if i == 1 else (H >> (i - 1), W >> (i - 1))
+                for key in ([f"enc{i}"] + ([f"dec{6 - i}"] if i < 5 else [])):
+                    names = ["a1", "raw2"] + (["a2"] if self.mode >= 2 else []) + (["raw3", "a3"] if self.mode == 3 else [])
+                    for nm in names:
+                        b[f"{key}.{nm}"] = act(h, w, n)
+                        if nm != "a2" and nm != "a3":
+                            b[f"g_{key}.{nm}"] = act(h, w, n)
         b["embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=bf, device=dev)
         b["g_embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=bf, device=dev)
         b["v16"] = act(self.H5, self.W5, PL.VEC_CH); b["g_v16"] = act(self.H5, self.W5, PL.VEC_CH)
@@ -364,6 +375,54 @@ class UNetEngine:
         if g_x is not None:
             self._conv_dgrad(cname, g_raw, g_x, k, 1, stats=g_x_stats, accumulate=accumulate)
 
+    def _add(self, a, bv, out):
+        L.call("add_bf16_strided", a.ptr(), a.ld, a.coff, bv.ptr(), bv.ld, bv.coff, out.ptr(), out.ld, out.coff, a.npix, a.C)
+
+    def _blk_fwd(self, key, blk, x, raw1, out, training):
+        """The mode-selected feature block (u_net.py:280-287, 314-319) on block input x -> out.
+        mode 0 convolutional_block_1, 1 convolutional_block_2, 2 residual_block_1 (+ x), 3 residual_block_2 (+ conv shortcut)."""
+        m = self.mode
+        if m == 0:
+            self._cbr_fwd(blk + ".c1", blk + ".bn1", x, raw1, out, 3, training)
+            return
+        b = self._buffers(x.N)
+        a1, raw2 = View(b[key + ".a1"]), View(b[key + ".raw2"])
+        self._cbr_fwd(blk + ".c1", blk + ".bn1", x, raw1, a1, 3, training)
+        if m == 1:
+            self._cbr_fwd(blk + ".c2", blk + ".bn2", a1, raw2, out, 3, training)
+            return
+        a2 = View(b[key + ".a2"])
+        self._cbr_fwd(blk + ".c2", blk + ".bn2", a1, raw2, a2, 3, training)
+        if m == 2:
+            self._add(a2, x, out)
+        else:
+            raw3, a3 = View(b[key + ".raw3"]), View(b[key + ".a3"])
+            self._cbr_fwd(blk + ".c3", blk + ".bn3", x, raw3, a3, 3, training)
+            self._add(a2, a3, out)
+
+    def _blk_bwd(self, key, blk, x, raw1, g_out, g_raw1, g_x, g_x_stats=None):
+        """Backward of _blk_fwd: g_out = dL/d(block output) -> parameter gradients of the block and g_x = dL/dx
+        (overwritten). Returns True when g_x_stats received the channel sums of the COMPLETE g_x."""
+        m = self.mode
+        if m == 0:
+            self._cbr_bwd(blk + ".c1", blk + ".bn1", x, raw1, g_out, g_raw1, 3, g_x=g_x, g_x_stats=g_x_stats)
+            return True
+        b = self._buffers(x.N)
+        a1, raw2 = View(b[key + ".a1"]), View(b[key + ".raw2"])
+        g_a1, g_raw2 = View(b[f"g_{key}.a1"]), View(b[f"g_{key}.raw2"])
+        # the Add of modes 2 / 3 passes g_out unchanged to both summands
+        self._cbr_bwd(blk + ".c2", blk + ".bn2", a1, raw2, g_out, g_raw2, 3, g_x=g_a1)
+        if m == 1:
+            self._cbr_bwd(blk + ".c1", blk + ".bn1", x, raw1, g_a1, g_raw1, 3, g_x=g_x, g_x_stats=g_x_stats)
+            return True
+        self._cbr_bwd(blk + ".c1", blk + ".bn1", x, raw1, g_a1, g_raw1, 3, g_x=g_x)
+        if m == 2:
+            self._add(g_x, g_out, g_x)                      # identity shortcut
+        else:
+            raw3, g_raw3 = View(b[key + ".raw3"]), View(b[f"g_{key}.raw3"])
+            self._cbr_bwd(blk + ".c3", blk + ".bn3", x, raw3, g_out, g_raw3, 3, g_x=g_x, accumulate=1)
+        return False
+
     # ------------------------------------------------------------------ forward
     def stage(self, spec_in, emb, spec_out=None):
         """Copies one batch into the static input buffers (outside any captured graph)."""
@@ -399,7 +458,7 @@ class UNetEngine:
             t, r = View(b[f"t{i}"]), View(b[f"r{i}"])
             e = View(b[f"cat{i}"], 0, n) if i < 5 else View(b["z"])
             self._conv_fprop(f"enc{i}.down", x, t, k, 1 if i == 1 else 2)
-            self._cbr_fwd(f"enc{i}.blk.c1", f"enc{i}.blk.bn1", t, r, e, 3, training)
+            self._blk_fwd(f"enc{i}", f"enc{i}.blk", t, r, e, training)
             x = e
         # ---- vector block + Add (u_net.py:253-263, 229)
         L.call("embedding_fwd", b["emb"].data_ptr(), self.param["vec.emb"].data_ptr(), b["embflat"].data_ptr(),
@@ -427,8 +486,7 @@ class UNetEngine:
             up = View(b[f"cat{i}"], n, n)
             self._conv_dgrad(f"dec{j}.up", x, up, k, 2, bias=True)     # Conv2DTranspose forward
             self._cbr_fwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"f{i}"]), k, training)
-            self._cbr_fwd(f"dec{j}.blk.c1", f"dec{j}.blk.bn1", View(b[f"f{i}"]), View(b[f"rb{i}"]), View(b[f"d{i}"]), 3,
-                          training)
+            self._blk_fwd(f"dec{j}", f"dec{j}.blk", View(b[f"f{i}"]), View(b[f"rb{i}"]), View(b[f"d{i}"]), training)
             x = View(b[f"d{i}"])
         # ---- head: Conv2D(2, 6x6, same) + sigmoid (u_net.py:247-249)
         self._conv_fprop("head", x, View(b["out"]), 6, 1, act=L.ACT_SIGMOID)
@@ -478,8 +536,8 @@ class UNetEngine:
                 i = 6 - j
                 n = self.F0 * 2 ** (i - 1)
                 cat, g_cat = View(b[f"cat{i}"]), View(b[f"g_cat{i}"])
-                self._cbr_bwd(f"dec{j}.blk.c1", f"dec{j}.blk.bn1", View(b[f"f{i}"]), View(b[f"rb{i}"]),
-                              View(b[f"g_d{i}"]), View(b[f"g_rb{i}"]), 3, g_x=View(b[f"g_f{i}"]))
+                self._blk_bwd(f"dec{j}", f"dec{j}.blk", View(b[f"f{i}"]), View(b[f"rb{i}"]),
+                              View(b[f"g_d{i}"]), View(b[f"g_rb{i}"]), View(b[f"g_f{i}"]))
                 st = self._bstat(f"dec{j}.cat", 2 * n)
                 self._cbr_bwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"g_f{i}"]),
                               View(b[f"g_rf{i}"]), k, g_x=g_cat, g_x_stats=st)
@@ -515,10 +573,12 @@ class UNetEngine:
                 n = self.F0 * 2 ** (i - 1)
                 t, r = View(b[f"t{i}"]), View(b[f"r{i}"])
                 st = self._bstat(f"enc{i}.t", n)
-                self._cbr_bwd(f"enc{i}.blk.c1", f"enc{i}.blk.bn1", t, r, g_e, View(b[f"g_r{i}"]), 3,
-                              g_x=View(b[f"g_t{i}"]), g_x_stats=st)
-                self.grad[f"enc{i}.down.b"].copy_(st[:n])
                 g_t = View(b[f"g_t{i}"])
+                if self._blk_bwd(f"enc{i}", f"enc{i}.blk", t, r, g_e, View(b[f"g_r{i}"]), g_t, g_x_stats=st):
+                    self.grad[f"enc{i}.down.b"].copy_(st[:n])
+                else:       # g_t was completed after the dgrad epilogue that produced the statistics: sum it directly
+                    L.call("channel_sum", g_t.ptr(), L.BF16, g_t.npix, n, g_t.ld, g_t.coff,
+                           self.grad[f"enc{i}.down.b"].data_ptr())
                 if i > 1:
                     e_prev = View(b[f"cat{i - 1}"], 0, n // 2)
                     g_e_prev = View(b[f"g_cat{i - 1}"], 0, n // 2)
@@ -586,8 +646,24 @@ class UNetEngine:
             st[f"enc{i}.down"] = nchw(b[f"t{i}"])
             st[f"enc{i}.blk.c1"] = nchw(b[f"r{i}"])
             bn(f"enc{i}.blk.bn1")
-            if i < 5:
-                st[f"enc{i}.blk.bn1.out"] = nchw(b[f"cat{i}"][..., :n])
+            # the last BN+ReLU output of the block IS the block output for modes 0 / 1 (e5 is skipped: the vector
+            # projection is accumulated into the same buffer afterwards)
+            if i < 5 and self.mode <= 1:
+                st[f"enc{i}.blk.bn{self.mode + 1}.out"] = nchw(b[f"cat{i}"][..., :n])
+
+        def extra(key):
+            blk = key + ".blk"
+            st[blk + ".bn1.out"] = nchw(b[key + ".a1"])
+            st[blk + ".c2"] = nchw(b[key + ".raw2"]); bn(blk + ".bn2")
+            if self.mode >= 2:
+                st[blk + ".bn2.out"] = nchw(b[key + ".a2"])
+            if self.mode == 3:
+                st[blk + ".c3"] = nchw(b[key + ".raw3"]); bn(blk + ".bn3")
+                st[blk + ".bn3.out"] = nchw(b[key + ".a3"])
+
+        if self.mode != 0:
+            for i in range(1, 6):
+                extra(f"enc{i}")
         st["bottleneck"] = nchw(b["z"])
         st["vec.dense.out"] = b["v16"].float().reshape(self._last_B, -1).cpu()
         for j in (2, 3, 4, 5):
@@ -595,7 +671,11 @@ class UNetEngine:
             n = self.F0 * 2 ** (i - 1)
             st[f"dec{j}.up"] = nchw(b[f"cat{i}"][..., n:])
             st[f"dec{j}.fuse"] = nchw(b[f"rf{i}"]); bn(f"dec{j}.fuse_bn"); st[f"dec{j}.fuse_bn.out"] = nchw(b[f"f{i}"])
-            st[f"dec{j}.blk.c1"] = nchw(b[f"rb{i}"]); bn(f"dec{j}.blk.bn1"); st[f"dec{j}.blk.bn1.out"] = nchw(b[f"d{i}"])
+            st[f"dec{j}.blk.c1"] = nchw(b[f"rb{i}"]); bn(f"dec{j}.blk.bn1")
+            if self.mode != 0:
+                extra(f"dec{j}")
+            if self.mode <= 1:
+                st[f"dec{j}.blk.bn{self.mode + 1}.out"] = nchw(b[f"d{i}"])
         return st
 
     def debug_tensors(self):
