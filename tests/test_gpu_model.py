@@ -305,3 +305,39 @@ def test_alternate_block_modes(mode):
         if not ok:
             bad.append((name, U.rel_l2(got, refg), U.max_abs(got, refg), scale))
     assert not bad, bad
+
+
+def test_without_batchnorm():
+    """BatchNorm=False (constructor option, u_net.py:367 `if BatchNorm:`): conv -> ReLU through the same kernels with
+    identity coefficients; forward and gradients against the oracle built the same way."""
+    g = torch.Generator().manual_seed(9)
+    om = O.UNetOracle(kernels=3, BatchNorm=False)
+    params = O.init_params(om.plan, seed=500)
+    for n, _, kind in om.plan:
+        if kind == "bias":
+            params[n] = 0.05 * torch.randn(params[n].shape, generator=g)
+    x = torch.rand(2, 144, 160, 2, generator=g); y = torch.rand(2, 144, 160, 2, generator=g)
+    emb = torch.randint(0, 2000, (2, 2, 16), generator=g, dtype=torch.int32)
+    mask = (torch.rand(2, 1440, generator=g) > 0.3).float() / 0.7
+    eng = UNetEngine(kernels=3, BatchNorm=False)
+    assert eng.trainable_names() == O.trainable_names(om.plan)
+    eng.load_state_dict(params)
+    out = eng.forward(x.cuda(), emb.cuda(), training=False).float().cpu()
+    ref = om.forward(params, x, emb, training=False)
+    assert U.max_abs(out, ref) < 1e-2 and U.rel_l2(out, ref) < 5e-3
+    st = O.new_opt_state(params, om.plan)
+    eng.forward(x.cuda(), emb.cuda(), training=True, dropout_mask=mask.cuda())
+    n = 2 * 144 * 160
+    eng.loss_and_grad(y.cuda(), 1.0 / n, 1.0 / n)
+    eng.backward(eng._buffers(2)["g_out"])
+    torch.cuda.synchronize()
+    oq = O.UNetOracle(kernels=3, BatchNorm=False, emulate_bf16=True)
+    oq.override = eng.forward_state()
+    _, grads, _ = O.train_step(oq, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    bad = []
+    for name in eng.trainable_names():
+        got, refg = eng.grad[name].cpu(), grads[name]
+        scale = float(refg.abs().max())
+        if not (U.rel_l2(got, refg) < 3e-2 or U.max_abs(got, refg) < 1e-7 + 2e-3 * scale):
+            bad.append((name, U.rel_l2(got, refg), U.max_abs(got, refg), scale))
+    assert not bad, bad

@@ -14,7 +14,7 @@ Deviations, all deliberate and visible:
   * `_save_parameters` also stores `kernels`. The reference omits it (u_net.py:180-187), so its own
     `UNet.load` rebuilds with `BatchNorm` shifted into the `kernels` slot -- a latent bug we do not copy.
   * all four block modes (0 convolutional_block_1 ... 3 residual_block_2) are wired on the device with
-    `BatchNorm=True`; every reference call site uses mode 0. `BatchNorm=False` raises NotImplementedError.
+    `BatchNorm=True` or `False`; every reference call site uses mode 0 with BatchNorm.
 """
 from __future__ import annotations
 

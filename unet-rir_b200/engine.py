@@ -117,8 +117,6 @@ class UNetEngine:
         if mode not in (0, 1, 2, 3):
             raise ValueError("mode must be 0 (convolutional_block_1), 1 (convolutional_block_2), 2 (residual_block_1) "
                              "or 3 (residual_block_2)  (u_net.py:280-287)")
-        if not BatchNorm:
-            raise NotImplementedError("BatchNorm=False is not wired in the CUDA engine")
         H, W, Cin = input_shape
         if H % 16 or W % 16:
             raise ValueError("input H and W must be multiples of 16 (four stride-2 stages)")
@@ -210,6 +208,9 @@ class UNetEngine:
         for b in bn_names:
             c = self.shapes[b + ".gamma"][0]
             self.bn_slot[b] = (o, 2 * c); o += 2 * c
+        # BatchNorm=False (u_net.py:367 `if BatchNorm:`): conv -> ReLU runs through the same kernels with identity
+        # coefficients (scale 1, shift 0, mean 0, rstd 1, gamma 1, zero reduction sums), one set per channel count
+        self._ident = {}
         # bias-gradient statistics emitted by dgrad epilogues (zeroed each backward)
         self.bstat_arena = torch.zeros(2 * 4 * (self.F0 * 16) * 12, dtype=torch.float32, device=dev)
         self.load_state_dict(PL.keras_init(self.plan, seed))
@@ -341,8 +342,21 @@ class UNetEngine:
         o, n = self.bn_slot[bn]
         return arena[o:o + n]
 
+    def _identity(self, c):
+        if c not in self._ident:
+            dev = self.device
+            one, zero = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+            self._ident[c] = {"ss": torch.cat([one, zero]), "mr": torch.cat([zero, one]), "gamma": one.clone(),
+                              "sums": torch.zeros(2 * c, device=dev)}
+        return self._ident[c]
+
     def _cbr_fwd(self, cname, bname, x, raw, out, k, training):
         """Conv2D(k, SAME) -> BatchNormalization -> ReLU  (convolutional_block_1, u_net.py:363-371)."""
+        if not self.BatchNorm:
+            self._conv_fprop(cname, x, raw, k, 1)
+            L.call("bn_relu_fwd", raw.ptr(), raw.ld, raw.coff, self._identity(raw.C)["ss"].data_ptr(), out.ptr(), out.ld,
+                   out.coff, raw.npix, raw.C, 1)
+            return
         stats = self._slot(self.stats_arena, bname) if training else None
         self._conv_fprop(cname, x, raw, k, 1, stats=stats)
         c = raw.C
@@ -362,6 +376,15 @@ class UNetEngine:
                raw.npix, c, 1)
 
     def _cbr_bwd(self, cname, bname, x, raw, g_out, g_raw, k, g_x=None, g_x_stats=None, accumulate=0):
+        if not self.BatchNorm:          # ReLU backward only: g_raw = g_out * (raw > 0); conv bias gradient = its pixel sum
+            idn = self._identity(raw.C)
+            L.call("bn_relu_bwd_apply", g_out.ptr(), g_out.ld, g_out.coff, raw.ptr(), raw.ld, raw.coff,
+                   idn["ss"].data_ptr(), idn["mr"].data_ptr(), idn["gamma"].data_ptr(), idn["sums"].data_ptr(),
+                   g_raw.ptr(), g_raw.ld, g_raw.coff, None, None, self.grad[cname + ".b"].data_ptr(), raw.npix, raw.C, 1)
+            self._conv_wgrad(cname, x, g_raw, k, 1)
+            if g_x is not None:
+                self._conv_dgrad(cname, g_raw, g_x, k, 1, stats=g_x_stats, accumulate=accumulate)
+            return
         ss, mr = self._slot(self.ss_arena, bname), self._slot(self.mr_arena, bname)
         sums = self._slot(self.sums_arena, bname)
         c = raw.C
@@ -636,6 +659,8 @@ class UNetEngine:
             return t.float().permute(0, 3, 1, 2).contiguous().cpu()
 
         def bn(bname):
+            if not self.BatchNorm:
+                return
             mr = self._slot(self.mr_arena, bname).float().cpu()
             c = mr.numel() // 2
             st[bname + ".mean"] = mr[:c].clone()
