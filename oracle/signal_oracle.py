@@ -147,6 +147,29 @@ def post_process(feature, des_shape=(129, 151), n_fft=N_FFT, win_length=WIN_LENG
     return istft(S, n_fft, win_length, hop_length)
 
 
+def griffinlim(S, n_iter=32, momentum=0.99, init_angles=None, rng=None, n_fft=N_FFT, win_length=WIN_LENGTH,
+               hop_length=HOP_LENGTH, pad_mode="constant"):
+    """librosa.griffinlim with its defaults (postprocess.py:130-131 passes only n_fft / win_length / hop_length):
+    fast Griffin-Lim, 32 iterations, momentum 0.99, random initial phases. S = magnitudes (n_bins, n_frames).
+    Third-party algorithm (librosa, unpinned version): restated from its published form --
+        angles_0 = exp(2 pi i U);  rebuilt_k = STFT(ISTFT(S * angles_k));
+        angles_{k+1} = normalise(rebuilt_k - momentum / (1 + momentum) * rebuilt_{k-1});  y = ISTFT(S * angles_n)."""
+    S = np.asarray(S, dtype=np.float64)
+    if init_angles is None:
+        rng = rng or np.random.default_rng()
+        init_angles = np.exp(2j * np.pi * rng.random(S.shape))
+    angles = np.asarray(init_angles, dtype=np.complex128)
+    rebuilt = np.zeros_like(angles)
+    length = hop_length * (S.shape[1] - 1)
+    for _ in range(n_iter):
+        tprev = rebuilt
+        inverse = istft(S * angles, n_fft, win_length, hop_length, length=length)
+        rebuilt = stft(inverse, n_fft, win_length, hop_length, pad_mode=pad_mode)
+        angles = rebuilt - (momentum / (1 + momentum)) * tprev
+        angles = angles / (np.abs(angles) + 1e-16)
+    return istft(S * angles, n_fft, win_length, hop_length, length=length)
+
+
 # -- metrics ---------------------------------------------------------------------------
 def generation_metrics(spec_true, spec_pred, wav_true, wav_pred):
     """The seven per-sample numbers of rir_generation.py:195-225."""

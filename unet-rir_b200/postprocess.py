@@ -4,7 +4,8 @@ polar-to-complex -> inverse STFT chain (:78-129) is ONE liburir kernel on the GP
   PostProcess(folder, algorithm=None).post_process(feature, vector, des_shape=(129,151), n_fft=256,
                                                    win_length=128, hop_length=64, sr=48000) -> waveform
   post_process_batch(features) -> (B, n_samples) CUDA tensor     (what rir_generation's loop batches into)
-`algorithm='gl'` (Griffin-Lim, :130-131) is a SURVEY 8(f) "next" item and raises NotImplementedError.
+`algorithm='gl'` (librosa.griffinlim, :130-131) is a batched GPU loop over the same STFT / iSTFT kernels
+(`griffinlim_batch`).
 Files are only written when `write_files=True` (the reference always writes, :73-74).
 """
 from __future__ import annotations
@@ -38,6 +39,51 @@ def post_process_batch(features, des_shape=(129, 151), n_fft=256, win_length=128
     return out
 
 
+def griffinlim_batch(amp, n_iter=32, momentum=0.99, init_angles=None, seed=None, n_fft=256, win_length=128,
+                     hop_length=64, padded=(144, 160)):
+    """librosa.griffinlim (fast Griffin-Lim: 32 iterations, momentum 0.99, random initial phases -- the defaults the
+    reference relies on, postprocess.py:130-131) for a batch of magnitude spectrograms on the GPU.
+
+    amp: (B, n_bins, n_frames) linear magnitudes (numpy or torch). Every iteration is one iSTFT launch, one STFT launch
+    (liburir kernels, un-normalised mode) and a few elementwise torch ops on (B, n_bins, n_frames) tensors.
+    init_angles: optional complex (B, n_bins, n_frames) unit phasors (parity tests inject them). -> (B, n_samples)."""
+    S = amp if isinstance(amp, torch.Tensor) else torch.as_tensor(np.asarray(amp), dtype=torch.float32)
+    S = S.to("cuda", torch.float32)
+    if S.dim() == 2:
+        S = S[None]
+    B, nb, nf = S.shape
+    n_samples = hop_length * (nf - 1)
+    Hp, Wp = max(padded[0], nb), max(padded[1], nf)
+    if init_angles is None:
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1)))
+        phase = 2 * np.pi * torch.rand(B, nb, nf, generator=gen, device="cuda")
+        angles = torch.polar(torch.ones_like(phase), phase)
+    else:
+        angles = torch.as_tensor(init_angles).to("cuda", torch.complex64)
+    d_inv = stft_desc(n_samples, n_fft, win_length, hop_length, (Hp, Wp), "constant", False, False)
+    spec = torch.zeros(B, Hp, Wp, 2, dtype=torch.float32, device="cuda")
+    spec[:, :nb, :nf, 0] = S
+    reb = torch.empty(B, Hp, Wp, 2, dtype=torch.float32, device="cuda")
+    wav = torch.empty(B, n_samples, dtype=torch.float32, device="cuda")
+    rebuilt = torch.zeros(B, nb, nf, dtype=torch.complex64, device="cuda")
+    c = momentum / (1.0 + momentum)
+
+    def inverse(ang):
+        spec[:, :nb, :nf, 1] = torch.angle(ang)
+        L.call("istft_from_ampphase", spec.data_ptr(), B, C.byref(d_inv), wav.data_ptr())
+
+    for _ in range(n_iter):
+        tprev = rebuilt
+        inverse(angles)
+        L.call("stft_ampphase", wav.data_ptr(), B, C.byref(d_inv), reb.data_ptr())
+        rebuilt = torch.polar(reb[:, :nb, :nf, 0], reb[:, :nb, :nf, 1])
+        angles = rebuilt - c * tprev
+        angles = angles / (angles.abs() + 1e-16)
+    inverse(angles)
+    return wav
+
+
 class PostProcess:
 
     def __init__(self, folder, algorithm=None, write_files=False):
@@ -52,8 +98,15 @@ class PostProcess:
 
     def post_process(self, feature, vector, des_shape=(129, 151),
                      n_fft=256, win_length=128, hop_length=64, sr=48000):
-        if self.algorithm == 'gl':
-            raise NotImplementedError("Griffin-Lim synthesis (postprocess.py:130-131) is not built yet")
+        if self.algorithm == 'gl':          # magnitudes only: un-pad, denormalise, Griffin-Lim phase retrieval
+            f = feature.detach().float().cpu().numpy() if isinstance(feature, torch.Tensor) else np.asarray(feature, dtype=np.float32)
+            a, p = self.padder.un_pad(f[:, :, 0], f[:, :, 1], des_shape)
+            a, _ = self.normalizer.denormalize(np.asarray(a, dtype=np.float32), np.asarray(p, dtype=np.float32))
+            self.waveform = griffinlim_batch(a[None], n_fft=n_fft, win_length=win_length, hop_length=hop_length)[0].cpu().numpy()
+            if self.write_files:
+                self.save_wav(sr, vector)
+                self.save_stft(f)
+            return self.waveform
         if isinstance(feature, torch.Tensor):
             feature_t = feature.detach()
         else:
