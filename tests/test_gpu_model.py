@@ -341,3 +341,30 @@ def test_without_batchnorm():
         if not (U.rel_l2(got, refg) < 3e-2 or U.max_abs(got, refg) < 1e-7 + 2e-3 * scale):
             bad.append((name, U.rel_l2(got, refg), U.max_abs(got, refg), scale))
     assert not bad, bad
+
+
+def test_long_rir_input_shape():
+    """BASELINE config 5 (long-RIR sweep): 0.4 s RIRs -> 301 frames -> input_shape (144, 304, 2). Ragged tiles at every
+    level (304 = 19 * 16, 19-wide bottleneck), Dense width 9 * 19 * 16 = 2736. Eval forward against the oracle and one
+    training step's losses; gradients of a few tensors against the oracle on the device's forward state."""
+    shape = (144, 304, 2)
+    om, params, x, y, emb, mask = _setup(B=2, kernels=3, seed=4, shape=shape)
+    eng = UNetEngine(input_shape=shape, kernels=3)
+    eng.load_state_dict(params)
+    out = eng.forward(x.cuda(), emb.cuda(), training=False).float().cpu()
+    ref = om.forward(params, x, emb, training=False)
+    assert U.max_abs(out, ref) < 1e-2 and U.rel_l2(out, ref) < 5e-3
+    st = O.new_opt_state(params, om.plan)
+    (loss, lp, ls), _, ref_out = O.train_step(om, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    eng.forward(x.cuda(), emb.cuda(), training=True, dropout_mask=mask.cuda())
+    n = 2 * shape[0] * shape[1]
+    losses = eng.loss_and_grad(y.cuda(), 1.0 / n, 1.0 / n)
+    assert abs(float(losses[0]) - float(loss)) < 3e-3 * float(loss)
+    eng.backward(eng._buffers(2)["g_out"])
+    torch.cuda.synchronize()
+    oq = O.UNetOracle(input_shape=shape, kernels=3, emulate_bf16=True)
+    oq.override = eng.forward_state()
+    _, grads, _ = O.train_step(oq, params, st, x, y, emb, 1e-3, dropout_mask=mask, apply=False)
+    for name in ("enc1.down.w", "enc2.down.w", "enc3.blk.c1.w", "enc5.blk.c1.w", "vec.dense.w", "vec.proj.w",
+                 "dec2.up.w", "dec3.fuse.w", "dec5.blk.c1.w", "head.w", "dec4.fuse_bn.gamma"):
+        assert U.rel_l2(eng.grad[name].cpu(), grads[name]) < 2.5e-2, (name, U.rel_l2(eng.grad[name].cpu(), grads[name]))

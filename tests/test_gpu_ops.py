@@ -227,3 +227,25 @@ def test_unsupported_shapes_fail_loudly():
         L.call("stft_ampphase", wav.data_ptr(), 1, C.byref(d), spec.data_ptr())
     with pytest.raises(L.UrirError):
         L.call("ampphase_loss", wav.data_ptr(), wav.data_ptr(), 3, 1.0, 1.0, 0, wav.data_ptr(), None, None, 0)
+
+
+def test_stft_long_rir():
+    """BASELINE config 5: 0.4 s at 48 kHz = 19200 samples -> (129, 301) -> padded (144, 304); STFT features and the
+    inverse against the numpy oracle."""
+    from unet_rir_b200.postprocess import post_process_batch
+    from unet_rir_b200.preprocess import preprocess_batch
+    rng = np.random.default_rng(2)
+    wav = SO.synthetic_rir(2, rng, length=19200)
+    spec = preprocess_batch(wav, padded=(144, 304)).cpu().numpy()
+    assert spec.shape == (2, 144, 304, 2)
+    for i in range(2):
+        w = wav[i] - wav[i].mean()
+        a, p = SO.normalize(*SO.extract(w))
+        assert a.shape == (129, 301)
+        assert np.abs(spec[i, :129, :301, 0] - a).max() < 2e-4
+        assert float(np.abs(spec[i, 129:]).max()) == 0.0 and float(np.abs(spec[i, :, 301:]).max()) == 0.0
+    back = post_process_batch(spec, des_shape=(129, 301)).cpu().numpy()
+    assert back.shape == (2, 19200)
+    for i in range(2):
+        w = wav[i] - wav[i].mean()
+        assert 20 * np.log10(np.linalg.norm(back[i][128:-128] - w[128:-128]) / np.linalg.norm(w[128:-128])) < -60
