@@ -346,9 +346,10 @@ def run_gpu(args, rank, world, local):
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, dt_cpu, threads = cpu_train_step_rate(8, 2, 1)
+        rate, dt_cpu, threads = cpu_train_step_rate(16, 18, 2)      # ~10-15 s of CPU work
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "oracle Trainer.step (fwd+loss+bwd+Adam, fp32) on batch 8, 2 timed steps after 1 warm-up"}
+               "sample": "oracle Trainer.step (fwd+loss+bwd+Adam, fp32, torch CPU on all host threads) on batches of 16 of "
+                         "the same synthetic workload, 18 timed steps after 2 warm-ups"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
