@@ -353,6 +353,8 @@ WGRAD_HALO_CASES = [
     (2, 24, 32, 128, 64),     # D4a class: two 64-channel x blocks (grid.y = 2)
     (5, 72, 80, 64, 64),      # many tiles per persistent CTA (ring wrap-around)
     (2, 20, 40, 32, 64),      # ragged tiles (H % 8 != 0, W % 16 != 0): TMA zero fill
+    (2, 36, 40, 128, 128),    # E3b / D3b class: dy in two 64-channel blocks (grid.z), two x blocks, ragged rows
+    (2, 36, 40, 256, 128),    # D3a class
 ]
 
 

@@ -40,6 +40,7 @@ constexpr int WH_SMEM_BUDGET = 200 * 1024;
 struct WhaloParams {
     int tiles_w, tiles_h, total_tiles;
     int C, Cc;                  // x channels in total / per CTA (32 or 64)
+    int K;                      // dy channels in total (a CTA handles KN of them: blockIdx.z)
     int n_mma;                  // MMAs per k-step: 1 (Cc = 32: 4 vertical slots) or 2 (Cc = 64: 2 slots each)
     int stages, stage_bytes, a_bytes, tx_bytes;
     int tmem_cols;
@@ -70,7 +71,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhaloMaps maps, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const int cblk = blockIdx.y;
+    const int cblk = blockIdx.y, kblk = blockIdx.z;
     const int STAGES = p.stages;
     const int n_iters = blockIdx.x < p.total_tiles ? (p.total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
@@ -100,7 +101,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhaloMaps maps, const __grid_cons
             mbar_wait(empty_bar + stage, phase ^ 1);
             mbar_expect_tx_elect(full_bar + stage, (uint32_t)p.tx_bytes);
             tma_load_4d_elect(&maps.a, full_bar + stage, dst, c0, h0 - 1, w0, n);
-            tma_load_4d_elect(&maps.b, full_bar + stage, dst + p.a_bytes, 0, h0, w0 - 1, n);
+            tma_load_4d_elect(&maps.b, full_bar + stage, dst + p.a_bytes, kblk * KN, h0, w0 - 1, n);
             dst += p.stage_bytes;
             if (++stage == STAGES) { stage = 0; phase ^= 1; dst = smem; }
         }
@@ -160,7 +161,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhaloMaps maps, const __grid_cons
                 const bool valid = dh < 3 && p.debug != 1;
                 {
                     const int tap = (valid ? dh : 0) * 3 + (2 - i);              // B atom i <-> horizontal tap 2 - i
-                    float* drow = p.dw + ((size_t)tap * p.C + cblk * p.Cc + c) * KN;
+                    float* drow = p.dw + ((size_t)tap * p.C + cblk * p.Cc + c) * p.K + kblk * KN;
 #pragma unroll
                     for (int c0 = 0; c0 < KN; c0 += 16) {
                         uint32_t r[16];
@@ -188,8 +189,10 @@ bool wgrad_halo_supported(const urir_conv_desc* d, bool forced) {
     if (d->P != d->H || d->Q != d->W) return false;      // ragged tiles: TMA zero fill contributes nothing
     if (d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16) return false;
     if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
-    if (!(d->C == 32 || d->C % 64 == 0) || !(d->K == 32 || d->K == 64)) return false;
+    if (!(d->C == 32 || d->C % 64 == 0) || !(d->K == 32 || d->K % 64 == 0)) return false;
     const long long tiles = (long long)d->N * cdiv(d->H, WH_TH) * cdiv(d->W, WH_TW);
+    // measured at 36x40 (960 ragged tiles, K = 128 in two blocks): 41 / 68 us vs 43 / 60 us for conv_wgrad_tc -- no gain,
+    // so AUTO keeps this kernel for the two wide levels only
     return forced || tiles >= 148 * 8;
 }
 
@@ -205,8 +208,8 @@ static int launch_wh(const WhaloMaps& maps, const WhaloParams& p, dim3 grid, int
 
 int conv_wgrad_halo(const urir_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
     WhaloMaps maps; WhaloParams p; memset(&p, 0, sizeof(p));
-    const int KN = d->K;
-    p.C = d->C; p.Cc = d->C == 32 ? 32 : 64;
+    const int KN = d->K == 32 ? 32 : 64;              // dy channels per CTA; grid.z covers the rest
+    p.C = d->C; p.K = d->K; p.Cc = d->C == 32 ? 32 : 64;
     p.n_mma = p.Cc == 32 ? 1 : 2;
     p.tiles_w = cdiv(d->W, WH_TW); p.tiles_h = cdiv(d->H, WH_TH); p.total_tiles = p.tiles_w * p.tiles_h * d->N;
     const int a_box = WH_PH * WH_TW * p.Cc * 2, b_box = WH_TH * WH_PW * KN * 2;
@@ -233,10 +236,10 @@ int conv_wgrad_halo(const urir_conv_desc* d, const void* x, const void* dy, floa
         if (rc) return rc;
     }
     if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->C * d->K, st));
-    const int n_cblk = d->C / p.Cc;
-    int gx = 148 / n_cblk; if (gx < 1) gx = 1;
+    const int n_cblk = d->C / p.Cc, n_kblk = d->K / KN;
+    int gx = 148 / (n_cblk * n_kblk); if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
-    dim3 grid(gx, n_cblk);
+    dim3 grid(gx, n_cblk, n_kblk);
     const int smem = p.stages * p.stage_bytes + 1024 + (2 * WH_MAX_STAGES + 2) * 8 + 16 + 1024;
     if (KN == 32) return launch_wh<32>(maps, p, grid, smem, st);
     if (KN == 64) return launch_wh<64>(maps, p, grid, smem, st);
