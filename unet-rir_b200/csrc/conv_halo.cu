@@ -302,17 +302,20 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 gout[i] = p.out + p.o_off + (long long)n * p.o_sn + (long long)hh * p.o_sh + (long long)ww * p.o_sw;
             }
             uint32_t pk[16];
-            // out += (accumulate): the previous contents of this lane's own pixel are fetched one 64-column phase
-            // ahead (before the accumulator barrier / during the previous phase), so the loads overlap the waits
+            // out += (accumulate): the previous contents are fetched in the SAME transposed layout the stores use (lane
+            // group of 4 = one pixel's 64 contiguous bytes per 32-channel group), one 64-column phase ahead (before
+            // the accumulator barrier / during the previous phase), and added after the transpose. The sum is formed
+            // in fp32 from the bf16-rounded result and the old bf16 value (one extra rounding, well inside the bf16
+            // tolerance); per-lane loads of the lane's own pixel cost half-empty sectors and measured 2x slower.
             constexpr int PH_COLS = BLOCK_N < 64 ? BLOCK_N : 64;
-            uint4 oldv[ACC ? PH_COLS / 8 : 1];
-            const __nv_bfloat16* orow = p.out + p.o_off + (long long)n * p.o_sn + (long long)h * p.o_sh + (long long)w * p.o_sw;
+            uint4 oldv[ACC ? PH_COLS / 8 : 1];                     // [32-channel group of the phase][pixel i of the lane group]
             auto load_old = [&](int ph) {
 #pragma unroll
-                for (int q = 0; q < PH_COLS / 8; ++q) {
-                    const int col = ph * PH_COLS + q * 8;
-                    oldv[q] = valid ? *reinterpret_cast<const uint4*>(orow + p.grp_off[n_tile * (BLOCK_N / 32) + (col >> 5)] + (col & 31))
-                                    : make_uint4(0, 0, 0, 0);
+                for (int gi = 0; gi < PH_COLS / 32; ++gi) {
+                    const int c32 = p.grp_off[n_tile * (BLOCK_N / 32) + ph * (PH_COLS / 32) + gi] + (lane & 3) * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        oldv[gi * 4 + i] = gvalid[i] ? *reinterpret_cast<const uint4*>(gout[i] + c32) : make_uint4(0, 0, 0, 0);
                 }
             };
             if (ACC) load_old(0);
@@ -329,19 +332,6 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
 #pragma unroll
                 for (int c = 0; c < PH_COLS / 32; ++c) tmem_ld32(lane_addr + ph * PH_COLS + c * 32, r + c * 32);
                 tmem_ld_wait();
-                if (ACC) {
-#pragma unroll
-                    for (int q = 0; q < PH_COLS / 8; ++q) {
-                        const uint32_t ow[4] = {oldv[q].x, oldv[q].y, oldv[q].z, oldv[q].w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = unpack_bf16x2(ow[j]);
-                            r[q * 8 + 2 * j] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * j]) + f.x);
-                            r[q * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * j + 1]) + f.y);
-                        }
-                    }
-                    if (ph + 1 < BLOCK_N / PH_COLS) load_old(ph + 1);
-                }
                 if (tre && ph == 0) p.trace[it * 8 + 6] = clock64();
 #pragma unroll
                 for (int bb = 0; bb < PH_COLS / 16; ++bb) {
@@ -361,13 +351,22 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                         // 32 channels = four 16-byte chunks per pixel. Transpose them across the 4 lanes of a group so
                         // that store i writes chunk (lane & 3) of pixel (group, i): 64 contiguous bytes per lane group
                         // (full sectors) instead of four scattered 16-byte pieces.
-                        if (p.debug == 6) {      // experiment: each lane stores its own pixel's 64 bytes, no transpose
-                            __nv_bfloat16* own = const_cast<__nv_bfloat16*>(orow) + p.grp_off[n_tile * (BLOCK_N / 32) + (b >> 1)];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                if (valid) *reinterpret_cast<uint4*>(own + 8 * i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                        } else {
+                        // (storing each lane's own 64 bytes without the transpose was measured 15-20 % slower at 64 channels)
+                        {
                         hl_transpose4(pk, lane);
+                        if (ACC) {
+                            const int gi = bb >> 1;                // 32-channel group within the phase
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t ow[4] = {oldv[gi * 4 + i].x, oldv[gi * 4 + i].y, oldv[gi * 4 + i].z, oldv[gi * 4 + i].w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 a = unpack_bf16x2(pk[4 * i + j]), o = unpack_bf16x2(ow[j]);
+                                    pk[4 * i + j] = pack_bf16x2(a.x + o.x, a.y + o.y);
+                                }
+                            }
+                            if (gi == PH_COLS / 32 - 1 && ph + 1 < BLOCK_N / PH_COLS) load_old(ph + 1);
+                        }
                         const int c32 = p.grp_off[n_tile * (BLOCK_N / 32) + (b >> 1)] + (lane & 3) * 8;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
