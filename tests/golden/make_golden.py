@@ -66,6 +66,25 @@ def main():
         trace.append({"train": t, "val": v, "improve": bool(imp), "stop": bool(stop), "count": es.count,
                       "val_min": mc.val_loss_min, "train_min": mc.train_loss_min, "saved": fm.saved})
     json.dump({"patience": 3, "trace": trace}, open(os.path.join(OUT, "callbacks_golden.json"), "w"), indent=1)
+    # rooms.py: the 16-int embedding of every (room, zone, array type, loudspeaker, microphone) combination sampled
+    rm = lift(os.path.join(REF, "rooms.py"), {"Quadrilateral", "Room", "UTSRoom", "return_room"})
+    rooms = {"AnechoicRoom": (490, 722, 490, 722, 90, 90, 90, 90, 529, [245, 361], 45),
+             "HemiAnechoicRoom": (490, 722, 490, 722, 90, 90, 90, 90, 529, [245, 361], 52),
+             "SmallMeetingRoom": (355, 410, 401, 378, 96, 90, 85, 88, 300, [175.5, 205], 497),
+             "MediumMeetingRoom": (736, 520, 650, 434.5, 81, 92, 98, 89, 300, [368, 217.5], 659),
+             "LargeMeetingRoom": (994, 923, 1087, 1022, 81.4, 105, 81.3, 92.3, 300, [497, 486.25], 1281),
+             "ShoeBoxRoom": (600, 1175, 600, 1175, 90, 90, 90, 90, 300, [300, 881.25], 667)}      # dataset.py:84-89
+    cases = []
+    for name, args in rooms.items():
+        room = rm["UTSRoom"](*args)
+        for zone in "ABCDE":
+            for array in ("Planar", "Circular"):
+                for l in (1, 7, 22, 60):
+                    for m in (1, 8, 9, 30, 31, 64):
+                        ch = [name, zone, array, str(l), str(m)]
+                        cases.append({"characteristics": ch, "embedding": [float(v) for v in room.return_embedding(ch)]})
+    json.dump({"rooms": {k: list(v[:9]) + [v[9], v[10]] for k, v in rooms.items()}, "cases": cases},
+              open(os.path.join(OUT, "rooms_golden.json"), "w"))
     print("wrote", sorted(os.listdir(OUT)))
 
 

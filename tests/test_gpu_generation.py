@@ -101,3 +101,46 @@ def test_griffin_lim_matches_oracle_and_recovers_the_magnitudes():
     assert w.shape == (9600,) and np.isfinite(w).all()
     sc = np.linalg.norm(np.abs(SO.stft(w)) - S[0]) / np.linalg.norm(S[0])
     assert sc < 0.4, sc
+
+
+def test_dataset_directory_walk(tmp_path):
+    """Dataset(dir) (dataset.py:121-182) on a small tree of synthetic wav files: filename parsing, room / array filters,
+    room-geometry embeddings, per-room in/out pairing with the seed-500 shuffle, GPU-preprocessed spectrograms equal
+    to the oracle's per-file pipeline, and the DataGenerator batch contract on top."""
+    from scipy.io import wavfile
+    from unet_rir_b200 import rooms as R
+    from unet_rir_b200.datageneratorv2 import DataGenerator
+    from unet_rir_b200.dataset import Dataset
+    rng = np.random.default_rng(5)
+    root = tmp_path / "room_impulse"
+    files = {}
+    for room in ("HemiAnechoicRoom", "SmallMeetingRoom", "AnechoicRoom"):
+        for zone in ("ZoneA", "ZoneC"):
+            for arr in ("PlanarMicrophoneArray", "CircularMicrophoneArray"):
+                d = root / room / zone / arr
+                d.mkdir(parents=True)
+                for l, m in ((3, 5), (7, 12), (22, 64)):
+                    w = SO.synthetic_rir(1, rng, length=12000)[0] * 0.1
+                    name = f"{room}_{zone}_{arr}_L{l}_M{m}.wav"
+                    wavfile.write(str(d / name), 48000, w)
+                    files[(room, zone[-1], arr.replace("MicrophoneArray", ""), str(l), str(m))] = w
+    ds = Dataset(str(tmp_path), "room_impulse", room=["All"], array=["PlanarMicrophoneArray"], room_characteristics=True)
+    assert len(ds) == 2 * 2 * 3                                   # anechoic room and circular arrays filtered out
+    assert ds.amp.shape == (12, 144, 160) and ds.emb.shape == (12, 16) and ds.emb.dtype == np.int32
+    chars = ds.return_characteristics()
+    for i in range(len(ds)):
+        ch = chars[i]
+        assert ch[2] == "Planar" and ch[0] in ("HemiAnechoicRoom", "SmallMeetingRoom")
+        assert list(ds.emb[i]) == [int(v) for v in R.uts_room(ch[0]).return_embedding(ch)]
+        w = files[tuple(ch)][:9600]
+        a, p = SO.preprocess(w)[..., 0], SO.preprocess(w)[..., 1]
+        assert np.abs(ds.amp[i] - a).max() < 2e-4
+        # pairs stay inside one room; index_out is a permutation of index_in
+        assert chars[ds.index_in[i]][0] == chars[ds.index_out[i]][0]
+    assert sorted(ds.index_in) == sorted(ds.index_out) == list(range(12))
+    assert ds.index_in[:6] == [i for i in range(12) if chars[i][0] == "HemiAnechoicRoom"]
+    gen = DataGenerator(ds, batch_size=4, partition="all", shuffle=False)
+    spec_in, emb, spec_out = gen[0]
+    assert spec_in.shape == (4, 144, 160, 2) and emb.shape == (4, 2, 16) and spec_out.dtype == np.float32
+    dbg = Dataset(str(tmp_path), "room_impulse", room=["All"], array=["PlanarMicrophoneArray"], debugging=True)
+    assert len(dbg) == 3

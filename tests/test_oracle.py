@@ -179,3 +179,17 @@ def test_oracle_train_step_decreases_loss():
         (loss, _, _), _, _ = O.train_step(om, params, st, x, y, emb, 1e-2)
         first = first if first is not None else float(loss)
     assert float(loss) < first
+
+
+def test_room_embeddings_match_reference_rooms_py():
+    """unet_rir_b200.rooms against the reference's own rooms.py, executed from its source by tests/golden/make_golden.py:
+    1440 (room, zone, array type, loudspeaker, microphone) combinations, every one of the 16 entries equal."""
+    import json
+    from unet_rir_b200 import rooms as R
+    d = json.load(open(os.path.join(GOLD, "rooms_golden.json")))
+    assert len(d["cases"]) == 1440
+    for c in d["cases"]:
+        got = R.uts_room(c["characteristics"][0]).return_embedding(c["characteristics"])
+        assert [float(v) for v in got] == c["embedding"], c
+    assert R.return_room([994]) == "Large" and R.return_room([1]) is None
+    assert max(max(c["embedding"]) for c in d["cases"]) < 2000          # fits Embedding(2000, 256), u_net.py:257
