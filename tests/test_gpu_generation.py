@@ -144,3 +144,24 @@ def test_dataset_directory_walk(tmp_path):
     assert spec_in.shape == (4, 144, 160, 2) and emb.shape == (4, 2, 16) and spec_out.dtype == np.float32
     dbg = Dataset(str(tmp_path), "room_impulse", room=["All"], array=["PlanarMicrophoneArray"], debugging=True)
     assert len(dbg) == 3
+
+
+def test_eval_forward_graph_replay_equals_eager():
+    """The inference forward is captured per batch size on its second call and replayed afterwards: the eager call, the
+    capture call and replays on NEW inputs and after a weight change all equal an engine with the graph disabled."""
+    from unet_rir_b200.engine import UNetEngine
+    g = torch.Generator().manual_seed(2)
+    a, b = UNetEngine(kernels=3), UNetEngine(kernels=3)
+    b.eval_cuda_graph = False
+    b.load_state_dict(a.state_dict())
+    for step in range(4):
+        x = torch.rand(4, 144, 160, 2, generator=g).cuda()
+        emb = torch.randint(0, 2000, (4, 2, 16), generator=g, dtype=torch.int32).cuda()
+        if step == 3:                                   # weights change between replays
+            sd = a.state_dict()
+            sd["head.b"] = sd["head.b"] + 0.5
+            a.load_state_dict(sd); b.load_state_dict(sd)
+        ya = a.forward(x, emb, training=False).clone()
+        yb = b.forward(x, emb, training=False).clone()
+        assert torch.equal(ya, yb), step
+    assert not isinstance(a._eval_graphs[4], str)

@@ -139,6 +139,8 @@ class UNetEngine:
         self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.side = torch.cuda.Stream(device=self.device)
         self.prefetcher = InputPrefetcher(self)
+        self.eval_cuda_graph = os.environ.get("URIR_NO_EVAL_GRAPH", "0") != "1"
+        self._eval_graphs = {}
         self.overlap_wgrad = os.environ.get("URIR_NO_OVERLAP", "0") != "1"
         self._side_dirty = False
 
@@ -465,9 +467,29 @@ class UNetEngine:
         otherwise a fresh counter-based mask is drawn when training and dropout is True.
         """
         b = self.stage(spec_in, emb)
+        B = spec_in.shape[0]
+        if not training and self.eval_cuda_graph:
+            # inference (rir_generation.py:160-170 runs batches of 4): ~60 small launches, host-bound when issued one
+            # by one, so the eval forward of each batch size is captured once (after a warm-up call) and replayed.
+            # Weights, BN moving statistics and I/O all live in fixed buffers, so the graph stays valid across updates.
+            st = self._eval_graphs.get(B)
+            if st is None:
+                self._forward_body(B, False)
+                self._eval_graphs[B] = "warm"
+            elif st == "warm":
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._forward_body(B, False)
+                self._eval_graphs[B] = g
+                g.replay()
+            else:
+                st.replay()
+            self._last_B = B
+            return b["out"]
         if training and dropout_mask is not None:
             b["mask"].copy_(dropout_mask)
-        return self._forward_body(spec_in.shape[0], training, dropout, injected_mask=dropout_mask is not None)
+        return self._forward_body(B, training, dropout, injected_mask=dropout_mask is not None)
 
     def _forward_body(self, B, training, dropout=True, injected_mask=False):
         b = self._buffers(B)
