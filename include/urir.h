@@ -48,6 +48,7 @@ extern "C" {
 
 #define URIR_ACT_NONE    0
 #define URIR_ACT_SIGMOID 1
+#define URIR_ACT_RELU    2    /* inference: BatchNorm folded into weights / bias, ReLU in the epilogue */
 
 /* One strided convolution y[N,P,Q,K] = conv(x[N,H,W,C], w[R,S,C,K]) (+bias), TF "SAME"
  * geometry given explicitly. Conv2DTranspose layers are described by the strided conv they are
@@ -122,6 +123,12 @@ int urir_conv_path(const urir_conv_desc* d, int op);
 /* fp32 HWIO master weights -> the two bf16 operand layouts. */
 int urir_weight_prep(const float* w_hwio, void* w_ck, void* w_kc, int taps, int C, int K,
                      void* stream);
+/* Inference-mode BatchNormalization folded into the convolution that precedes it (one launch for all layers):
+ * table_dev = n_entries x {w fp32 HWIO ptr, scale_shift fp32 [2K] ptr (urir_bn_finalize, inference mode), bias fp32 [K]
+ * ptr, out w_kc bf16 [tap][K][C] ptr, out bias fp32 [K] ptr, taps, C, K} (int64, device memory):
+ *   w_kc[t][k][c] = bf16(w[t][c][k] * scale[k]),  bias_out[k] = bias[k] * scale[k] + shift[k].
+ * A fprop with these operands and act = URIR_ACT_RELU equals conv -> BN (moving statistics) -> ReLU. */
+int urir_weight_fold_bn_batched(const int64_t* table_dev, int n_entries, void* stream);
 /* the same for every kernel of a model in ONE launch: table_dev = n_entries x {w fp32 ptr, w_ck ptr,
  * w_kc ptr, taps, C, K} as int64 in device memory (refresh after each optimiser step). */
 int urir_weight_prep_batched(const int64_t* table_dev, int n_entries, void* stream);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liburir.so")
 
 F32, BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_HALO = 0, 1, 2, 3
-ACT_NONE, ACT_SIGMOID = 0, 1
+ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
 
 
 class UrirError(RuntimeError):
@@ -50,6 +50,7 @@ _PROTOS = {
     "urir_weight_prep_up2": (_i, [_vp, _vp, _i, _i, _vp]),
     "urir_conv2d_dgrad_up2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_weight_prep_batched": (_i, [_vp, _i, _vp]),
+    "urir_weight_fold_bn_batched": (_i, [_vp, _i, _vp]),
     "urir_channel_sum": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp]),
     "urir_bn_finalize": (_i, [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _i, _vp]),
     "urir_bn_relu_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _ll, _i, _i, _vp]),

@@ -32,6 +32,7 @@ int conv_dgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, co
 int conv_wgrad_simt_dispatch(const urir_conv_desc*, const void*, const void*, float*, cudaStream_t);
 int weight_prep(const float*, void*, void*, int, int, int, cudaStream_t);
 int weight_prep_batched(const long long*, int, cudaStream_t);
+int weight_fold_bn_batched(const long long*, int, cudaStream_t);
 bool igemm_fprop_supported(const urir_conv_desc*);
 bool igemm_dgrad_supported(const urir_conv_desc*);
 int conv_fprop_igemm(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
@@ -204,6 +205,11 @@ int urir_weight_prep(const float* w, void* w_ck, void* w_kc, int taps, int C, in
 int urir_weight_prep_batched(const int64_t* table_dev, int n_entries, void* stream) {
     URIR_CHECK_ARG(table_dev && n_entries > 0, "weight_prep_batched: bad args");
     return weight_prep_batched(reinterpret_cast<const long long*>(table_dev), n_entries, (cudaStream_t)stream);
+}
+
+int urir_weight_fold_bn_batched(const int64_t* table_dev, int n_entries, void* stream) {
+    URIR_CHECK_ARG(table_dev && n_entries > 0, "weight_fold_bn_batched: bad args");
+    return weight_fold_bn_batched(reinterpret_cast<const long long*>(table_dev), n_entries, (cudaStream_t)stream);
 }
 
 int urir_channel_sum(const void* x, int dtype, long long npix, int C, int ld, int coff, float* out, void* stream) {

@@ -110,7 +110,7 @@ __device__ __forceinline__ void hl_transpose4(uint32_t (&pk)[16], int lane) {
 __device__ __forceinline__ int hl_col_of_lane(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
 
 // NG = epilogue groups (2: warps 0-3, 8-11; 4: additionally warps 12-15, 16-19 -- 640 threads, <= 96 registers)
-template <int BLOCK_N, int BLOCK_K, bool ACC, int NG>
+template <int BLOCK_N, int BLOCK_K, bool ACC, int NG, bool RELU>
 __global__ void __launch_bounds__(NG == 4 ? 640 : 384, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
     constexpr uint32_t SWZ = (BLOCK_K == 64) ? SWZ_128B : SWZ_64B;
@@ -343,6 +343,10 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                         v[4 * j4] = __uint_as_float(r[bb * 16 + 4 * j4]) + bs.x; v[4 * j4 + 1] = __uint_as_float(r[bb * 16 + 4 * j4 + 1]) + bs.y;
                         v[4 * j4 + 2] = __uint_as_float(r[bb * 16 + 4 * j4 + 2]) + bs.z; v[4 * j4 + 3] = __uint_as_float(r[bb * 16 + 4 * j4 + 3]) + bs.w;
                     }
+                    if (RELU) {              // inference: BatchNorm folded into weights / bias (urir_weight_fold_bn_batched)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
                     pk[(b & 1) * 8 + 0] = pack_bf16x2(v[0], v[1]); pk[(b & 1) * 8 + 1] = pack_bf16x2(v[2], v[3]);
                     pk[(b & 1) * 8 + 2] = pack_bf16x2(v[4], v[5]); pk[(b & 1) * 8 + 3] = pack_bf16x2(v[6], v[7]);
                     pk[(b & 1) * 8 + 4] = pack_bf16x2(v[8], v[9]); pk[(b & 1) * 8 + 5] = pack_bf16x2(v[10], v[11]);
@@ -448,7 +452,7 @@ static void halo_fix_stages(HaloParams& p) {
 // op 0: fprop (GEMM-K = C, GEMM-N = K), op 1: dgrad (GEMM-K = K, GEMM-N = C)
 bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
     if (d->stride != 1 || d->P != d->H || d->Q != d->W || d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16) return false;
-    if (d->act != URIR_ACT_NONE || d->accumulate) return false;
+    if ((d->act != URIR_ACT_NONE && !(d->act == URIR_ACT_RELU && op == 0)) || d->accumulate) return false;
     if (d->R > 6 || d->S > 6 || d->R * d->S > 36) return false;
     if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
     const int kg = op == 0 ? d->C : d->K, ng = op == 0 ? d->K : d->C;
@@ -461,10 +465,10 @@ bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
     return forced || tiles >= 148 * 4;
 }
 
-template <int BN, int BK, bool ACC = false, int NG = 2>
+template <int BN, int BK, bool ACC = false, int NG = 2, bool RELU = false>
 static int launch_halo(const HaloMaps& maps, const HaloParams& p, int n_tiles, int smem, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = conv_halo_kernel<BN, BK, ACC, NG>;
+    auto kern = conv_halo_kernel<BN, BK, ACC, NG, RELU>;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BUDGET + 4096)); attr_set = true; }
     int gx = 148 / n_tiles; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
@@ -526,6 +530,11 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     }
     const int smem = p.w_bytes + p.stages * p.a_stage_bytes + ((HL_MAX_FSETS + 1) * HL_MAX_STAGES + 9) * 8 + 16 + 3 * BN * 4 + 1024;
     const int n_tiles = ng / BN;
+    if (d->act == URIR_ACT_RELU) {
+#define URIR_HLR(BN_, BK_) if (BN == BN_ && BK == BK_) return launch_halo<BN_, BK_, false, 2, true>(maps, p, n_tiles, smem, st);
+        URIR_HLR(32, 32) URIR_HLR(32, 64) URIR_HLR(64, 32) URIR_HLR(64, 64) URIR_HLR(128, 32) URIR_HLR(128, 64)
+#undef URIR_HLR
+    }
     { static int ng4 = -1; if (ng4 < 0) { const char* e = getenv("URIR_HALO_NG4"); ng4 = (e && e[0] == '1') ? 1 : 0; }
       if (ng4 && BN == 32 && BK == 32) return launch_halo<32, 32, false, 4>(maps, p, n_tiles, smem, st);
       if (ng4 && BN == 32 && BK == 64) return launch_halo<32, 64, false, 4>(maps, p, n_tiles, smem, st); }

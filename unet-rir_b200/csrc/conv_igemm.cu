@@ -44,7 +44,7 @@ struct IgemmParams {
     void* out;                      // bf16, or fp32 when out_f32
     int n_total;                    // Ngemm (valid output channels; may be < gridDim.y * BLOCK_N)
     int out_f32;                    // 1: fp32 output (head), columns stored individually
-    int act;                        // URIR_ACT_SIGMOID only with out_f32
+    int act;                        // URIR_ACT_SIGMOID only with out_f32; URIR_ACT_RELU (bf16 output, inference)
     IgemmTap taps[36];
 };
 
@@ -194,6 +194,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
                 for (int j = 0; j < 16; ++j) {
                     v[j] = __uint_as_float(r[j]);
                     if (p.bias && c0 + j < n_left) v[j] += __ldg(p.bias + n_tile * BLOCK_N + c0 + j);
+                    if (p.act == URIR_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
                     if (!valid || c0 + j >= n_left) v[j] = 0.f;
                 }
                 if (valid) {
@@ -345,7 +346,7 @@ bool igemm_fprop_supported(const urir_conv_desc* d) {
     if (d->x_dtype != URIR_BF16 || d->x_ld % 8 || d->x_coff % 8 || d->C % 8 || d->R * d->S > 36) return false;
     if (d->stride != 1 && d->stride != 2) return false;
     if (d->y_dtype == URIR_BF16)
-        return d->K % 16 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 && d->act == URIR_ACT_NONE;
+        return d->K % 16 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0 && (d->act == URIR_ACT_NONE || d->act == URIR_ACT_RELU);
     return d->K <= 32;                       // fp32 output (the sigmoid head): scalar stores, one masked N tile
 }
 bool igemm_dgrad_supported(const urir_conv_desc* d) {

@@ -90,6 +90,7 @@ conv_fprop_simt(ConvP p, const TX* __restrict__ x, const __nv_bfloat16* __restri
         }
         if (live) {
             if (p.act == URIR_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
+            if (p.act == URIR_ACT_RELU) v = fmaxf(v, 0.f);
             if (p.accumulate) v += ld_as_f32(yp + i);
             st_from_f32(yp + i, v);
         }
@@ -340,6 +341,64 @@ __global__ void __launch_bounds__(256) weight_prep_batched_kernel(const long lon
 int weight_prep_batched(const long long* table_dev, int n_entries, cudaStream_t st) {
     URIR_CHECK_ARG(n_entries <= WP_MAX_ENTRIES, "weight_prep_batched: at most %d entries", WP_MAX_ENTRIES);
     weight_prep_batched_kernel<<<148 * 8, 256, 0, st>>>(table_dev, n_entries);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
+// Inference-mode BatchNorm folded into the preceding convolution, all layers in one launch:
+// table[e] = {w fp32, scale_shift fp32 [2K], bias fp32 [K], out w_kc bf16 [tap][K][C], out bias fp32 [K], taps, C, K}.
+__global__ void __launch_bounds__(256) weight_fold_bn_batched_kernel(const long long* __restrict__ table, int n_entries) {
+    __shared__ long long tile_start[WP_MAX_ENTRIES + 1];
+    __shared__ float tile[64][65];
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        for (int e = 0; e < n_entries; ++e) {
+            tile_start[e] = acc;
+            const long long* t = table + 8 * e;
+            acc += t[5] * ((t[6] + 63) / 64) * ((t[7] + 63) / 64);
+        }
+        tile_start[n_entries] = acc;
+    }
+    __syncthreads();
+    const long long total = tile_start[n_entries];
+    int e = 0;
+    for (long long tl = blockIdx.x; tl < total; tl += gridDim.x) {
+        while (tl >= tile_start[e + 1]) ++e;
+        const long long* t = table + 8 * e;
+        const float* w = reinterpret_cast<const float*>(t[0]);
+        const float* ss = reinterpret_cast<const float*>(t[1]);
+        const float* bias = reinterpret_cast<const float*>(t[2]);
+        __nv_bfloat16* w_kc = reinterpret_cast<__nv_bfloat16*>(t[3]);
+        float* bias_out = reinterpret_cast<float*>(t[4]);
+        const int C = (int)t[6], K = (int)t[7];
+        const int tiles_k = (K + 63) / 64, tiles_c = (C + 63) / 64;
+        long long r = tl - tile_start[e];
+        const int tk = (int)(r % tiles_k); r /= tiles_k;
+        const int tc = (int)(r % tiles_c); const long long tap = r / tiles_c;
+        const int c0 = tc * 64, k0 = tk * 64;
+        const size_t base = (size_t)tap * C * K;
+        const int col = threadIdx.x & 63, row0 = threadIdx.x >> 6;
+        if (tap == 0 && tc == 0 && threadIdx.x < 64 && k0 + threadIdx.x < K) {        // the layer's folded bias, once
+            const int k = k0 + threadIdx.x;
+            bias_out[k] = fmaf(bias ? bias[k] : 0.f, ss[k], ss[K + k]);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = row0; rr < 64; rr += 4) {
+            const int c = c0 + rr, k = k0 + col;
+            tile[rr][col] = (c < C && k < K) ? w[base + (size_t)c * K + k] * ss[k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = row0; rr < 64; rr += 4) {
+            const int k = k0 + rr, c = c0 + col;
+            if (k < K && c < C) w_kc[base + (size_t)k * C + c] = f2bf(tile[col][rr]);
+        }
+    }
+}
+int weight_fold_bn_batched(const long long* table_dev, int n_entries, cudaStream_t st) {
+    URIR_CHECK_ARG(n_entries <= WP_MAX_ENTRIES, "weight_fold_bn_batched: at most %d entries", WP_MAX_ENTRIES);
+    weight_fold_bn_batched_kernel<<<148 * 8, 256, 0, st>>>(table_dev, n_entries);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }

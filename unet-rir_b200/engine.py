@@ -141,6 +141,7 @@ class UNetEngine:
         self.prefetcher = InputPrefetcher(self)
         self.eval_cuda_graph = os.environ.get("URIR_NO_EVAL_GRAPH", "0") != "1"
         self._eval_graphs = {}
+        self.fold_bn_eval = self.BatchNorm and os.environ.get("URIR_NO_BN_FOLD", "0") != "1"
         self.overlap_wgrad = os.environ.get("URIR_NO_OVERLAP", "0") != "1"
         self._side_dirty = False
 
@@ -300,11 +301,13 @@ class UNetEngine:
         w_ck, w_kc = self.wops[name + ".w"]
         return w_ck.data_ptr(), w_kc.data_ptr()
 
-    def _conv_fprop(self, name, x, y, k, stride, stats=None, act=L.ACT_NONE, accumulate=0, bias=True):
+    def _conv_fprop(self, name, x, y, k, stride, stats=None, act=L.ACT_NONE, accumulate=0, bias=True, w_kc=None,
+                    bias_ptr=None):
         d = self._desc(x, y, k, stride, act, accumulate)
-        w_ck, w_kc = self._w(name)
-        L.call("conv2d_fprop", C.byref(d), x.ptr(), w_ck, w_kc,
-               self.param[name + ".b"].data_ptr() if bias else None, y.ptr(),
+        w_ck, w_kc_default = self._w(name)
+        if bias_ptr is None:
+            bias_ptr = self.param[name + ".b"].data_ptr() if bias else None
+        L.call("conv2d_fprop", C.byref(d), x.ptr(), w_ck, w_kc_default if w_kc is None else w_kc, bias_ptr, y.ptr(),
                None if stats is None else stats.data_ptr())
 
     def _conv_dgrad(self, name, dy, dx, k, stride, stats=None, accumulate=0, bias=False):
@@ -344,6 +347,39 @@ class UNetEngine:
         o, n = self.bn_slot[bn]
         return arena[o:o + n]
 
+    # ------------------------------------------------------------------ inference: BatchNorm folded into the convs
+    @staticmethod
+    def _conv_of_bn(bname):
+        return bname.replace("fuse_bn", "fuse") if bname.endswith("fuse_bn") else bname.replace(".bn", ".c")
+
+    def _fold_setup(self):
+        """bf16 [tap][K][C] copies of every BN-followed kernel with the inference-mode BN scale folded in, folded fp32
+        biases, and the device table urir_weight_fold_bn_batched reads."""
+        dev = self.device
+        self.wfold, self.bfold, rows = {}, {}, []
+        for bname in self.bn_slot:
+            cname = self._conv_of_bn(bname)
+            kh, kw, cin, cout = self.shapes[cname + ".w"]
+            self.wfold[cname] = torch.empty(kh * kw, cout, cin, dtype=torch.bfloat16, device=dev)
+            self.bfold[cname] = torch.empty(cout, dtype=torch.float32, device=dev)
+            rows.append([self.param[cname + ".w"].data_ptr(), self._slot(self.ss_arena, bname).data_ptr(),
+                         self.param[cname + ".b"].data_ptr(), self.wfold[cname].data_ptr(), self.bfold[cname].data_ptr(),
+                         kh * kw, cin, cout])
+        self._fold_table = torch.tensor(rows, dtype=torch.int64, device=dev)
+
+    def _fold_refresh(self):
+        """moving statistics -> scale / shift of every BN layer, then ONE launch folds them into kernels and biases
+        (re-done on every inference forward: the weights or statistics may have changed since the last one)."""
+        if getattr(self, "_fold_table", None) is None:
+            self._fold_setup()
+        for bname in self.bn_slot:
+            c = self.shapes[bname + ".gamma"][0]
+            ss, mr = self._slot(self.ss_arena, bname), self._slot(self.mr_arena, bname)
+            L.call("bn_finalize", None, 1.0, self.param[bname + ".gamma"].data_ptr(), self.param[bname + ".beta"].data_ptr(),
+                   self.state[bname + ".moving_mean"].data_ptr(), self.state[bname + ".moving_var"].data_ptr(),
+                   PL.BN_MOMENTUM, PL.BN_EPS, self.bn_unbiased, ss.data_ptr(), mr.data_ptr(), c)
+        L.call("weight_fold_bn_batched", self._fold_table.data_ptr(), self._fold_table.shape[0])
+
     def _identity(self, c):
         if c not in self._ident:
             dev = self.device
@@ -359,6 +395,14 @@ class UNetEngine:
             L.call("bn_relu_fwd", raw.ptr(), raw.ld, raw.coff, self._identity(raw.C)["ss"].data_ptr(), out.ptr(), out.ld,
                    out.coff, raw.npix, raw.C, 1)
             return
+        if not training and self.fold_bn_eval:
+            d = self._desc(x, out, k, 1, L.ACT_RELU)
+            if L.load().urir_conv_path(C.byref(d), 0) == 1:          # tensor-core kernels carry the ReLU epilogue
+                # conv -> BN(moving statistics) -> ReLU as ONE kernel: scale folded into the bf16 kernel, shift into the
+                # bias (_fold_refresh), ReLU in the epilogue, output straight into `out` -- no raw tensor, no BN pass
+                self._conv_fprop(cname, x, out, k, 1, act=L.ACT_RELU, w_kc=self.wfold[cname].data_ptr(),
+                                 bias_ptr=self.bfold[cname].data_ptr())
+                return
         stats = self._slot(self.stats_arena, bname) if training else None
         self._conv_fprop(cname, x, raw, k, 1, stats=stats)
         c = raw.C
@@ -496,6 +540,8 @@ class UNetEngine:
         k = self.kernels
         if training:
             self.stats_arena.zero_()
+        elif self.fold_bn_eval:
+            self._fold_refresh()
         # ---- encoder (encoding_block, u_net.py:265-289)
         x = View(b["x_in"])
         for i in range(1, 6):
