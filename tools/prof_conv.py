@@ -42,6 +42,15 @@ CASES = {
     "wgrad_s2_l4": ("wgrad", 64, 18, 20, 256, 512, 3, 2),
     "wgrad_s2_l3": ("wgrad", 64, 36, 40, 128, 256, 3, 2),
     "wgrad_s2_full": ("wgrad", 64, 144, 160, 32, 64, 3, 2),
+    "dgrad_l4": ("dgrad", 64, 18, 20, 256, 256, 3, 1),
+    "fprop_l4a": ("fprop", 64, 18, 20, 512, 256, 3, 1),
+    "dgrad_l4a": ("dgrad", 64, 18, 20, 512, 256, 3, 1),
+    "dgrad_l3a": ("dgrad", 64, 36, 40, 256, 128, 3, 1),
+    "dgrad_deep": ("dgrad", 64, 9, 10, 512, 512, 3, 1),
+    "fprop_s2_l4": ("fprop", 64, 36, 40, 128, 256, 3, 2),
+    "fprop_s2_l5": ("fprop", 64, 18, 20, 256, 512, 3, 2),
+    "dgrad_s2_l4": ("dgrad", 64, 36, 40, 128, 256, 3, 2),
+    "dgrad_s2_l5": ("dgrad", 64, 18, 20, 256, 512, 3, 2),
     "fprop_s2": ("fprop", 64, 144, 160, 32, 64, 3, 2),
 }
 
@@ -67,7 +76,9 @@ def run(which, reps=int(os.environ.get("PROF_REPS", "3"))):
         t_end = __import__("time").time() + 0.3
         while __import__("time").time() < t_end:
             (a @ a); torch.cuda.synchronize()
-    w_up2 = torch.randn(4, 4 * Cc, K, device="cuda").to(torch.bfloat16) if (op == "dgrad" and s == 2 and k == 3) else None
+    w_up2 = None
+    if op == "dgrad" and s == 2 and k == 3 and L.load().urir_conv_path(C.byref(d), 3) == 1:
+        w_up2 = torch.randn(4, 4 * Cc, K, device="cuda").to(torch.bfloat16)
     def launch():
         if w_up2 is not None and not os.environ.get("PROF_NO_UP2"):
             L.call("conv2d_dgrad_up2", C.byref(d), dy.data_ptr(), w_up2.data_ptr(), None, x.data_ptr())
