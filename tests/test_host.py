@@ -209,3 +209,20 @@ def test_rt60_and_edc_of_known_decays():
     e = RG.edc_db(torch.as_tensor(h)).numpy()
     assert np.allclose(e[:, 0], 0.0) and (np.diff(e, axis=1) <= 1e-12).all()
     assert np.abs(e[0] - SO.edc_db(h[0])).max() < 1e-9
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's keys,
+    produced without a GPU and without touching /root/reference."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "unet_train_samples_per_sec" and line["unit"] == "samples/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"]
