@@ -233,7 +233,9 @@ def test_stem_wgrad_on_tensor_cores_and_batched_weight_prep():
     U.run_wgrad(d, x8, dyg, dw)
     assert U.rel_l2(dw, gw) < F32_TOL
     # batched weight prep == per-kernel weight prep
-    ws = [torch.randn(3, 3, 32, 64, generator=g).cuda(), torch.randn(6, 6, 32, 2, generator=g).cuda()]
+    # vector path (K % 4 == 0, even C) with full and ragged 64x64 tiles, and the scalar path (K = 2, K = 6, odd C)
+    ws = [torch.randn(*s, generator=g).cuda() for s in
+          [(3, 3, 32, 64), (6, 6, 32, 2), (3, 3, 2, 32), (1, 1, 96, 100), (2, 1, 70, 132), (1, 1, 33, 64), (1, 2, 64, 6)]]
     outs, rows = [], []
     for wt in ws:
         kh, kw, c, k = wt.shape

@@ -317,6 +317,44 @@ __global__ void __launch_bounds__(256) weight_prep_batched_kernel(const long lon
         const size_t base = (size_t)tap * C * K;
         const int col = threadIdx.x & 63, row0 = threadIdx.x >> 6;
         __syncthreads();                                   // previous tile's transposed reads are done
+        const bool vec = (K % 4 == 0) && (C % 2 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
+                         (!w_ck || (reinterpret_cast<uintptr_t>(w_ck) & 7) == 0) &&
+                         (!w_kc || (reinterpret_cast<uintptr_t>(w_kc) & 3) == 0);
+        if (vec) {
+            // 16-byte loads (four per thread, all in flight), 8-byte w_ck stores, 4-byte transposed w_kc stores
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = threadIdx.x + 256 * j, c = c0 + (idx >> 4), k = k0 + (idx & 15) * 4;
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < C && k < K) v[j] = *reinterpret_cast<const float4*>(w + base + (size_t)c * K + k);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = threadIdx.x + 256 * j, rr = idx >> 4, cc = (idx & 15) * 4;
+                const int c = c0 + rr, k = k0 + cc;
+                if (w_ck && c < C && k < K) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[j].x, v[j].y), hi = __floats2bfloat162_rn(v[j].z, v[j].w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(w_ck + base + (size_t)c * K + k) = pk;
+                }
+                tile[rr][cc] = v[j].x; tile[rr][cc + 1] = v[j].y; tile[rr][cc + 2] = v[j].z; tile[rr][cc + 3] = v[j].w;
+            }
+            __syncthreads();
+            if (w_kc) {
+                const int c2 = (threadIdx.x & 31) * 2, r0 = threadIdx.x >> 5;
+#pragma unroll
+                for (int rr = r0; rr < 64; rr += 8) {
+                    const int k = k0 + rr, c = c0 + c2;
+                    if (k < K && c < C)
+                        *reinterpret_cast<__nv_bfloat162*>(w_kc + base + (size_t)k * C + c) =
+                            __floats2bfloat162_rn(tile[c2][rr], tile[c2 + 1][rr]);
+                }
+            }
+            continue;
+        }
 #pragma unroll 4
         for (int rr = row0; rr < 64; rr += 4) {
             const int c = c0 + rr, k = k0 + col;

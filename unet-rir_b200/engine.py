@@ -18,6 +18,7 @@ Data layout in HBM (all NHWC):
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from collections import OrderedDict
@@ -329,14 +330,20 @@ class UNetEngine:
         captured into the CUDA graph as a parallel branch."""
         # accumulate = 1: the flat gradient buffer was zeroed once at the start of backward (no per-layer memset)
         d = self._desc(x, dy, k, stride, accumulate=1)
+        with self._side_branch():
+            L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
+
+    @contextlib.contextmanager
+    def _side_branch(self):
+        """Work that only feeds the optimiser: ordered after everything issued so far on the current stream,
+        run on the side stream (or inline when overlap is off), joined later by _join_side()."""
         if not self.overlap_wgrad:
-            L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
+            yield
             return
-        main = torch.cuda.current_stream()
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            L.call("conv2d_wgrad", C.byref(d), x.ptr(), dy.ptr(), self.grad[name + ".w"].data_ptr())
+        self.side.wait_stream(torch.cuda.current_stream())
         self._side_dirty = True
+        with torch.cuda.stream(self.side):
+            yield
 
     def _join_side(self):
         if self._side_dirty:
@@ -542,6 +549,26 @@ class UNetEngine:
             self.stats_arena.zero_()
         elif self.fold_bn_eval:
             self._fold_refresh()
+        # ---- vector block (u_net.py:253-263): independent of the encoder, so it runs on the side stream
+        main = torch.cuda.current_stream()
+        fork = self.overlap_wgrad
+        if fork:
+            self.side.wait_stream(main)
+        with torch.cuda.stream(self.side if fork else main):
+            L.call("embedding_fwd", b["emb"].data_ptr(), self.param["vec.emb"].data_ptr(), b["embflat"].data_ptr(),
+                   B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+            mask = None
+            if training:
+                if injected_mask:
+                    mask = b["mask"]
+                elif dropout:
+                    L.call("dropout_mask", b["mask"].data_ptr(), b["mask"].numel(), PL.DROPOUT_RATE,
+                           self.dropout_seed, self.step_dev.data_ptr())
+                    mask = b["mask"]
+            self._fwd_mask = mask
+            L.call("dense_fwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
+                   self.param["vec.dense.b"].data_ptr(), L.ptr(mask), b["v16"].data_ptr(), B, self.T * PL.EMB_DIM,
+                   self.dense_n)
         # ---- encoder (encoding_block, u_net.py:265-289)
         x = View(b["x_in"])
         for i in range(1, 6):
@@ -551,21 +578,9 @@ class UNetEngine:
             self._conv_fprop(f"enc{i}.down", x, t, k, 1 if i == 1 else 2)
             self._blk_fwd(f"enc{i}", f"enc{i}.blk", t, r, e, training)
             x = e
-        # ---- vector block + Add (u_net.py:253-263, 229)
-        L.call("embedding_fwd", b["emb"].data_ptr(), self.param["vec.emb"].data_ptr(), b["embflat"].data_ptr(),
-               B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
-        mask = None
-        if training:
-            if injected_mask:
-                mask = b["mask"]
-            elif dropout:
-                L.call("dropout_mask", b["mask"].data_ptr(), b["mask"].numel(), PL.DROPOUT_RATE,
-                       self.dropout_seed, self.step_dev.data_ptr())
-                mask = b["mask"]
-        self._fwd_mask = mask
-        L.call("dense_fwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
-               self.param["vec.dense.b"].data_ptr(), L.ptr(mask), b["v16"].data_ptr(), B, self.T * PL.EMB_DIM,
-               self.dense_n)
+        # ---- Add (u_net.py:229): z = e5 + proj(v16)
+        if fork:
+            main.wait_stream(self.side)
         z = View(b["z"])
         self._conv_fprop("vec.proj", View(b["v16"]), z, 1, 1, accumulate=1)
         # ---- decoder (decoding_block, u_net.py:291-321)
@@ -620,7 +635,8 @@ class UNetEngine:
             d1 = View(b["d1"])
             # head
             self._conv_wgrad("head", d1, g_out, 6, 1)
-            L.call("channel_sum", g_out.ptr(), L.F32, g_out.npix, 2, 2, 0, self.grad["head.b"].data_ptr())
+            with self._side_branch():
+                L.call("channel_sum", g_out.ptr(), L.F32, g_out.npix, 2, 2, 0, self.grad["head.b"].data_ptr())
             self._conv_dgrad("head", g_out, View(b["g_d1"]), 6, 1)
             # decoder, top (level 1) down to level 4
             for j in (5, 4, 3, 2):
@@ -649,12 +665,14 @@ class UNetEngine:
             g_z = View(b["g_z"])
             self._conv_wgrad("vec.proj", View(b["v16"]), g_z, 1, 1)
             self._conv_dgrad("vec.proj", g_z, View(b["g_v16"]), 1, 1)
-            L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
-                   b["g_v16"].data_ptr(), L.ptr(self._fwd_mask), b["g_v16_eff"].data_ptr(),
-                   self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
-                   b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
-            L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), L.BF16,
-                   self.grad["vec.emb"].data_ptr(), B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+            # the Dense / Embedding gradients only feed the optimiser: side stream, next to the encoder's dgrad chain
+            with self._side_branch():
+                L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
+                       b["g_v16"].data_ptr(), L.ptr(self._fwd_mask), b["g_v16_eff"].data_ptr(),
+                       self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
+                       b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
+                L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), L.BF16,
+                       self.grad["vec.emb"].data_ptr(), B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
             if segment == 1:
                 self._join_side()
         if segment in (None, 2):
