@@ -712,17 +712,25 @@ l2_reg_batched_kernel(const long long* __restrict__ table, float coef, float* __
     const float* p = reinterpret_cast<const float*>(e[0]);
     float* g = reinterpret_cast<float*>(e[1]);
     const long long n = e[2];
+    const float c2 = 2.f * coef;
     float s = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+    const long long n4 = vec ? (n >> 2) : 0;
+    for (long long i = tid; i < n4; i += nth) {            // 16-byte accesses
+        const float4 v = reinterpret_cast<const float4*>(p)[i];
+        float4 gg = reinterpret_cast<float4*>(g)[i];
+        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+        gg.x = fmaf(c2, v.x, gg.x); gg.y = fmaf(c2, v.y, gg.y); gg.z = fmaf(c2, v.z, gg.z); gg.w = fmaf(c2, v.w, gg.w);
+        reinterpret_cast<float4*>(g)[i] = gg;
+    }
+    for (long long i = (n4 << 2) + tid; i < n; i += nth) {
         const float v = p[i];
         s = fmaf(v, v, s);
-        g[i] = fmaf(2.f * coef, v, g[i]);
+        g[i] = fmaf(c2, v, g[i]);
     }
-    __shared__ float r[8];
     s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) { float a = 0.f; for (int i = 0; i < 8; ++i) a += r[i]; atomicAdd(out, a * coef); }
+    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(out, s * coef);
 }
 
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long n8) {
@@ -782,7 +790,7 @@ int sumsq(const float* x, long long n, float scale, float* out, int accumulate, 
 }
 int l2_reg_batched(const long long* table_dev, int n_entries, float coef, float* out, cudaStream_t st) {
     URIR_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
-    l2_reg_batched_kernel<<<dim3(64, n_entries), 256, 0, st>>>(table_dev, coef, out);
+    l2_reg_batched_kernel<<<dim3(148 * 2, n_entries), 256, 0, st>>>(table_dev, coef, out);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }

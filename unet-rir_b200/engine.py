@@ -618,9 +618,10 @@ class UNetEngine:
         o, n = slots[key]
         return self.bstat_arena[o:o + n]
 
-    def _backward_body(self, B, segment=None):
+    def _backward_body(self, B, segment=None, dense_dw=True):
         """segment: None = everything; 0 = head + decoder, 1 = bottleneck / vector block, 2 = encoder
-        (the order gradients become final, used for bucketed all-reduce overlap)."""
+        (the order gradients become final, used for bucketed all-reduce overlap). dense_dw=False leaves the Dense
+        kernel / bias gradients to dense_grad_from_gathered (data-parallel: gather operands, not gradients)."""
         b = self._buffers(B)
         k = self.kernels
         if segment in (None, 0):
@@ -669,7 +670,8 @@ class UNetEngine:
             with self._side_branch():
                 L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
                        b["g_v16"].data_ptr(), L.ptr(self._fwd_mask), b["g_v16_eff"].data_ptr(),
-                       self.grad["vec.dense.w"].data_ptr(), self.grad["vec.dense.b"].data_ptr(),
+                       self.grad["vec.dense.w"].data_ptr() if dense_dw else None,
+                       self.grad["vec.dense.b"].data_ptr() if dense_dw else None,
                        b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
                 L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), L.BF16,
                        self.grad["vec.emb"].data_ptr(), B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
@@ -697,6 +699,21 @@ class UNetEngine:
                 else:
                     self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
             self._join_side()
+
+    def dense_operands(self, B):
+        """(x, dy) of the Dense layer's kernel gradient dw = x^T dy after backward segment 1: the flattened
+        embeddings [B, T*EMB_DIM] and the (dropout-masked) output gradient [B, dense_n], both bf16."""
+        b = self._buffers(B)
+        return b["embflat"], (b["g_v16_eff"] if self._fwd_mask is not None else b["g_v16"])
+
+    def dense_grad_from_gathered(self, x_all, dy_all):
+        """Dense kernel and bias gradients of the GLOBAL batch from the all-gathered operands
+        (rows = world * B): sum_r x_r^T dy_r == [x_1; ..; x_R]^T [dy_1; ..; dy_R]. 1.2 MB of operands per replica
+        cross the NVLinks instead of a 47 MB fp32 gradient."""
+        rows = x_all.shape[0]
+        L.call("dense_bwd", x_all.data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
+               dy_all.data_ptr(), None, None, self.grad["vec.dense.w"].data_ptr(),
+               self.grad["vec.dense.b"].data_ptr(), None, rows, self.T * PL.EMB_DIM, self.dense_n)
 
     # ------------------------------------------------------------------ loss + optimiser
     def loss_and_grad(self, y_true, w_amp, w_ph, need_grad=True):

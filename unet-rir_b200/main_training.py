@@ -11,8 +11,10 @@ What is kept exactly:
   * Adam lr 5e-7 with lr*0.9^(epoch/80) from epoch 80 (:43, :342-344).
 What changes: the all-reduce is NCCL over NVLink through torch.distributed, issued per gradient
 bucket from a side stream as soon as the backward segment that produces the bucket has been
-enqueued (decoder+head, then bottleneck, then encoder -- reverse layer order), so the 84 MB of
-gradient traffic overlaps the remaining backward kernels. Each segment is a CUDA graph.
+enqueued (decoder+head, then bottleneck, then encoder -- reverse layer order), so the gradient traffic
+overlaps the remaining backward kernels. Each segment is a CUDA graph. The Dense layer's kernel gradient (47 of
+the 84 MB) can instead be formed from all-gathered operands (1.2 MB per replica; URIR_DP_GATHER_DENSE=1): same
+result, 56 % less NVLink traffic, but no faster on NVSwitch, so the plain all-reduce stays the default.
 """
 from __future__ import annotations
 
@@ -86,6 +88,14 @@ class DistributedTrainer:
         self._graphs = None
         self._calls = 0
         self.overlap = os.environ.get("URIR_DP_OVERLAP", "1") != "0"
+        # Dense layer (56 % of all parameters): all-gather its two small operands and form the global-batch kernel
+        # gradient locally instead of all-reducing 47 MB of fp32 gradient (see engine.dense_grad_from_gathered)
+        # (opt-in: measured equal to the plain all-reduce on NVSwitch at 2 and 8 GPUs, profiles/r01_layer_roofline.txt)
+        self.gather_dense = self.world > 1 and self.overlap and os.environ.get("URIR_DP_GATHER_DENSE", "0") == "1"
+        o = self.eng.offsets
+        self._o_dense = o["vec.dense.w"][0]
+        self._o_after_dense = o["vec.dense.b"][0] + o["vec.dense.b"][1]
+        self._gathered = None
         self.eng.set_lr(lr)
 
     # loss weights: w_amp * sum sq err + w_ph * sum (1 - cos)
@@ -108,7 +118,7 @@ class DistributedTrainer:
         e._backward_body(B, segment=0)
 
     def _seg_bottleneck(self, B):
-        self.eng._backward_body(B, segment=1)
+        self.eng._backward_body(B, segment=1, dense_dw=not self.gather_dense)
 
     def _seg_encoder(self, B):
         self.eng._backward_body(B, segment=2)
@@ -147,8 +157,34 @@ class DistributedTrainer:
                 s(B)
             if i < 3 and self.world > 1 and self.overlap:
                 lo, hi = self.buckets[i]
-                works.append(dist.all_reduce(self.eng.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                if not self.gather_dense:
+                    works.append(dist.all_reduce(self.eng.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                elif i == 0:
+                    works.append(dist.all_reduce(self.eng.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                elif i == 1:
+                    # bottleneck bucket = [embedding | Dense kernel, bias | projection]: gather the Dense operands,
+                    # reduce the projection now; the embedding table rides with the (adjacent) encoder bucket
+                    gathers = self._gather_dense_operands(B)
+                    works.append(dist.all_reduce(self.eng.G[self._o_after_dense:hi], op=dist.ReduceOp.SUM, async_op=True))
+                else:
+                    # Dense kernel gradient of the global batch on the side stream, beside the encoder's backward
+                    e = self.eng
+                    with torch.cuda.stream(e.side):
+                        for w in gathers:
+                            w.wait()
+                        e.dense_grad_from_gathered(*self._gathered)
+                    works.append(dist.all_reduce(e.G[0:self._o_dense], op=dist.ReduceOp.SUM, async_op=True))
+            if i == 2 and self.gather_dense:
+                torch.cuda.current_stream().wait_stream(self.eng.side)
         self._calls += 1
+
+    def _gather_dense_operands(self, B):
+        x, dy = self.eng.dense_operands(B)
+        if self._gathered is None or self._gathered[0].shape[0] != self.world * B:
+            self._gathered = (torch.empty(self.world * B, x.shape[1], dtype=x.dtype, device=x.device),
+                              torch.empty(self.world * B, dy.shape[1], dtype=dy.dtype, device=dy.device))
+        return [dist.all_gather_into_tensor(self._gathered[0], x.view(B, -1), async_op=True),
+                dist.all_gather_into_tensor(self._gathered[1], dy.view(B, -1), async_op=True)]
 
     def prefetch(self, spec_in, emb, spec_out):
         """Start the host -> device copy of the next shard on a copy stream (same argument order as train_step)."""
