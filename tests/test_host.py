@@ -176,6 +176,15 @@ if rank == 0:
     err = float((flat - ref).norm() / ref.norm())
     full = flat_grads(x, y, emb, B, 1)[0]                                   # different BN statistics: must differ
     print("DP_ERR", err, float((flat - full).norm() / full.norm()))
+# URIR_DP_GATHER_DENSE: a Dense kernel gradient summed over replicas == the product of the all-gathered operands
+gr = torch.Generator().manual_seed(100 + rank)
+xr, dyr = torch.randn(4, 24, generator=gr), torch.randn(4, 10, generator=gr)
+summed = xr.t() @ dyr
+dist.all_reduce(summed, op=dist.ReduceOp.SUM)
+xa, dya = [torch.empty(4 * world, t.shape[1]) for t in (xr, dyr)]
+dist.all_gather_into_tensor(xa, xr); dist.all_gather_into_tensor(dya, dyr)
+if rank == 0:
+    print("GATHER_ERR", float((xa.t() @ dya - summed).norm() / summed.norm()))
 dist.destroy_process_group()
 '''
 
@@ -191,6 +200,8 @@ def test_data_parallel_arithmetic_world2_gloo(tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith("DP_ERR")][0].split()
     assert float(line[1]) < 1e-5            # bucketed all-reduce == sum of per-replica gradients
     assert float(line[2]) > 1e-3            # and is NOT the full-batch-BN gradient (BN is per replica)
+    gather = [l for l in out.stdout.splitlines() if l.startswith("GATHER_ERR")][0].split()
+    assert float(gather[1]) < 1e-6          # gathered-operand Dense gradient == all-reduced Dense gradient
 
 
 def test_rt60_and_edc_of_known_decays():
