@@ -40,6 +40,7 @@ struct ThinParams {
     const __nv_bfloat16* w_ck; const float* bias;
     __nv_bfloat16* out; int out_ld, out_coff;
     float* dw;
+    unsigned long long mag_w, mag_h;   // ceil(2^40 / tiles_w), ceil(2^40 / tiles_h): exact division of tile indices < 2^20
     short toff[TH_MAX_TAPS];    // patch pixel index offset of tap t
 };
 
@@ -48,23 +49,36 @@ __device__ __forceinline__ int thin_widx(const ThinParams& p, int tap, int ct, i
     return p.thin_is_x ? (tap * 2 + ct) * p.CW_total + cw : (tap * p.CW_total + cw) * 2 + ct;
 }
 
+// (runtime integer divisions were a quarter of this kernel's instructions: tile indices are < 2^20, so
+// q = (tile * ceil(2^40 / d)) >> 40 is exact)
 __device__ __forceinline__ void thin_tile_coords(const ThinParams& p, int tile, int& n, int& h0, int& w0) {
-    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-    const int th = tile % p.tiles_h; n = tile / p.tiles_h;
+    const unsigned q1 = (unsigned)(((unsigned long long)(unsigned)tile * p.mag_w) >> 40);      // tile / tiles_w
+    const int tw = tile - (int)q1 * p.tiles_w;
+    const unsigned q2 = (unsigned)(((unsigned long long)q1 * p.mag_h) >> 40);                  // ... / tiles_h
+    const int th = (int)q1 - (int)q2 * p.tiles_h;
+    n = (int)q2;
     h0 = th * TH_BH; w0 = tw * TH_BW;
 }
 
-// this thread's (up to 3) entries of the halo patch of `tile`, zero outside the image (SAME padding)
-__device__ __forceinline__ void thin_load_patch(const ThinParams& p, int tile, float2 (&pr)[3]) {
-    int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+// this thread's (up to 3) patch entries as (row << 16 | column), -1 beyond the patch: tile independent, computed once
+__device__ __forceinline__ void thin_patch_coords(const ThinParams& p, int (&pyx)[3]) {
     const int npatch = p.PH * p.PW;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int i = threadIdx.x + 128 * q;
+        const int py = i / p.PW, px = i - py * p.PW;
+        pyx[q] = i < npatch ? ((py << 16) | px) : -1;
+    }
+}
+
+// this thread's (up to 3) entries of the halo patch of `tile`, zero outside the image (SAME padding)
+__device__ __forceinline__ void thin_load_patch(const ThinParams& p, int tile, const int (&pyx)[3], float2 (&pr)[3]) {
+    int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
         pr[q] = make_float2(0.f, 0.f);
-        if (i < npatch) {
-            const int py = i / p.PW, px = i - py * p.PW;
-            const int gh = h0 + p.oh0 + py, gw = w0 + p.ow0 + px;
+        if (pyx[q] >= 0) {
+            const int gh = h0 + p.oh0 + (pyx[q] >> 16), gw = w0 + p.ow0 + (pyx[q] & 0xffff);
             if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W)
                 pr[q] = __ldg(reinterpret_cast<const float2*>(p.thin + ((size_t)(n * p.H + gh) * p.W + gw) * p.thin_ld + p.thin_coff));
         }
@@ -77,8 +91,31 @@ __device__ __forceinline__ void thin_store_patch(const ThinParams& p, float2* pa
 }
 
 // im2col row of pixel `m` (= threadIdx.x) -> 16-byte chunks c = 0 .. nchunks-1 of the swizzled tile
+// KSZ = 3 / 6: square kernel of that size with compile-time tap offsets (FLIP: the mirrored taps of an input gradient),
+// so every tap is one shared-memory load with an immediate offset; KSZ = 0: any geometry through p.toff / p.ntaps
+template <int KSZ, bool FLIP>
 __device__ __forceinline__ void thin_build_row(const ThinParams& p, const float2* patch, uint8_t* sA) {
     const int m = threadIdx.x;
+    if constexpr (KSZ > 0) {
+        constexpr int NT = KSZ * KSZ, PW = TH_BW + KSZ - 1, NCH = 2 * ((2 * NT + 15) / 16);
+        const float2* src = patch + (m / TH_BW) * PW + (m % TH_BW);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            uint32_t wd[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int tap = 4 * c + e;
+                wd[e] = 0u;
+                if (tap < NT) {
+                    const int r = tap / KSZ, sx = tap % KSZ;
+                    const float2 v = src[FLIP ? (KSZ - 1 - r) * PW + (KSZ - 1 - sx) : r * PW + sx];
+                    wd[e] = pack_bf16x2(v.x, v.y);
+                }
+            }
+            *reinterpret_cast<uint4*>(sA + (c >> 3) * TH_ATOM + m * 128 + (((c & 7) ^ (m & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+        return;
+    }
     const int base = (m / TH_BW) * p.PW + (m % TH_BW);
 #pragma unroll
     for (int c = 0; c < TH_MAX_TAPS / 4; ++c) {
@@ -104,6 +141,7 @@ __device__ __forceinline__ void thin_build_row(const ThinParams& p, const float2
 constexpr int TG_B_ATOM = 32 * 128;
 constexpr int TG_SMEM = 2 * TH_ATOM + 2 * TG_B_ATOM + TH_PATCH_MAX * 8 + 64 + 1024;
 
+template <int KSZ, bool FLIP>
 __global__ void __launch_bounds__(128)
 thin_gemm_kernel(const __grid_constant__ ThinParams p) {
     constexpr uint32_t IDESC = make_idesc_bf16(128, 32, 0, 0);
@@ -148,14 +186,15 @@ thin_gemm_kernel(const __grid_constant__ ThinParams p) {
     for (int j = 0; j < 32; ++j) bias_v[j] = p.bias ? __ldg(p.bias + n0 + j) : 0.f;
 
     float2 pr[3];
+    int pyx[3]; thin_patch_coords(p, pyx);
     int tile = blockIdx.x;
-    if (tile < p.total_tiles) thin_load_patch(p, tile, pr);
+    if (tile < p.total_tiles) thin_load_patch(p, tile, pyx, pr);
     for (int it = 0; tile < p.total_tiles; ++it, tile += gridDim.x) {
         thin_store_patch(p, patch, pr);
         __syncthreads();
-        thin_build_row(p, patch, sA);
+        thin_build_row<KSZ, FLIP>(p, patch, sA);
         const int next = tile + gridDim.x;
-        if (next < p.total_tiles) thin_load_patch(p, next, pr);      // in flight across the MMA and the epilogue
+        if (next < p.total_tiles) thin_load_patch(p, next, pyx, pr);      // in flight across the MMA and the epilogue
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
@@ -205,6 +244,7 @@ thin_gemm_kernel(const __grid_constant__ ThinParams p) {
 constexpr int TW_A_STAGE = 2 * TH_ATOM, TW_B_STAGE = 128 * 64;
 constexpr int TW_SMEM = 2 * TW_A_STAGE + 2 * TW_B_STAGE + TH_PATCH_MAX * 8 + 128 + 1024;
 
+template <int KSZ, bool FLIP>
 __global__ void __launch_bounds__(128)
 thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_constant__ ThinParams p) {
     constexpr uint32_t IDESC = make_idesc_bf16(128, 32, 1, 1);
@@ -248,9 +288,10 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
     const uint32_t b_lo0 = ((uint32_t)(TW_B_STAGE >> 4) << 16) | (smem_u32(sB) >> 4);
 
     float2 pr[3];
+    int pyx[3]; thin_patch_coords(p, pyx);
     int tile = blockIdx.x;
     int n_iters = 0;
-    if (tile < p.total_tiles) thin_load_patch(p, tile, pr);
+    if (tile < p.total_tiles) thin_load_patch(p, tile, pyx, pr);
     for (int it = 0; tile < p.total_tiles; ++it, tile += gridDim.x) {
         const int s = it & 1;
         if (it >= 2) mbar_wait(bar_mma + s, ((it >> 1) - 1) & 1);       // the MMAs that read stage s are done
@@ -261,9 +302,9 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
         }
         thin_store_patch(p, patch, pr);
         __syncthreads();
-        thin_build_row(p, patch, sA + s * a_stage);
+        thin_build_row<KSZ, FLIP>(p, patch, sA + s * a_stage);
         const int next = tile + gridDim.x;
-        if (next < p.total_tiles) thin_load_patch(p, next, pr);
+        if (next < p.total_tiles) thin_load_patch(p, next, pyx, pr);
         fence_proxy_async();
         __syncthreads();
         if (warp == 0) {
@@ -310,7 +351,8 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
 // ---------------------------------------------------------------------------------------------
 static bool thin_geometry_ok(const urir_conv_desc* d) {
     return d->stride == 1 && d->P == d->H && d->Q == d->W && d->W % TH_BW == 0 && d->H % TH_BH == 0 &&
-           d->R * d->S <= 36 && d->R <= 6 && d->S <= 6;
+           d->R * d->S <= 36 && d->R <= 6 && d->S <= 6 &&
+           (long long)d->N * (d->W / TH_BW) * (d->H / TH_BH) < (1 << 20);       // thin_tile_coords' exact-division range
 }
 // op: 0 fprop (thin = x), 1 dgrad (thin = dy), 2 wgrad (either)
 bool thin_supported(const urir_conv_desc* d, int op) {
@@ -331,6 +373,7 @@ static void thin_fill(ThinParams& p, const urir_conv_desc* d, bool thin_is_x) {
     p.PH = TH_BH + d->R - 1; p.PW = TH_BW + d->S - 1;
     p.tiles_w = d->W / TH_BW; p.tiles_h = d->H / TH_BH; p.total_tiles = p.tiles_w * p.tiles_h * d->N;
     p.KS = (2 * p.ntaps + 15) / 16; p.nchunks = 2 * p.KS;
+    p.mag_w = ((1ull << 40) + p.tiles_w - 1) / p.tiles_w; p.mag_h = ((1ull << 40) + p.tiles_h - 1) / p.tiles_h;
     p.thin_is_x = thin_is_x ? 1 : 0;
     p.CW_total = thin_is_x ? d->K : d->C;
     if (thin_is_x) { p.oh0 = -d->pad_top; p.ow0 = -d->pad_left; }
@@ -348,8 +391,16 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
     p.thin = (const float*)thin; p.w_ck = (const __nv_bfloat16*)w_ck; p.bias = bias; p.out = (__nv_bfloat16*)wide;
     if (thin_is_x) { p.thin_ld = d->x_ld; p.thin_coff = d->x_coff; p.out_ld = d->y_ld; p.out_coff = d->y_coff; }
     else { p.thin_ld = d->y_ld; p.thin_coff = d->y_coff; p.out_ld = d->x_ld; p.out_coff = d->x_coff; }
-    static bool attr_set = false;
-    if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(thin_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM)); attr_set = true; }
+    // square 3x3 / 6x6 kernels (the stem and the head of the model) get compile-time tap offsets; anything else the generic path
+    const int ksz = (d->R == d->S && (d->R == 3 || d->R == 6)) ? d->R : 0;
+    void (*kern)(const ThinParams) = thin_gemm_kernel<0, false>;
+    if (ksz == 3) kern = thin_is_x ? thin_gemm_kernel<3, false> : thin_gemm_kernel<3, true>;
+    if (ksz == 6) kern = thin_is_x ? thin_gemm_kernel<6, false> : thin_gemm_kernel<6, true>;
+    static bool attr_set[3][2] = {};
+    if (!attr_set[ksz / 3][thin_is_x]) {
+        URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        attr_set[ksz / 3][thin_is_x] = true;
+    }
     // the per-tile phases of a CTA (patch load, im2col build, MMA, store) run back to back, so throughput comes
     // from co-resident CTAs: as many as the shared memory of the layer's atom count allows
     const int atoms = p.nchunks > 8 ? 2 : 1;
@@ -357,7 +408,7 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
     const int per_sm = atoms == 1 ? 8 : 4;             // measured: 80 -> 56 us for the stem; no gain beyond 4 with two atoms
     int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
     dim3 grid(gx, p.CW_total / 32);
-    thin_gemm_kernel<<<grid, 128, smem, st>>>(p);
+    kern<<<grid, 128, smem, st>>>(p);
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }
@@ -378,8 +429,15 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
         int rc = encode_map(&map, (const char*)wide + (size_t)wide_coff * 2, 4, dims, strides, box, 64);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM)); attr_set = true; }
+    const int ksz = (d->R == d->S && (d->R == 3 || d->R == 6)) ? d->R : 0;
+    void (*kern)(const CUtensorMap, const ThinParams) = thin_wgrad_kernel<0, false>;
+    if (ksz == 3) kern = thin_is_x ? thin_wgrad_kernel<3, false> : thin_wgrad_kernel<3, true>;
+    if (ksz == 6) kern = thin_is_x ? thin_wgrad_kernel<6, false> : thin_wgrad_kernel<6, true>;
+    static bool attr_set[3][2] = {};
+    if (!attr_set[ksz / 3][thin_is_x]) {
+        URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+        attr_set[ksz / 3][thin_is_x] = true;
+    }
     if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.ntaps * d->C * d->K, st));
     const int atoms = p.nchunks > 8 ? 2 : 1;
     // with one atom the M = 128 instruction also reads the 16 KB after its A stage (the other stage / the B
@@ -388,7 +446,7 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     const int per_sm = 2;                              // more CTAs only add dw reductions (measured slower)
     int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
     dim3 grid(gx, p.CW_total / 32);
-    thin_wgrad_kernel<<<grid, 128, smem, st>>>(map, p);
+    kern<<<grid, 128, smem, st>>>(map, p);
     URIR_LAUNCH_OK(1);
     return URIR_OK;
 }
