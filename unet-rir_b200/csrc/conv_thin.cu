@@ -11,6 +11,7 @@
 // same shared-memory image of the im2col tile: 128 rows (pixels) of 128 B, 16-byte chunks XOR-swizzled with
 // (row % 8) -- consumed K-major by thin_gemm and MN-major by thin_wgrad.
 // The head's forward (wide -> thin) lives in conv_head.cu.
+#include <stdlib.h>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -405,7 +406,10 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
     // from co-resident CTAs: as many as the shared memory of the layer's atom count allows
     const int atoms = p.nchunks > 8 ? 2 : 1;
     const int smem = atoms * (TH_ATOM + TG_B_ATOM) + TH_PATCH_MAX * 8 + 64 + 1024;
-    const int per_sm = atoms == 1 ? 8 : 4;             // measured: 80 -> 56 us for the stem; no gain beyond 4 with two atoms
+    // = the CTAs that are actually resident (93 registers, <= 43 KB): a grid of 8 per SM ran as 1.6 waves of persistent
+    // CTAs. Measured per call (B = 64): stem fprop 49 -> 41 us, head dgrad 75 -> 66 us against 8 / 4 per SM.
+    int per_sm = 5;
+    { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_GEMM_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0) per_sm = ov; }
     int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
     dim3 grid(gx, p.CW_total / 32);
     kern<<<grid, 128, smem, st>>>(p);
@@ -443,7 +447,8 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     // with one atom the M = 128 instruction also reads the 16 KB after its A stage (the other stage / the B
     // stages: finite bf16 data inside the allocation); those accumulator rows 64..127 are never read back
     const int smem = 2 * atoms * TH_ATOM + 2 * TW_B_STAGE + TH_PATCH_MAX * 8 + 128 + 1024;
-    const int per_sm = 2;                              // more CTAs only add dw reductions (measured slower)
+    int per_sm = 2;                                    // more CTAs only add dw reductions (measured slower)
+    { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_WGRAD_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0 && atoms == 1) per_sm = ov; }
     int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
     dim3 grid(gx, p.CW_total / 32);
     kern<<<grid, 128, smem, st>>>(map, p);
