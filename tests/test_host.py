@@ -237,3 +237,12 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
+
+
+def test_multiply_shift_tile_division_is_exact_below_2_pow_20():
+    """conv_thin.cu thin_tile_coords divides tile indices by tiles_w / tiles_h as (tile * ceil(2^40 / d)) >> 40 and
+    thin_geometry_ok admits only launches with fewer than 2^20 tiles: the identity must hold for every such index."""
+    n = np.arange(1 << 20, dtype=np.uint64)
+    for d in (1, 2, 3, 5, 7, 9, 10, 18, 20, 36, 40, 72, 80, 144, 160, 1000, 4097, 1 << 19, (1 << 20) - 1):
+        mag = np.uint64(((1 << 40) + d - 1) // d)
+        assert np.array_equal((n * mag) >> np.uint64(40), n // np.uint64(d)), d
