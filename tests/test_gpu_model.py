@@ -136,6 +136,44 @@ def test_adam_step_moves_parameters_like_oracle():
         assert abs(float(du.abs().mean()) - float(du_ref.abs().mean())) < 0.05 * float(du_ref.abs().mean()), name
 
 
+def test_trainer_train_epoch_loop(capsys):
+    """Trainer.train (amp_phase_trainer.py:37-127): history rows [loss, phase, stft] per epoch, loss = phase + stft,
+    validation rows equal model_loss of the eval forward, checkpoint / early-stopping protocol, the console lines."""
+    from unet_rir_b200.amp_phase_trainer import EarlyStopping, ModelCheckpoint, Trainer
+    from unet_rir_b200.dl_models.u_net import UNet
+    g = torch.Generator().manual_seed(11)
+
+    class Gen:                                   # DataGenerator contract: (spec_in, emb, spec_out) per index
+        def __init__(self, n):
+            self.items = [(torch.rand(2, 144, 160, 2, generator=g), torch.randint(0, 2000, (2, 2, 16), generator=g, dtype=torch.int32),
+                           torch.rand(2, 144, 160, 2, generator=g)) for _ in range(n)]
+        def __len__(self):
+            return len(self.items)
+        def __getitem__(self, i):
+            return self.items[i]
+
+    unet = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+    mc, es = ModelCheckpoint("/tmp/urir_train_loop", False, 1), EarlyStopping(2)
+    tr = Trainer(0.9, 3, "adam", [mc, es], [True, 1], 1e-3, "loop")
+    train_gen, val_gen = Gen(3), Gen(2)
+    model, hist = tr.train(unet, train_gen, val_gen)
+    out = capsys.readouterr().out
+    assert model is unet and 1 <= hist.epochs <= 3
+    th, vh = hist.train_loss_history, hist.val_loss_history
+    assert th.shape == (hist.epochs, 3) and vh.shape == (hist.epochs, 3)
+    assert np.isfinite(th).all() and np.isfinite(vh).all()
+    assert np.allclose(th[:, 0], th[:, 1] + th[:, 2], rtol=1e-5) and np.allclose(vh[:, 0], vh[:, 1] + vh[:, 2], rtol=1e-5)
+    assert abs(tr.learning_rate - 1e-3 * np.exp(-0.25 * (hist.epochs - 1 - 1))) < 1e-12 or hist.epochs == 1
+    # the last epoch's validation row, recomputed from the final weights
+    rows = []
+    for i in range(len(val_gen)):
+        spec_in, emb, spec_out = val_gen[i]
+        rows.append([float(v) for v in tr.model_loss(spec_out, unet.model([spec_in, emb], training=False))])
+    assert np.allclose(np.mean(rows, axis=0), vh[-1], rtol=1e-4)
+    assert abs(mc.val_loss_min - min(10, float(vh[:, 0].min()))) < 1e-6
+    assert out.count("[INFO]: Starting epoch") == hist.epochs and "Perdidas training:" in out and " - Perdidas combinadas: " in out
+
+
 def test_many_graph_replays_stay_healthy():
     """Soak test: 600 replays of the captured train step. Guards the pipelines' mbarrier protocols against
     timing-dependent hangs (a two-issuer ring whose stage ownership alternated between fills once aliased mbarrier

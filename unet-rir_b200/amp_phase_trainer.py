@@ -111,78 +111,68 @@ class Trainer:
         return spec_in, spec_out, emb
 
     def train(self, model, train_generator, val_generator):
+        """Epoch loop of the reference (:37-127): same console lines, same history rows [loss, phase, stft], same
+        checkpoint / early-stopping protocol; returns (model, History)."""
         print("[INFO]: Training model...")
-        numUpdates = train_generator.__len__()
-        numUpdates_val = val_generator.__len__()
-
-        for epoch in range(0, self.n_epochs):
-            train_loss, train_loss_phase, train_loss_stft = [], [], []
-            val_loss, val_loss_phase, val_loss_stft = [], [], []
-
+        n_train, n_val = len(train_generator), len(val_generator)
+        last = -1
+        for epoch in range(self.n_epochs):
+            last = epoch
             print("\n[INFO]: Starting epoch {}/{}...".format(epoch + 1, self.n_epochs), end="\n")
             sys.stdout.flush()
-            epochStart = time.time()
+            t_start = time.time()
+            self._apply_lr_schedule(epoch)
+            train_sums = self._train_epoch(model, train_generator, n_train)
+            val_sums = self._validate(model, val_generator, n_val)
+            print("took {:.4} seconds".format(time.time() - t_start))
 
-            # exponential lr in last epochs (:56-59)
-            if self.lr_exp_decay:
-                if epoch >= self.lr_exp_decay_epoch:
-                    self.learning_rate = self.lr0 * np.exp(-0.25 * (epoch - self.lr_exp_decay_epoch))
+            train_means = [_mean(col) for col in train_sums]
+            self._report("Perdidas training:", " - Perdidas: ", train_means)
+            val_means = [_mean(col) for col in val_sums]
+            self._report("Perdidas validation:", " - Perdidas combinadas: ", val_means)
+            self.train_loss_history[epoch, :] = train_means
+            self.val_loss_history[epoch, :] = val_means
 
-            nxt = self._next_batch(train_generator, 0) if numUpdates > 0 else None
-            for i in range(0, numUpdates):
-                spec_in, spec_out, emb = nxt
-                loss, loss_phase, loss_stft = self.step(spec_in, spec_out, emb, model)
-                if i + 1 < numUpdates:        # next batch's H2D copy overlaps this step (enqueued, not waited for)
-                    nxt = self._next_batch(train_generator, i + 1)
-                    self.prefetch(nxt[0], nxt[1], nxt[2], model)
-                train_loss.append(loss)
-                train_loss_phase.append(loss_phase)
-                train_loss_stft.append(loss_stft)
-
-            for i in range(0, numUpdates_val):
-                spec_in, spec_out, emb = self._next_batch(val_generator, i)
-                with torch.no_grad():
-                    spec_generated = model.model([spec_in, emb], training=False)
-                loss, loss_phase, loss_stft = self.model_loss(spec_out, spec_generated)
-                val_loss.append(loss)
-                val_loss_phase.append(loss_phase)
-                val_loss_stft.append(loss_stft)
-
-            elapsed = (time.time() - epochStart)
-            print("took {:.4} seconds".format(elapsed))
-
-            train_loss = _mean(train_loss)
-            train_loss_phase = _mean(train_loss_phase)
-            train_loss_stft = _mean(train_loss_stft)
-            print("Perdidas training:")
-            print(" - Perdidas: " + str(train_loss))
-            print(" - Perdidas fase: " + str(train_loss_phase))
-            print(" - Perdidas módulo: " + str(train_loss_stft))
-
-            val_loss = _mean(val_loss)
-            val_loss_phase = _mean(val_loss_phase)
-            val_loss_stft = _mean(val_loss_stft)
-            print("Perdidas validation:")
-            print(" - Perdidas combinadas: " + str(val_loss))
-            print(" - Perdidas fase: " + str(val_loss_phase))
-            print(" - Perdidas módulo: " + str(val_loss_stft))
-
-            self.train_loss_history[epoch][0] = train_loss
-            self.train_loss_history[epoch][1] = train_loss_phase
-            self.train_loss_history[epoch][2] = train_loss_stft
-            self.val_loss_history[epoch][0] = val_loss
-            self.val_loss_history[epoch][1] = val_loss_phase
-            self.val_loss_history[epoch][2] = val_loss_stft
-
-            improve = self.model_checkpoint.checkpoint(train_loss=train_loss, val_loss=val_loss, model=model)
-            stop = self.early_stop.stop_count(improve=improve)
-
-            if stop:
+            improved = self.model_checkpoint.checkpoint(train_loss=train_means[0], val_loss=val_means[0], model=model)
+            if self.early_stop.stop_count(improve=improved):
                 break
+        done = last + 1
+        return model, History(done, self.train_loss_history[:done, :], self.val_loss_history[:done, :])
 
-        n_epochs = epoch + 1
-        H = History(n_epochs, self.train_loss_history[:n_epochs, :], self.val_loss_history[:n_epochs, :])
-        return model, H
+    def _apply_lr_schedule(self, epoch):
+        # exponential decay over the last epochs (:56-59)
+        if self.lr_exp_decay and epoch >= self.lr_exp_decay_epoch:
+            self.learning_rate = self.lr0 * np.exp(-0.25 * (epoch - self.lr_exp_decay_epoch))
+
+    def _train_epoch(self, model, gen, n_batches):
+        """One pass over the training generator; returns three lists (loss, phase, stft) of per-step device scalars."""
+        cols = ([], [], [])
+        batch = self._next_batch(gen, 0) if n_batches > 0 else None
+        for i in range(n_batches):
+            spec_in, spec_out, emb = batch
+            step_losses = self.step(spec_in, spec_out, emb, model)
+            if i + 1 < n_batches:             # next batch's H2D copy overlaps this step (enqueued, not waited for)
+                batch = self._next_batch(gen, i + 1)
+                self.prefetch(batch[0], batch[1], batch[2], model)
+            for col, v in zip(cols, step_losses):
+                col.append(v)
+        return cols
+
+    def _validate(self, model, gen, n_batches):
+        cols = ([], [], [])
+        for i in range(n_batches):
+            spec_in, spec_out, emb = self._next_batch(gen, i)
+            with torch.no_grad():
+                generated = model.model([spec_in, emb], training=False)
+            for col, v in zip(cols, self.model_loss(spec_out, generated)):
+                col.append(v)
+        return cols
+
+    @staticmethod
+    def _report(title, first_label, means):
+        print(title)
+        for label, v in zip((first_label, " - Perdidas fase: ", " - Perdidas módulo: "), means):
+            print(label + str(v))
 
     # ------------------------------------------------------------------ one optimiser step (:130-141)
     def _device_step(self, eng, B):
@@ -272,54 +262,37 @@ class Trainer:
 ########################################################
 
 class ModelCheckpoint(object):
-    def __init__(self, filepath, save_best_only, verbose):
-        self.filepath = filepath
-        self.save_best_only = save_best_only
-        self.verbose = verbose
+    """Best-validation bookkeeping of the reference (:175-203): both minima start at 10, a strictly smaller validation
+    loss counts as an improvement (and saves the model when save_best_only is set)."""
 
-        'Secondary initialization'
-        self.train_loss_min = 10
-        self.val_loss_min = 10
+    def __init__(self, filepath, save_best_only, verbose):
+        self.filepath, self.save_best_only, self.verbose = filepath, save_best_only, verbose
+        self.train_loss_min = self.val_loss_min = 10
 
     def checkpoint(self, train_loss, val_loss, model):
-        improve = False
-        if val_loss < self.val_loss_min:
-
-            if self.verbose:
-                print('Validation loss improved from ' + str(self.val_loss_min) + ' to ' + str(val_loss))
-
-            if self.save_best_only:
-                model.save(self.filepath)
-
-            self.val_loss_min = val_loss
-            self.train_loss_min = train_loss
-            improve = True
-
-        else:
+        if not val_loss < self.val_loss_min:
             if self.verbose:
                 print('Validation loss did not improve')
-
-        return improve
+            return False
+        if self.verbose:
+            print('Validation loss improved from ' + str(self.val_loss_min) + ' to ' + str(val_loss))
+        if self.save_best_only:
+            model.save(self.filepath)
+        self.val_loss_min, self.train_loss_min = val_loss, train_loss
+        return True
 
 
 class EarlyStopping(object):
+    """Stops when `patience` consecutive epochs brought no improvement (:206-223); the counter resets on improvement and
+    the comparison is `==`, so a patience of 0 never fires."""
+
     def __init__(self, patience):
         self.patience = patience
-
-        'Secondary initialization'
         self.count = 0
 
     def stop_count(self, improve):
-        stop = False
-        if improve:
-            self.count = 0
-        else:
-            self.count = self.count + 1
-
-        if self.count == self.patience:
-            stop = True
-
-        return stop
+        self.count = 0 if improve else self.count + 1
+        return self.count == self.patience
 
 
 class History(object):
