@@ -85,10 +85,34 @@ int         urir_version(void);
 const char* urir_last_error(void);
 /* number of kernels launched by this library since load; kind 0 = all, 1 = tcgen05 only */
 long long   urir_launch_count(int kind);
+/* which kernel family served the convolution calls: urir_family_calls(f) = successful urir_conv2d_* calls dispatched to
+ * family f since load; urir_family_name(f) its name. Parity tests use these to prove that the dispatch they checked
+ * against the oracle is the one the benchmark times. */
+#define URIR_FAM_SIMT           0   /* CUDA-core direct convolution (cross-check path)                      */
+#define URIR_FAM_IGEMM          1   /* one-tile-per-CTA tcgen05 implicit GEMM (fprop / dgrad)              */
+#define URIR_FAM_HALO           2   /* persistent halo-tile tcgen05 kernel, stride-1 fprop / dgrad         */
+#define URIR_FAM_HALO_S2_FPROP  3   /* the same kernel over the four parity planes of a stride-2 input     */
+#define URIR_FAM_HALO_UP2       4   /* stride-2 dgrad / Conv2DTranspose forward as one 2x2 problem         */
+#define URIR_FAM_THIN_GEMM      5   /* 2-channel stem fprop / head dgrad                                   */
+#define URIR_FAM_HEAD_FPROP     6   /* 2-channel 6x6 sigmoid head                                          */
+#define URIR_FAM_WGRAD_TC       7   /* split-pixel tcgen05 weight gradient                                 */
+#define URIR_FAM_WGRAD_HALO     8   /* persistent halo weight gradient, stride 1                           */
+#define URIR_FAM_WGRAD_HALO_S2  9   /* persistent halo weight gradient, stride 2                           */
+#define URIR_FAM_THIN_WGRAD    10   /* 2-channel stem / head weight gradient                               */
+#define URIR_FAM_DEEP          11   /* persistent padded-sequence tcgen05 kernel of the deep (<= 36x40) layers */
+#define URIR_FAM_COUNT         12
+long long   urir_family_calls(int family);
+const char* urir_family_name(int family);
 /* programmatic dependent launch of the library's kernels (default on; URIR_NO_PDL=1 starts with it off):
  * a kernel's prologue may overlap its predecessor's tail. Returns the previous setting. Turn it off to time
  * kernels one by one with events. */
 int         urir_set_pdl(int enabled);
+/* deterministic mode (default off; URIR_DETERMINISTIC=1 starts with it on): every cross-CTA floating-point reduction
+ * (BatchNorm statistics from the conv epilogues, BatchNorm backward sums, weight-gradient splits, bias gradients,
+ * embedding gradient, loss scalars) is committed in a fixed CTA order instead of by unordered atomics, so two runs
+ * on the same inputs are bit-identical. Slower (the commits serialise); meant for parity tests. Returns the previous
+ * setting. Takes effect for kernels launched (or captured into a graph) afterwards. */
+int         urir_set_deterministic(int enabled);
 
 /* ---- convolutions: replace tf.keras Conv2D / Conv2DTranspose and their autodiff ------- */
 /* Conv2D forward (dl_models/u_net.py:269-276, 366, 248, 262). Also Conv2DTranspose's
@@ -208,6 +232,17 @@ int urir_ampphase_loss(const float* y_true, const float* y_pred, long long npix,
 int urir_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev,
               const int32_t* step_dev, float beta1, float beta2, float eps, void* stream);
 int urir_sgd(float* p, const float* g, long long n, const float* lr_dev, void* stream);
+/* tf.keras.optimizers.Nadam ("nadam" in the optimiser name, amp_phase_trainer.py:30-31; Keras momentum schedule
+ * u_t = b1 (1 - 0.5 * 0.96^(0.004 t))). coef_dev: fp32[4] device state owned by the caller, [0] = running product of
+ * u_i (the kernel treats *step_dev == 0 as a fresh state). Two launches; graph capturable. */
+int urir_nadam(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, const int32_t* step_dev,
+               float* coef_dev, float beta1, float beta2, float eps, void* stream);
+/* tensorflow_addons LAMB (the generic trainer's "lamb" option, trainer.py:37-38): Adam direction with a per-variable
+ * trust ratio ||w|| / ||update||. table_dev = n_vars x {element offset, element count} (int64, device) of the variables
+ * inside the flat buffers; upd = fp32 scratch of the flat size; norms = fp32[2 * n_vars] scratch. */
+int urir_lamb(float* p, const float* g, float* m, float* v, float* upd, const int64_t* table_dev, int n_vars, float* norms,
+              const float* lr_dev, const int32_t* step_dev, float beta1, float beta2, float eps, float weight_decay,
+              void* stream);
 int urir_step_increment(int32_t* step_dev, void* stream);
 /* y += a*x (fp32) -- L2 kernel-regulariser gradient of the DP loss (main_training.py:232-233) */
 int urir_axpy(float* y, const float* x, float a, long long n, void* stream);

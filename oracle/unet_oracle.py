@@ -16,7 +16,8 @@ What is restated (all citations into /root/reference):
   * dl_models/u_net.py:324-386   the four block modes -> UNetOracle._block
   * amp_phase_trainer.py:143-168 model_loss           -> amp_phase_loss
   * main_training.py:203-235     compute_loss (DP)    -> dp_loss
-  * amp_phase_trainer.py:30-35   Keras Adam/SGD       -> keras_adam_step / keras_sgd_step
+  * amp_phase_trainer.py:30-35   Keras Adam/SGD/Nadam -> keras_adam_step / keras_sgd_step / keras_nadam_step
+  * trainer.py:37-38             tfa LAMB             -> tfa_lamb_step
 
 Tensors are NHWC float32 at the interface, exactly like the reference's
 (datageneratorv2.py:88-102). Kernels are stored in Keras layouts: Conv2D HWIO,
@@ -392,6 +393,39 @@ def keras_adam_step(params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1
         m[n].mul_(beta1).add_(g, alpha=1 - beta1)
         v[n].mul_(beta2).addcmul_(g, g, value=1 - beta2)
         params[n].sub_(lr_t * m[n] / (v[n].sqrt() + eps))
+
+
+def keras_nadam_step(params, grads, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-7):
+    """tf.keras.optimizers.Nadam (optimizer_v2/nadam.py, the "nadam" branch of amp_phase_trainer.py:30-31).
+    state = {"step": completed steps, "m_schedule": running product of the momentum schedule (1.0 at the start)}."""
+    t = state["step"] + 1
+    u_t = beta1 * (1.0 - 0.5 * 0.96 ** (0.004 * t))
+    u_t1 = beta1 * (1.0 - 0.5 * 0.96 ** (0.004 * (t + 1)))
+    ms = state["m_schedule"] * u_t
+    ms_next = ms * u_t1
+    state["m_schedule"], state["step"] = ms, t
+    for n in grads:
+        g = grads[n]
+        g_prime = g / (1.0 - ms)
+        m[n].mul_(beta1).add_(g, alpha=1 - beta1)
+        v[n].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        m_prime = m[n] / (1.0 - ms_next)
+        v_prime = v[n] / (1.0 - beta2 ** t)
+        m_bar = (1.0 - u_t) * g_prime + u_t1 * m_prime
+        params[n].sub_(lr * m_bar / (v_prime.sqrt() + eps))
+
+
+def tfa_lamb_step(params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0):
+    """tensorflow_addons.optimizers.LAMB (trainer.py:37-38), step is 1-based: Adam direction with bias correction,
+    per-variable trust ratio ||w|| / ||update|| (1 when either norm is zero)."""
+    for n in grads:
+        g = grads[n]
+        m[n].mul_(beta1).add_(g, alpha=1 - beta1)
+        v[n].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        upd = (m[n] / (1 - beta1 ** step)) / ((v[n] / (1 - beta2 ** step)).sqrt() + eps) + weight_decay * params[n]
+        wn, un = float(params[n].norm()), float(upd.norm())
+        ratio = wn / un if (wn > 0 and un > 0) else 1.0
+        params[n].sub_(lr * ratio * upd)
 
 
 def keras_sgd_step(params, grads, lr):

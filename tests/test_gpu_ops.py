@@ -249,3 +249,94 @@ def test_stft_long_rir():
     for i in range(2):
         w = wav[i] - wav[i].mean()
         assert 20 * np.log10(np.linalg.norm(back[i][128:-128] - w[128:-128]) / np.linalg.norm(w[128:-128])) < -60
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: the other optimisers of the reference (amp_phase_trainer.py:30-35, trainer.py:37-38) on the device
+# ------------------------------------------------------------------------------------------------
+def test_sgd_nadam_lamb_match_keras_conventions():
+    g = torch.Generator().manual_seed(12)
+    sizes = [1000, 37, 4096, 8]                       # four "variables" laid out back to back (offsets 4-aligned)
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o); o += (s + 3) // 4 * 4
+    n = o
+    p0 = torch.randn(n, generator=g)
+    for o_, s in zip(offs, sizes):
+        p0[o_ + s:o_ + (s + 3) // 4 * 4] = 0
+    grads = [torch.randn(n, generator=g) * (10.0 ** (t - 2)) for t in range(4)]
+    lr = 2e-3
+    lr_dev = torch.tensor([lr], device="cuda")
+
+    # ---- SGD (tf.keras.optimizers.SGD defaults: no momentum)
+    pc = p0.clone().cuda()
+    ref = {"w": p0.clone()}
+    for gr in grads:
+        O.keras_sgd_step(ref, {"w": gr}, lr)
+        L.call("sgd", pc.data_ptr(), gr.cuda().data_ptr(), n, lr_dev.data_ptr())
+    assert U.rel_l2(pc, ref["w"]) < 1e-6
+
+    # ---- Nadam (momentum-schedule product carried in device memory across steps)
+    pc, mc, vc = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    coef = torch.ones(4, device="cuda")
+    ref, m, v, state = {"w": p0.clone().double()}, {"w": torch.zeros(n).double()}, {"w": torch.zeros(n).double()}, {"step": 0, "m_schedule": 1.0}
+    for gr in grads:
+        O.keras_nadam_step(ref, {"w": gr.double()}, m, v, state, lr)
+        L.call("nadam", pc.data_ptr(), gr.cuda().data_ptr(), mc.data_ptr(), vc.data_ptr(), n, lr_dev.data_ptr(),
+               step.data_ptr(), coef.data_ptr(), 0.9, 0.999, 1e-7)
+        L.call("step_increment", step.data_ptr())
+    assert abs(float(coef[0]) - state["m_schedule"]) < 1e-6 * state["m_schedule"]
+    assert U.rel_l2(pc - p0.cuda(), (ref["w"] - p0.double()).float()) < 2e-5
+    assert U.rel_l2(mc, m["w"].float()) < 1e-6 and U.rel_l2(vc, v["w"].float()) < 1e-6
+
+    # ---- LAMB: per-variable trust ratio
+    pc, mc, vc = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    upd, norms = torch.empty(n, device="cuda"), torch.zeros(2 * len(sizes), device="cuda")
+    table = torch.tensor([[o_, s] for o_, s in zip(offs, sizes)], dtype=torch.int64, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    names = [f"v{i}" for i in range(len(sizes))]
+    ref = {k: p0[o_:o_ + s].clone().double() for k, o_, s in zip(names, offs, sizes)}
+    m = {k: torch.zeros_like(t) for k, t in ref.items()}
+    v = {k: torch.zeros_like(t) for k, t in ref.items()}
+    for t, gr in enumerate(grads, 1):
+        O.tfa_lamb_step(ref, {k: gr[o_:o_ + s].double() for k, o_, s in zip(names, offs, sizes)}, m, v, t, lr)
+        L.call("lamb", pc.data_ptr(), gr.cuda().data_ptr(), mc.data_ptr(), vc.data_ptr(), upd.data_ptr(), table.data_ptr(),
+               len(sizes), norms.data_ptr(), lr_dev.data_ptr(), step.data_ptr(), 0.9, 0.999, 1e-6, 0.0)
+        L.call("step_increment", step.data_ptr())
+    for k, o_, s in zip(names, offs, sizes):
+        got, want = pc[o_:o_ + s].cpu() - p0[o_:o_ + s], (ref[k] - p0[o_:o_ + s].double()).float()
+        assert U.rel_l2(got, want) < 5e-5, (k, U.rel_l2(got, want))
+
+
+def test_trainer_optimizer_selection_runs_on_the_device():
+    """'nadam' / 'sgd' / 'adam' substring selection (amp_phase_trainer.py:30-35): each drives its own device kernel inside
+    the captured step; one Nadam step equals the oracle's Keras Nadam applied to the device's gradient."""
+    from unet_rir_b200.amp_phase_trainer import EarlyStopping, ModelCheckpoint, Trainer
+    from unet_rir_b200.dl_models.u_net import UNet
+    g = torch.Generator().manual_seed(13)
+    x = torch.rand(2, 144, 160, 2, generator=g); y = torch.rand(2, 144, 160, 2, generator=g)
+    emb = torch.randint(0, 2000, (2, 2, 16), generator=g, dtype=torch.int32)
+    for name, expect in (("Nadam", "nadam"), ("my_sgd", "sgd"), ("adam", "adam")):
+        unet = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+        eng = unet.model.engine
+        tr = Trainer(0.9, 1, name.lower(), [ModelCheckpoint("/tmp/urir_opt", False, 0), EarlyStopping(5)], [False, 0], 1e-3, "opt")
+        assert tr.optimizer == expect
+        tr.dropout = False
+        p0 = eng.P.clone()
+        tr.step(x, y, emb, unet)
+        gdev = eng.G.clone()
+        step = eng.P - p0
+        if expect == "sgd":
+            assert U.rel_l2(step, -1e-3 * gdev) < 1e-5
+        elif expect == "nadam":
+            ref, m, v = {"w": p0.double().cpu()}, {"w": torch.zeros_like(p0).double().cpu()}, {"w": torch.zeros_like(p0).double().cpu()}
+            O.keras_nadam_step(ref, {"w": gdev.double().cpu()}, m, v, {"step": 0, "m_schedule": 1.0}, 1e-3)
+            assert U.rel_l2(step.cpu(), (ref["w"] - p0.double().cpu()).float()) < 1e-4
+        else:
+            ref, m, v = {"w": p0.double().cpu()}, {"w": torch.zeros_like(p0).double().cpu()}, {"w": torch.zeros_like(p0).double().cpu()}
+            O.keras_adam_step(ref, {"w": gdev.double().cpu()}, m, v, 1, 1e-3)
+            assert U.rel_l2(step.cpu(), (ref["w"] - p0.double().cpu()).float()) < 1e-4
+        for _ in range(2):                      # capture + replay stay finite
+            l = tr.step(x, y, emb, unet)[0]
+        assert bool(torch.isfinite(l))

@@ -246,3 +246,107 @@ def test_multiply_shift_tile_division_is_exact_below_2_pow_20():
     for d in (1, 2, 3, 5, 7, 9, 10, 18, 20, 36, 40, 72, 80, 144, 160, 1000, 4097, 1 << 19, (1 << 20) - 1):
         mag = np.uint64(((1 << 40) + d - 1) // d)
         assert np.array_equal((n * mag) >> np.uint64(40), n // np.uint64(d)), d
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: Keras weight import (f1), per-room reports (f3), checkpoint manager (a18)
+# ------------------------------------------------------------------------------------------------
+def _keras_topological_shuffle(pairs, rng):
+    """A functional Keras model lists layers by depth, not creation: emulate with a random permutation of LAYERS
+    (variables of one layer stay together), which the importer must undo through class + auto-name index."""
+    groups, cur = [], None
+    for plan_name, kname in pairs:
+        layer = kname.split("/")[0]
+        if layer != cur:
+            groups.append([]); cur = layer
+        groups[-1].append((plan_name, kname))
+    order = rng.permutation(len(groups))
+    return [pv for g in order for pv in groups[g]]
+
+
+@pytest.mark.parametrize("mode,kernels", [(0, 3), (0, 6), (3, 3)])
+def test_keras_npz_import_maps_every_variable(tmp_path, mode, kernels):
+    """tools/export_tf_weights.py's file format -> plan: 77 trainable + 26 moving statistics (mode 0) land on the right
+    plan entries whatever the order of the variables in the file and whatever the auto-name counters started at;
+    HWIO / HWOI / (in, out) layouts are taken as they are (u_net.py:192-199, 269-304)."""
+    from unet_rir_b200 import keras_weights as KW
+    from unet_rir_b200 import plan as PL
+    plan = PL.layer_plan(mode=mode, kernels=kernels)
+    ref = PL.keras_init(plan, seed=7)
+    rng = np.random.default_rng(1)
+    for n in ref:                                   # make every tensor distinctive, including BN state
+        ref[n] = ref[n] + torch.from_numpy(rng.standard_normal(tuple(ref[n].shape)).astype(np.float32)) * 0.01
+    pairs = KW.keras_names_for_plan(plan, offsets={"conv2d": 24, "batch_normalization": 13, "conv2d_transpose": 4})
+    if mode == 0:
+        assert len(pairs) == 103 and sum(1 for n, _, k in plan if k in PL.TRAINABLE_KINDS) == 77
+    assert ("vec.dense.w", "encoder_inf_dense/kernel:0") in pairs
+    shuffled = _keras_topological_shuffle(pairs, rng)
+    path = tmp_path / "w.npz"
+    np.savez(path, names=np.array([k for _, k in shuffled]),
+             **{f"arr_{i}": ref[p].numpy() for i, (p, _) in enumerate(shuffled)})
+    got = KW.read_keras_npz(str(path), plan)
+    assert list(got) == [n for n, _, _ in plan]
+    for n in ref:
+        assert got[n].dtype == torch.float32 and torch.equal(got[n], ref[n]), n
+    # shapes as Keras stores them
+    assert tuple(got["dec2.up.w"].shape) == (kernels, kernels, 256, 512)          # Conv2DTranspose: (kh, kw, out, in)
+    assert tuple(got["enc2.down.w"].shape) == (kernels, kernels, 32, 64)          # Conv2D: HWIO
+    assert tuple(got["vec.dense.w"].shape) == (2 * 16 * 256, 9 * 10 * 16)
+    # a file from a differently configured model is refused, not silently mis-mapped
+    other = PL.layer_plan(mode=mode, kernels=3 if kernels == 6 else 6)
+    with pytest.raises(ValueError):
+        KW.read_keras_npz(str(path), other)
+    names = [k for _, k in shuffled][:-2]
+    np.savez(tmp_path / "short.npz", names=np.array(names), **{f"arr_{i}": ref[p].numpy() for i, (p, _) in enumerate(shuffled[:-2])})
+    with pytest.raises(ValueError):
+        KW.read_keras_npz(str(tmp_path / "short.npz"), plan)
+
+
+def test_per_room_reports_follow_the_reference_format(tmp_path):
+    """rir_generation.py:303-532: six room groups in the reference's order, np.mean per group, positional(4) numbers for
+    the three spectrogram metrics, scientific(4) for the waveform / misalignment ones, the three files' names / headers."""
+    from unet_rir_b200 import rir_generation as R
+    rooms = ["HemiAnechoicRoom", "LargeMeetingRoom", "LargeMeetingRoom", "ShoeBoxRoom", "SmallMeetingRoom", "LargeMeetingRoom"]
+    res = {"total_mse": np.array([.5, .25, .75, .125, 1., .5]), "amp_mse": np.array([.1, .2, .3, .4, .5, .1]),
+           "phase_loss": np.array([1., 1., 1., 1., 1., 1.]), "wav_mse": np.array([1e-3, 2e-3, 3e-3, 4e-3, 5e-3, 1e-3]),
+           "wav_mse_50ms": np.array([1e-4] * 6), "missa_amp_db": np.array([-10., -20., -30., -5., -1., -10.]),
+           "missa_wav_db": np.array([-1., -2., -3., -4., -5., -6.]), "t_model_inference_avg": 0.0123456, "t_postprocess": 2e-4}
+    table = R.write_reports(res, rooms, "unet", str(tmp_path), 4, 1.5, t_loss=3e-5)
+    assert table["Large"]["n"] == 3 and abs(table["Large"]["total_mse"] - 0.5) < 1e-12 and table["Medium"]["n"] == 0
+    assert math.isnan(table["Medium"]["wav_mse"])
+    losses = open(tmp_path / "unet_losses.csv").read().splitlines()
+    assert losses[0] == ("room,n samples,MSE spectrogram,MSE magnitude,1-cos(y-y_) phase,MSE waveform,MSE waveform 50ms,"
+                         "Misalignment magnitude,Misalignment waveform")
+    assert [l.split(",")[0] for l in losses[1:]] == ["Global", "HemiAnechoic", "Large", "Medium", "Shoe", "Small"]
+    assert losses[3] == "Large,3,0.5,0.2,1.,2.e-03,1.e-04,-2.e+01,-3.6667e+00"
+    t = open(tmp_path / "unet_infer_time.csv").read().splitlines()
+    assert t[0] == "n_samples,t_model_inference_avg,batch_size,t_postprocess,t_loss_calc,t_global"
+    assert t[1] == "6,0.01235,4,0.0002,0.00003,1.5"
+    txt = open(tmp_path / "unet_results_inference.txt").read()
+    assert txt.startswith("unet results:\n\nTook 0.01235 s on average to infer spectrograms with batch size of 4\n")
+    assert "LargeMeetingRoom losses (3 samples):\nTotal loss: 0.5 (MSE whole spectrogram)\t|\tAmplitude loss: 0.2 (MSE amplitude)" in txt
+    assert "SmallMeetingRoom losses: (1 samples)\n" in txt and "Misalignment loss (amplitude): -1.e+00 (dB)\t|\t Misalignment loss (wav): -5.e+00 (dB)\n" in txt
+
+
+def test_checkpoint_manager_keeps_the_last_two(tmp_path):
+    """tf.train.CheckpointManager(max_to_keep=2) + save every second epoch (main_training.py:172, 363-364)."""
+    from unet_rir_b200.main_training import CheckpointManager
+
+    class FakeTrainer:
+        def __init__(self): self.v = 0
+        def checkpoint_state(self): return {"v": self.v}
+        def load_checkpoint_state(self, st): self.v = st["v"]
+
+    tr = FakeTrainer()
+    m = CheckpointManager(tr, str(tmp_path), max_to_keep=2)
+    assert m.latest_checkpoint is None
+    for epoch in range(6):
+        tr.v = epoch
+        if epoch % 2 == 0:
+            m.save()
+    assert sorted(os.listdir(tmp_path)) == ["ckpt-2.pt", "ckpt-3.pt"]
+    tr2 = FakeTrainer()
+    m2 = CheckpointManager(tr2, str(tmp_path), max_to_keep=2)
+    assert m2.restore_latest().endswith("ckpt-3.pt") and tr2.v == 4
+    m2.save()
+    assert sorted(os.listdir(tmp_path)) == ["ckpt-3.pt", "ckpt-4.pt"]

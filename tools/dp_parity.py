@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""N-GPU numerical check of the data-parallel step (main_training.py:253-291, 323-327).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dp_parity.py [--batch 8] [--out gpurun_out/dp_parity.json]
+
+With deterministic reductions on (urir_set_deterministic), on every rank:
+  1. DistributedTrainer.train_step x 3 on this rank's shard (eager, graph capture, graph replay; lr = 0 so the weights
+     stay put): G_dp = the flat gradient after the three bucketed NCCL all-reduces + the L2 regulariser term.
+  2. A second engine with the same weights computes THIS shard's gradient alone (same loss weights, no collective);
+     the shard gradients of all ranks are all-gathered and summed in rank order, the regulariser 2*0.001*W added.
+  Checks: (a) G_dp is bit-identical on all ranks; (b) G_dp == sum of shard gradients per tensor to 1e-5 rel-L2
+  (the all-reduce adds nothing but fp32 rounding); (c) the replayed graph reproduces the eager step bit for bit;
+  (d) on rank 0, the gradient of the same GLOBAL batch on one GPU (BatchNorm statistics over the whole batch) differs
+  from G_dp by more than 1e-3 in the BatchNorm-coupled tensors: the replicas really normalise per shard, as plain
+  BatchNormalization under MirroredStrategy does (u_net.py:368).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8, help="samples per replica")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "dp_parity.json"))
+    args = ap.parse_args()
+    from unet_rir_b200 import _lib as L
+    from unet_rir_b200 import plan as PL
+    from unet_rir_b200.dl_models.u_net import UNet
+    from unet_rir_b200.engine import UNetEngine
+    from unet_rir_b200.main_training import DistributedTrainer, init_distributed
+
+    rank, world, local = init_distributed("nccl")
+    dev = torch.device("cuda", local)
+    L.set_deterministic(True)
+    B, GB = args.batch, args.batch * world
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(GB, 144, 160, 2, generator=g); y = torch.rand(GB, 144, 160, 2, generator=g)
+    for t in (x, y):
+        t[:, 129:] = 0; t[:, :, 151:] = 0
+    emb = torch.randint(0, 2000, (GB, 2, 16), generator=g, dtype=torch.int32)
+    sl = slice(rank * B, (rank + 1) * B)
+    params = PL.keras_init(PL.layer_plan(kernels=3), seed=500)
+    for n, t in params.items():                                  # non-trivial BN affine / biases
+        if n.endswith(".gamma"):
+            t.add_(0.2 * torch.randn(t.shape, generator=g))
+        elif n.endswith(".beta") or n.endswith(".b"):
+            t.add_(0.1 * torch.randn(t.shape, generator=g))
+
+    unet = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+    eng = unet.model.engine
+    eng.load_state_dict(params)
+    dt = DistributedTrainer(unet, per_replica_batch=B, alpha=0.9, lr=0.0, loss="dp", world=world, rank=rank, dropout=False)
+    g_steps = []
+    for _ in range(3):
+        dt.train_step(x[sl], emb[sl], y[sl])
+        torch.cuda.synchronize()
+        g_steps.append(eng.G.clone())
+    G_dp = g_steps[-1]
+    res = {"world": world, "per_replica_batch": B, "graph": type(dt._graphs.get(B)).__name__}
+    res["replay_equals_eager_bitwise"] = bool(torch.equal(g_steps[0], g_steps[2]) and torch.equal(g_steps[0], g_steps[1]))
+
+    # (a) identical on every rank
+    gathered = [torch.empty_like(G_dp) for _ in range(world)]
+    dist.all_gather(gathered, G_dp)
+    res["identical_on_all_ranks"] = all(bool(torch.equal(gathered[0], t)) for t in gathered)
+
+    # (b) sum of per-shard gradients
+    e2 = UNetEngine(kernels=3)
+    e2.load_state_dict(params)
+    e2.forward(x[sl].to(dev), emb[sl].to(dev), training=True, dropout=False)
+    wa, wp = dt._weights(B)
+    e2.loss_and_grad(y[sl].to(dev), wa, wp)
+    e2.backward(e2._buffers(B)["g_out"])
+    torch.cuda.synchronize()
+    shard = [torch.empty_like(e2.G) for _ in range(world)]
+    dist.all_gather(shard, e2.G)
+    total = torch.zeros_like(e2.G)
+    for t in shard:
+        total += t
+    for n in eng.trainable_names():
+        if PL.l2_regularised(n):
+            o, cnt = eng.offsets[n]
+            total[o:o + cnt] += 2 * PL.L2_COEF * eng.P[o:o + cnt]
+    worst, worst_name = 0.0, None
+    for n in eng.trainable_names():
+        o, cnt = eng.offsets[n]
+        a, b = G_dp[o:o + cnt], total[o:o + cnt]
+        r = rel_l2(a, b) if float(b.abs().max()) > 1e-12 else float((a - b).abs().max())
+        if r > worst:
+            worst, worst_name = r, n
+    res["max_rel_l2_vs_sum_of_shards"] = worst
+    res["worst_tensor"] = worst_name
+    res["sum_check_pass"] = worst < 1e-5
+
+    # (d) full-batch BatchNorm on one GPU gives a DIFFERENT gradient
+    if rank == 0:
+        e3 = UNetEngine(kernels=3)
+        e3.load_state_dict(params)
+        e3.forward(x.to(dev), emb.to(dev), training=True, dropout=False)
+        e3.loss_and_grad(y.to(dev), wa, wp)
+        e3.backward(e3._buffers(GB)["g_out"])
+        torch.cuda.synchronize()
+        full = e3.G.clone()
+        for n in eng.trainable_names():
+            if PL.l2_regularised(n):
+                o, cnt = eng.offsets[n]
+                full[o:o + cnt] += 2 * PL.L2_COEF * eng.P[o:o + cnt]
+        diffs = {}
+        for n in ("enc1.blk.c1.w", "enc3.blk.bn1.gamma", "dec2.fuse.w", "dec5.blk.c1.w", "head.w"):
+            o, cnt = eng.offsets[n]
+            diffs[n] = rel_l2(G_dp[o:o + cnt], full[o:o + cnt])
+        res["rel_l2_vs_full_batch_bn"] = diffs
+        res["per_replica_bn_confirmed"] = min(diffs.values()) > 1e-3
+    L.set_deterministic(False)
+    if rank == 0:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out, "w") as f:
+            json.dump(res, f, indent=1)
+        print(json.dumps(res), flush=True)
+    ok = res["identical_on_all_ranks"] and res["sum_check_pass"] and res["replay_equals_eager_bitwise"] and res.get("per_replica_bn_confirmed", True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,11 +40,14 @@ _PROTOS = {
     "urir_version": (C.c_int, []),
     "urir_last_error": (C.c_char_p, []),
     "urir_launch_count": (C.c_longlong, [_i]),
+    "urir_family_calls": (C.c_longlong, [_i]),
+    "urir_family_name": (C.c_char_p, [_i]),
     "urir_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_conv2d_dgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_conv2d_wgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "urir_conv_path": (_i, [C.POINTER(ConvDesc), _i]),
     "urir_set_pdl": (_i, [_i]),
+    "urir_set_deterministic": (_i, [_i]),
     "urir_l2_reg_batched": (_i, [_vp, _i, _f, _vp, _vp]),
     "urir_weight_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "urir_weight_prep_up2": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -67,6 +70,8 @@ _PROTOS = {
     "urir_ampphase_loss": (_i, [_vp, _vp, _ll, _f, _f, _i, _vp, _vp, _vp, _i, _vp]),
     "urir_adam": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _f, _f, _vp]),
     "urir_sgd": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "urir_nadam": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _f, _f, _f, _vp]),
+    "urir_lamb": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     "urir_step_increment": (_i, [_vp, _vp]),
     "urir_axpy": (_i, [_vp, _vp, _f, _ll, _vp]),
     "urir_sumsq": (_i, [_vp, _ll, _f, _vp, _i, _vp]),
@@ -117,8 +122,24 @@ def ptr(t) -> int | None:
     return t.data_ptr()
 
 
+def set_deterministic(enabled: bool) -> bool:
+    """Fixed-order cross-CTA reductions (bit-identical reruns; slower). Returns the previous setting. CUDA graphs
+    captured before the switch keep the mode they were captured in."""
+    return bool(load().urir_set_deterministic(1 if enabled else 0))
+
+
 def launch_count(kind: int = 0) -> int:
     return int(load().urir_launch_count(kind))
+
+
+FAMILIES = ("simt", "igemm", "halo", "halo_s2_fprop", "halo_up2", "thin_gemm", "head_fprop", "wgrad_tc", "wgrad_halo",
+            "wgrad_halo_s2", "thin_wgrad", "deep")
+
+
+def family_calls() -> dict:
+    """name -> number of successful urir_conv2d_* calls served by that kernel family since the library was loaded."""
+    lib = load()
+    return {lib.urir_family_name(i).decode(): int(lib.urir_family_calls(i)) for i in range(len(FAMILIES))}
 
 
 _profile = None     # when a list: every call appends (name, conv-desc-or-None, start_event, end_event)

@@ -41,34 +41,6 @@ def _mean(values):
     return float(np.mean(values))
 
 
-class _KerasNadam:
-    """tf.keras.optimizers.Nadam (Dozat 2015 with Keras' momentum schedule) on the flat buffers.
-    Elementwise torch ops: the Nadam branch (amp_phase_trainer.py:30-31) is not on the measured path."""
-
-    def __init__(self, engine, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
-        self.e, self.b1, self.b2, self.eps = engine, beta_1, beta_2, epsilon
-        self.t, self.m_schedule = 0, 1.0
-
-    def apply(self, lr):
-        e = self.e
-        self.t += 1
-        t = self.t
-        u_t = self.b1 * (1.0 - 0.5 * 0.96 ** (0.004 * t))
-        u_t1 = self.b1 * (1.0 - 0.5 * 0.96 ** (0.004 * (t + 1)))
-        m_sched_new = self.m_schedule * u_t
-        m_sched_next = m_sched_new * u_t1
-        self.m_schedule = m_sched_new
-        g = e.G
-        e.M.mul_(self.b1).add_(g, alpha=1 - self.b1)
-        e.V.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
-        g_prime = g / (1.0 - m_sched_new)
-        m_prime = e.M / (1.0 - m_sched_next)
-        v_prime = e.V / (1.0 - self.b2 ** t)
-        m_bar = (1.0 - u_t) * g_prime + u_t1 * m_prime
-        e.P.sub_(lr * m_bar / (v_prime.sqrt() + self.eps))
-        e.refresh_operands()
-
-
 class Trainer:
 
     def __init__(self, alpha, n_epochs, optimizer, callbacks, lr_exp_decay, lr0, file_name):
@@ -97,7 +69,6 @@ class Trainer:
         else:
             raise ValueError(f"optimizer must contain 'nadam', 'sgd' or 'adam', got {optimizer!r}")
         self.learning_rate = lr0
-        self._nadam = None
         self._graphs = {}
         self.use_cuda_graph = True
         self.dropout = True
@@ -188,6 +159,8 @@ class Trainer:
             eng.adam_step()
         elif self.optimizer == 'sgd':
             eng.sgd_step()
+        else:
+            eng.nadam_step()
 
     def prefetch(self, spec_in, spec_out, emb, model):
         """Optional: start the host -> device copy of the NEXT batch (same argument order as step) on a copy
@@ -205,12 +178,8 @@ class Trainer:
             spec_out = _dev_tensor(spec_out, torch.float32, dev)
             emb = _dev_tensor(emb, torch.int32, dev)
             eng.stage(spec_in, emb, spec_out)
-        if self.optimizer == 'nadam':
-            self._device_step(eng, B)
-            if self._nadam is None:
-                self._nadam = _KerasNadam(eng)
-            self._nadam.apply(self.learning_rate)
-        elif not self.use_cuda_graph:
+        eng.sync_operands()              # the masters may have been changed through torch since the last refresh
+        if not self.use_cuda_graph:
             self._device_step(eng, B)
         else:
             key = (id(eng), B, self.optimizer, self.dropout)
@@ -307,48 +276,32 @@ class History(object):
 
 def plot_graphs(x1=None, y1=None, x2=None, y2=None, x3=None, y3=None, x4=None, y4=None, label1='', label2='',
                 label3='', label4='', filename='./Graphic.png'):
-    import matplotlib.pyplot as plt      # lazy: matplotlib is optional here
-    if x1 is None:
-        x1 = np.arange(0, len(y1))
-    if y2 is not None and x2 is None:
-        x2 = np.arange(0, len(y2))
-    if y3 is not None and x3 is None:
-        x3 = np.arange(0, len(y3))
-    if y4 is not None and x4 is None:
-        x4 = np.arange(0, len(y4))
-    plt.style.use("ggplot")
-    plt.figure()
-    plt.plot(x1, y1, label=label1)
-    for xx, yy, ll in ((x2, y2, label2), (x3, y3, label3), (x4, y4, label4)):
-        if yy is not None:
-            plt.plot(xx, yy, label=ll)
-    plt.title("Graphic")
-    plt.xlabel("Epoch ")
-    plt.ylabel("Loss")
-    plt.legend()
-    plt.savefig(filename)
-    plt.close()
+    """Up to four labelled loss curves over epochs into one PNG (the helper of amp_phase_trainer.py:246-275; same
+    signature). A missing x axis becomes 0..len(y)-1. matplotlib is imported on use: it is optional here."""
+    import matplotlib.pyplot as plt
+    curves = [(x, y, lab) for x, y, lab in ((x1, y1, label1), (x2, y2, label2), (x3, y3, label3), (x4, y4, label4))
+              if y is not None]
+    with plt.style.context("ggplot"):
+        fig, ax = plt.subplots()
+        for x, y, lab in curves:
+            ax.plot(np.arange(len(y)) if x is None else x, y, label=lab)
+        ax.set(title="Graphic", xlabel="Epoch ", ylabel="Loss")
+        ax.legend()
+        fig.savefig(filename)
+        plt.close(fig)
 
 
 def params_saver(file_name, batch_size, optimizer, criterion, lr, BatchNorm, normalization, epochs,
                  callbacks, alpha, beta, number_filters_0):
-    params = {}
-    params['batch_size'] = batch_size
-    params['optimizer'] = str(optimizer)
-    params['criterion'] = str(criterion)
-    params['epochs'] = epochs
-    params['lr'] = lr
-    params['alpha'] = alpha
-    params['beta'] = beta
-    params['batch_norm'] = BatchNorm
-    params['normalization'] = normalization
-    params['number_filters_0'] = number_filters_0
-    params['val_loss'] = float(callbacks[0].val_loss_min)
-    params['train_loss'] = float(callbacks[0].train_loss_min)
-    params['patience'] = callbacks[1].patience
-
+    """Writes <file_name>/hiperparametros.json with the run's hyper-parameters and the best losses the checkpoint
+    callback saw (amp_phase_trainer.py:278-297: same file name, same keys)."""
+    checkpoint, early_stop = callbacks[0], callbacks[1]
+    record = dict(batch_size=batch_size, optimizer=str(optimizer), criterion=str(criterion), epochs=epochs, lr=lr,
+                  alpha=alpha, beta=beta, batch_norm=BatchNorm, normalization=normalization,
+                  number_filters_0=number_filters_0, val_loss=float(checkpoint.val_loss_min),
+                  train_loss=float(checkpoint.train_loss_min), patience=early_stop.patience)
     with open(file_name + '/hiperparametros.json', 'w') as fp:
-        json.dump(params, fp)
+        json.dump(record, fp)
 
 
 def rmse_coef(y_true, y_pred):

@@ -24,7 +24,48 @@ bool pdl_enabled() {
     if (v < 0) { const char* e = getenv("URIR_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; g_pdl.store(v); }
     return v == 1;
 }
+int sm_count() {
+    static std::atomic<int> n{0};
+    int v = n.load();
+    if (v <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = 4 * 37;                     // no device visible (host-side queries in the CPU test suite): B200's count
+        cudaGetLastError();
+        n.store(v);
+    }
+    return v;
+}
+
+// deterministic mode: see urir_common.cuh
+static std::atomic<int> g_det{-1};
+bool deterministic() {
+    int v = g_det.load();
+    if (v < 0) { const char* e = getenv("URIR_DETERMINISTIC"); v = (e && e[0] == '1') ? 1 : 0; g_det.store(v); }
+    return v == 1;
+}
+constexpr int GATE_SLOTS = 4096;
+__device__ unsigned int g_gate_slots[GATE_SLOTS];
+unsigned int* next_gate() {
+    if (!deterministic()) return nullptr;
+    static unsigned int* base = nullptr;
+    static std::atomic<unsigned int> next{0};
+    if (base == nullptr) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_gate_slots) != cudaSuccess) return nullptr;
+        base = static_cast<unsigned int*>(p);
+    }
+    return base + (next.fetch_add(1) % GATE_SLOTS);
+}
 void count_launch(int kind) { g_launches_all++; if (kind == 1) g_launches_tc++; }
+
+// per-kernel-family call counters of the convolution entry points (urir_family_calls): parity tests assert through them
+// that the dispatch they exercised is the one the benchmark times (halo / stride-2 halo / up-2 / deep / ...)
+static const char* const g_family_names[URIR_FAM_COUNT] = {
+    "simt", "igemm", "halo", "halo_s2_fprop", "halo_up2", "thin_gemm", "head_fprop", "wgrad_tc", "wgrad_halo",
+    "wgrad_halo_s2", "thin_wgrad", "deep"};
+static std::atomic<long long> g_family_calls[URIR_FAM_COUNT];
+static inline int fam(int family, int rc) { if (rc == URIR_OK) g_family_calls[family]++; return rc; }
 
 // implemented in the other translation units
 int conv_fprop_simt_dispatch(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
@@ -66,6 +107,9 @@ int channel_sum(const void*, int, long long, int, int, int, float*, cudaStream_t
 int ampphase_loss(const float*, const float*, long long, float, float, int, float*, float*, void*, int, cudaStream_t);
 int adam(float*, const float*, float*, float*, long long, const float*, const int*, float, float, float, cudaStream_t);
 int sgd(float*, const float*, long long, const float*, cudaStream_t);
+int nadam(float*, const float*, float*, float*, long long, const float*, const int*, float*, float, float, float, cudaStream_t);
+int lamb(float*, const float*, float*, float*, float*, const long long*, int, float*, const float*, const int*, float, float,
+         float, float, cudaStream_t);
 int step_increment(int*, cudaStream_t);
 int axpy(float*, const float*, float, long long, cudaStream_t);
 int sumsq(const float*, long long, float, float*, int, cudaStream_t);
@@ -111,8 +155,11 @@ extern "C" {
 
 int urir_version(void) { return URIR_VERSION; }
 const char* urir_last_error(void) { return g_err; }
+int urir_set_deterministic(int enabled) { const int prev = deterministic() ? 1 : 0; g_det.store(enabled ? 1 : 0); return prev; }
 int urir_set_pdl(int enabled) { const int prev = pdl_enabled() ? 1 : 0; g_pdl.store(enabled ? 1 : 0); return prev; }
 long long urir_launch_count(int kind) { return kind == 1 ? g_launches_tc.load() : g_launches_all.load(); }
+long long urir_family_calls(int family) { return (family >= 0 && family < URIR_FAM_COUNT) ? g_family_calls[family].load() : -1; }
+const char* urir_family_name(int family) { return (family >= 0 && family < URIR_FAM_COUNT) ? g_family_names[family] : ""; }
 
 int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, const void* w_kc, const float* bias,
                       void* y, float* stats, void* stream) {
@@ -120,20 +167,21 @@ int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, 
     URIR_CHECK_ARG(x && y, "conv2d_fprop: null tensor");
     cudaStream_t st = (cudaStream_t)stream;
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && thin_supported(d, 0))
-        return thin_gemm(d, x, w_ck, bias, y, true, st);                       // the 2-channel stem
+        return fam(URIR_FAM_THIN_GEMM, thin_gemm(d, x, w_ck, bias, y, true, st));                       // the 2-channel stem
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && head_fprop_supported(d))
-        return head_fprop(d, x, w_ck, bias, y, st);                            // the 2-channel head
+        return fam(URIR_FAM_HEAD_FPROP, head_fprop(d, x, w_ck, bias, y, st));                            // the 2-channel head
     if (w_kc && d->stride == 2 && d->impl != URIR_IMPL_SIMT && d->impl != URIR_IMPL_TC && !env_force_simt() &&
         halo_s2_fprop_supported(d, d->impl == URIR_IMPL_HALO))
-        return conv_halo_s2_fprop(d, x, w_kc, bias, y, stats, st);
+        return fam(URIR_FAM_HALO_S2_FPROP, conv_halo_s2_fprop(d, x, w_kc, bias, y, stats, st));
     if (d->impl == URIR_IMPL_HALO && !(w_kc && halo_supported(d, 0, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the halo-tile tcgen05 path");
     if (w_kc && ((d->impl == URIR_IMPL_HALO) || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && halo_supported(d, 0, false))))
-        return conv_halo(d, 0, x, w_kc, bias, y, stats, st);
+        return fam(URIR_FAM_HALO, conv_halo(d, 0, x, w_kc, bias, y, stats, st));
     const bool tc_ok = igemm_fprop_supported(d) && w_kc != nullptr;
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
-    return use_tc ? conv_fprop_igemm(d, x, w_kc, bias, y, stats, st) : conv_fprop_simt_dispatch(d, x, w_ck, bias, y, stats, st);
+    return use_tc ? fam(URIR_FAM_IGEMM, conv_fprop_igemm(d, x, w_kc, bias, y, stats, st))
+                  : fam(URIR_FAM_SIMT, conv_fprop_simt_dispatch(d, x, w_ck, bias, y, stats, st));
 }
 
 int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck, const void* w_kc, const float* bias,
@@ -143,40 +191,41 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
     URIR_CHECK_ARG(d->act == URIR_ACT_NONE, "conv2d_dgrad: activation not supported");
     cudaStream_t st = (cudaStream_t)stream;
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && !bias && thin_supported(d, 1))
-        return thin_gemm(d, dy, w_ck, nullptr, dx, false, st);                 // the 2-channel head
+        return fam(URIR_FAM_THIN_GEMM, thin_gemm(d, dy, w_ck, nullptr, dx, false, st));                 // the 2-channel head
     if (d->impl == URIR_IMPL_HALO && !(w_ck && halo_supported(d, 1, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the halo-tile tcgen05 path");
     if (w_ck && ((d->impl == URIR_IMPL_HALO) || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && halo_supported(d, 1, false))))
-        return conv_halo(d, 1, dy, w_ck, bias, dx, stats, st);
+        return fam(URIR_FAM_HALO, conv_halo(d, 1, dy, w_ck, bias, dx, stats, st));
     const bool tc_ok = igemm_dgrad_supported(d) && w_ck != nullptr;
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
-    return use_tc ? conv_dgrad_igemm(d, dy, w_ck, bias, dx, stats, st) : conv_dgrad_simt_dispatch(d, dy, w_kc, bias, dx, stats, st, w_ck);
+    return use_tc ? fam(URIR_FAM_IGEMM, conv_dgrad_igemm(d, dy, w_ck, bias, dx, stats, st))
+                  : fam(URIR_FAM_SIMT, conv_dgrad_simt_dispatch(d, dy, w_kc, bias, dx, stats, st, w_ck));
 }
 
 int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
     int rc = check_conv(d, "conv2d_wgrad"); if (rc) return rc;
     URIR_CHECK_ARG(x && dy && dw, "conv2d_wgrad: null tensor");
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && thin_supported(d, 2)) return thin_wgrad(d, x, dy, dw, st);
+    if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && thin_supported(d, 2)) return fam(URIR_FAM_THIN_WGRAD, thin_wgrad(d, x, dy, dw, st));
     if (d->stride == 2 && (d->impl == URIR_IMPL_HALO || (d->impl == URIR_IMPL_AUTO && !env_force_simt())) &&
         wgrad_halo_s2_supported(d, d->impl == URIR_IMPL_HALO))
-        return conv_wgrad_halo_s2(d, x, dy, dw, st);
+        return fam(URIR_FAM_WGRAD_HALO_S2, conv_wgrad_halo_s2(d, x, dy, dw, st));
     if (d->impl == URIR_IMPL_HALO && !wgrad_halo_supported(d, true))
         return fail(URIR_ERR_UNSUP, "conv2d_wgrad: shape not supported by the halo-tile tcgen05 path");
     if (d->impl == URIR_IMPL_HALO || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && wgrad_halo_supported(d, false)))
-        return conv_wgrad_halo(d, x, dy, dw, st);
+        return fam(URIR_FAM_WGRAD_HALO, conv_wgrad_halo(d, x, dy, dw, st));
     const bool tc_ok = wgrad_tc_supported(d);
     if (d->impl == URIR_IMPL_TC && !tc_ok) return fail(URIR_ERR_UNSUP, "conv2d_wgrad: shape not supported by the tcgen05 path");
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
-    return use_tc ? conv_wgrad_tc(d, x, dy, dw, st) : conv_wgrad_simt_dispatch(d, x, dy, dw, st);
+    return use_tc ? fam(URIR_FAM_WGRAD_TC, conv_wgrad_tc(d, x, dy, dw, st)) : fam(URIR_FAM_SIMT, conv_wgrad_simt_dispatch(d, x, dy, dw, st));
 }
 
 int urir_conv2d_dgrad_up2(const urir_conv_desc* d, const void* dy, const void* w_up2, const float* bias, void* dx, void* stream) {
     int rc = check_conv(d, "conv2d_dgrad_up2"); if (rc) return rc;
     URIR_CHECK_ARG(dy && dx && w_up2, "conv2d_dgrad_up2: null tensor");
     if (!halo_up2_supported(d)) return fail(URIR_ERR_UNSUP, "conv2d_dgrad_up2: shape not supported (3x3 stride 2 on an even input, 4C <= 512, resident weights)");
-    return conv_halo_up2(d, dy, w_up2, bias, dx, (cudaStream_t)stream);
+    return fam(URIR_FAM_HALO_UP2, conv_halo_up2(d, dy, w_up2, bias, dx, (cudaStream_t)stream));
 }
 int urir_weight_prep_up2(const float* w_hwio, void* w_up2, int C, int K, void* stream) {
     URIR_CHECK_ARG(w_hwio && w_up2 && C > 0 && K > 0, "weight_prep_up2: bad args");
@@ -282,6 +331,18 @@ int urir_adam(float* p, const float* g, float* m, float* v, long long n, const f
               float beta1, float beta2, float eps, void* stream) {
     URIR_CHECK_ARG(p && g && m && v && lr_dev && step_dev, "adam: null tensor");
     return adam(p, g, m, v, n, lr_dev, step_dev, beta1, beta2, eps, (cudaStream_t)stream);
+}
+int urir_nadam(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, const int32_t* step_dev,
+               float* coef_dev, float beta1, float beta2, float eps, void* stream) {
+    URIR_CHECK_ARG(p && g && m && v && lr_dev && step_dev && coef_dev && n > 0, "nadam: bad args");
+    return nadam(p, g, m, v, n, lr_dev, step_dev, coef_dev, beta1, beta2, eps, (cudaStream_t)stream);
+}
+int urir_lamb(float* p, const float* g, float* m, float* v, float* upd, const int64_t* table_dev, int n_vars, float* norms,
+              const float* lr_dev, const int32_t* step_dev, float beta1, float beta2, float eps, float weight_decay,
+              void* stream) {
+    URIR_CHECK_ARG(p && g && m && v && upd && table_dev && norms && lr_dev && step_dev && n_vars > 0, "lamb: bad args");
+    return lamb(p, g, m, v, upd, reinterpret_cast<const long long*>(table_dev), n_vars, norms, lr_dev, step_dev, beta1,
+                beta2, eps, weight_decay, (cudaStream_t)stream);
 }
 int urir_sgd(float* p, const float* g, long long n, const float* lr_dev, void* stream) {
     URIR_CHECK_ARG(p && g && lr_dev && n > 0, "sgd: bad args");

@@ -18,6 +18,7 @@
 // Epilogue as in conv_igemm.cu: +bias, per-channel sum / sum of squares (BatchNorm statistics or bias
 // gradients), bf16, 32-byte stores into the (possibly channel-sliced) NHWC destination.
 #include <stdlib.h>
+#include <atomic>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -52,6 +53,7 @@ struct HaloParams {
     int bias_mod;               // bias index = GEMM-N column % bias_mod (the 4 parity classes of an up-2 layer share it)
     int accumulate;             // out += result (fp32 add before the bf16 rounding)
     int grp_off[16];            // output element offset of every 32-column group of GEMM-N (channel / parity placement)
+    unsigned int* gate;         // deterministic mode: CTAs commit their statistics in blockIdx order (urir_common.cuh)
     int debug;                  // URIR_HALO_DEBUG: 1 no global stores, 2 no epilogue math/stores, 3 no MMAs, 4 no TMA loads (timing experiments)
     long long* trace;           // debug (URIR_HALO_TRACE): clock64 stamps of CTA 0, 8 per tile, first 128 tiles
     short tap_row[36];          // first box row of tap t = dw * PH + dh
@@ -395,25 +397,38 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             if (tre) p.trace[it * 8 + 5] = clock64();
         }
         if (want_stats) {
+            float s1[NB], s2[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const float s1 = hl_halve_tail<HS>(acc1 + b * PART, lane);
-                const float s2 = hl_halve_tail<HS>(acc2 + b * PART, lane);
-                if ((lane & 1) == 0) {
-                    const int col = b * 16 + hl_col_of_lane(lane);
-                    atomicAdd(sstats + col, s1);
-                    atomicAdd(sstats + BLOCK_N + col, s2);
+                s1[b] = hl_halve_tail<HS>(acc1 + b * PART, lane);
+                s2[b] = hl_halve_tail<HS>(acc2 + b * PART, lane);
+            }
+            // the NG * 4 epilogue warps fold their column sums into shared memory one warp at a time (fixed order:
+            // no floating-point atomics, the result does not depend on warp timing); once per kernel
+            const int me = eg * 4 + quarter;
+#pragma unroll 1
+            for (int turn = 0; turn < NG * 4; ++turn) {
+                if (turn == me && (lane & 1) == 0) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const int col = b * 16 + hl_col_of_lane(lane);
+                        sstats[col] += s1[b];
+                        sstats[BLOCK_N + col] += s2[b];
+                    }
                 }
+                gate_bar(1, NG * 4 * 32);
             }
         }
     }
     __syncthreads();
     if (p.stats) {
+        gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
         for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) {
             const int which = i / BLOCK_N, col = i % BLOCK_N;
             if (n_tile * BLOCK_N + col < p.n_total)
                 atomicAdd(p.stats + which * p.n_total + n_tile * BLOCK_N + col, sstats[i]);
         }
+        gate_leave(p.gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
     }
     if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
     if (p.trace && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 148) {
@@ -462,15 +477,15 @@ bool halo_supported(const urir_conv_desc* d, int op, bool forced) {
     if (BN < 64 && BN < ng && !forced) return false;      // 44-cycle N = 32 MMAs over several N tiles do not pay
     // worth it only where the one-tile-per-CTA kernel is latency / L2 bound: many tiles per SM
     const long long tiles = (long long)d->N * cdiv(d->H, HL_TH) * cdiv(d->W, HL_TW);
-    return forced || tiles >= 148 * 4;
+    return forced || tiles >= sm_count() * 4;
 }
 
 template <int BN, int BK, bool ACC = false, int NG = 2, bool RELU = false>
 static int launch_halo(const HaloMaps& maps, const HaloParams& p, int n_tiles, int smem, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};    // benign if two threads both set the attribute
     auto kern = conv_halo_kernel<BN, BK, ACC, NG, RELU>;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BUDGET + 4096)); attr_set = true; }
-    int gx = 148 / n_tiles; if (gx < 1) gx = 1;
+    int gx = sm_count() / n_tiles; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     dim3 grid(gx, n_tiles);
     URIR_CUDA_OK(launch_pdl(kern, grid, dim3(NG == 4 ? 640 : 384), smem, st, maps, p));
@@ -500,7 +515,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     halo_fix_stages(p);
     if (p.stages < 2) return fail(URIR_ERR_UNSUP, "halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
     p.o_sn = (long long)d->H * d->W * o_ld; p.o_sh = (long long)d->W * o_ld; p.o_sw = o_ld; p.o_off = o_coff;
-    p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)out; p.n_total = ng;
+    p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)out; p.n_total = ng; p.gate = stats ? next_gate() : nullptr;
     p.bias_mod = ng; p.accumulate = 0;
     for (int g = 0; g < 16; ++g) p.grp_off[g] = 32 * g;
     { const char* e = getenv("URIR_HALO_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr; }
@@ -645,7 +660,7 @@ bool halo_s2_fprop_supported(const urir_conv_desc* d, bool forced) {
         if (9LL * d->C * bn * 2 + 3 * stage + 2048 <= HL_SMEM_BUDGET) { BN = bn; break; }
     if (BN == 0 || (BN < 64 && BN < d->K)) return false;
     const long long tiles = (long long)d->N * cdiv(d->P, HL_TH) * cdiv(d->Q, HL_TW);
-    return forced || tiles >= 148 * 4;
+    return forced || tiles >= sm_count() * 4;
 }
 
 int conv_halo_s2_fprop(const urir_conv_desc* d, const void* x, const void* w_kc, const float* bias, void* y, float* stats,
@@ -669,7 +684,7 @@ int conv_halo_s2_fprop(const urir_conv_desc* d, const void* x, const void* w_kc,
     p.stages = (HL_SMEM_BUDGET - 2048 - p.w_bytes) / p.a_stage_bytes;
     halo_fix_stages(p);
     p.o_sn = (long long)d->P * d->Q * d->y_ld; p.o_sh = (long long)d->Q * d->y_ld; p.o_sw = d->y_ld; p.o_off = d->y_coff;
-    p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)y; p.n_total = ng;
+    p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)y; p.n_total = ng; p.gate = stats ? next_gate() : nullptr;
     p.bias_mod = ng; p.accumulate = 0;
     for (int g = 0; g < 16; ++g) p.grp_off[g] = 32 * g;
     p.oh0 = 0; p.ow0 = 0;
@@ -717,7 +732,7 @@ __global__ void weight_prep_up2_kernel(const float* __restrict__ w, __nv_bfloat1
 }
 int weight_prep_up2(const float* w, void* out, int C, int K, cudaStream_t st) {
     const long long n = 16LL * C * K;
-    int blocks = cdiv(n, 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    int blocks = cdiv(n, 256); if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     weight_prep_up2_kernel<<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)out, C, K);
     URIR_LAUNCH_OK(0);
     return URIR_OK;

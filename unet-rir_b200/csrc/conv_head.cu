@@ -13,6 +13,7 @@
 // Warp roles (192 threads, persistent, one CTA per SM): warps 0-3 epilogue (TMEM lane quarter = warp),
 // warp 4 TMA producer, warp 5 MMA issuer; 3 smem stages; two TMEM accumulator stages of 4 x 16 columns so
 // the epilogue of region i overlaps the MMAs of region i+1.
+#include <atomic>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -191,9 +192,9 @@ int head_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, const f
         if (rc) return rc;
     }
     const int smem = 8192 + HF_STAGES * p.stage_bytes + 128 + 1024;
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};    // benign if two threads both set the attribute
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(head_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 + HF_STAGES * 21 * HF_ROWB + 128 + 1024)); attr_set = true; }
-    const int grid = p.total < 148 ? p.total : 148;
+    const int grid = p.total < sm_count() ? p.total : sm_count();
     head_fprop_kernel<<<grid, 192, smem, st>>>(map, p);
     URIR_LAUNCH_OK(1);
     return URIR_OK;

@@ -19,6 +19,8 @@
 // or bias gradients; warp transpose-reduce, smem atomics, one global atomic per channel per CTA)
 // -> bf16 -> 32-byte stores straight into the (possibly channel-sliced = concat, possibly
 // parity-strided) NHWC destination.
+#include <stdlib.h>
+#include <atomic>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -45,6 +47,7 @@ struct IgemmParams {
     int n_total;                    // Ngemm (valid output channels; may be < gridDim.y * BLOCK_N)
     int out_f32;                    // 1: fp32 output (head), columns stored individually
     int act;                        // URIR_ACT_SIGMOID only with out_f32; URIR_ACT_RELU (bf16 output, inference)
+    unsigned int* gate;             // deterministic mode: CTAs commit their statistics in blockIdx order (urir_common.cuh)
     IgemmTap taps[36];
 };
 
@@ -58,7 +61,7 @@ struct IgemmSmem {
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFF = TILE_BYTES;                      // full[S], empty[S], tmem_full
     static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 8;   // + tmem ptr slot
-    static constexpr int TOTAL = STAT_OFF + 2 * BLOCK_N * 4 + 1024;  // + alignment slack
+    static constexpr int TOTAL = STAT_OFF + 4 * 2 * BLOCK_N * 4 + 1024;  // per-epilogue-warp statistics + alignment slack
 };
 
 // sum 16 per-lane values across the 32 lanes of a warp: after the call lanes with (lane&1)==0
@@ -118,7 +121,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
         prefetch_tmap(&maps.b);
         prefetch_tmap(&maps.a[0]);
     }
-    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) sstats[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 2 * BLOCK_N; i += blockDim.x) sstats[i] = 0.f;
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -231,10 +234,10 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
                     for (int j = 0; j < 16; ++j) q[j] = v[j] * v[j];
                     const float s1 = warp_colsum16(v, lane);
                     const float s2 = warp_colsum16(q, lane);
-                    if ((lane & 1) == 0) {
+                    if ((lane & 1) == 0) {      // one tile per CTA: every (warp, column) slot is written exactly once
                         const int col = c0 + col_of_lane(lane);
-                        atomicAdd(sstats + col, s1);
-                        atomicAdd(sstats + BLOCK_N + col, s2);
+                        sstats[warp * 2 * BLOCK_N + col] = s1;
+                        sstats[warp * 2 * BLOCK_N + BLOCK_N + col] = s2;
                     }
                 }
             }
@@ -242,12 +245,18 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant_
         }
     }
     __syncthreads();
-    if (p.stats && tile_live) {
-        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) {
-            const int which = i / BLOCK_N, col = i % BLOCK_N;
-            if (n_tile * BLOCK_N + col < p.n_total)
-                atomicAdd(p.stats + which * p.n_total + n_tile * BLOCK_N + col, sstats[i]);
+    if (p.stats) {
+        gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
+        if (tile_live) {
+            for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) {
+                const int which = i / BLOCK_N, col = i % BLOCK_N;
+                // the four epilogue warps' partial sums, added in a fixed order
+                const float v = (sstats[i] + sstats[2 * BLOCK_N + i]) + (sstats[4 * BLOCK_N + i] + sstats[6 * BLOCK_N + i]);
+                if (n_tile * BLOCK_N + col < p.n_total)
+                    atomicAdd(p.stats + which * p.n_total + n_tile * BLOCK_N + col, v);
+            }
         }
+        gate_leave(p.gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
     }
     if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
@@ -283,9 +292,19 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
     const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    // L2 promotion: a tensor that is a channel SLICE of a wider NHWC buffer (skip-concat halves: innermost extent
+    // narrower than the pixel pitch) must not promote its fetches past the slice, or every box drags the other
+    // half of the buffer through DRAM (ncu, round 1: 188.9 MB read for 94.4 MB of operand). Dense tensors keep 256 B.
+    const uint64_t inner_bytes = dims[0] * 2;
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (rank > 1 && inner_bytes < strides_bytes[0])
+        promo = inner_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : inner_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+              : inner_bytes >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    { static int force = -2; if (force == -2) { const char* e = getenv("URIR_TMA_PROMO"); force = e ? atoi(e) : -1; }
+      if (force == 0) promo = CU_TENSOR_MAP_L2_PROMOTION_NONE; else if (force == 64) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+      else if (force == 128) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B; else if (force == 256) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B; }
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(URIR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]",
                     (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
@@ -316,7 +335,7 @@ static int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 template <int BLOCK_N, int BLOCK_K, int STAGES>
 static int launch_cfg(const IgemmMaps& maps, const IgemmParams& p, int n_tiles, cudaStream_t st) {
     using L = IgemmSmem<BLOCK_N, BLOCK_K, STAGES>;
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};    // benign if two threads both set the attribute
     auto kern = conv_igemm_kernel<BLOCK_N, BLOCK_K, STAGES>;
     if (!attr_set) {
         URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -368,7 +387,7 @@ int conv_fprop_igemm(const urir_conv_desc* d, const void* x, const void* w_kc, c
     p.NB = d->N; p.n_classes = 1; p.cls_OW[0] = d->Q; p.cls_OH[0] = d->P; p.cls_off[0] = d->y_coff;
     p.o_sn = (long long)d->P * d->Q * d->y_ld; p.o_sh = (long long)d->Q * d->y_ld; p.o_sw = d->y_ld;
     p.kchunks = (d->C + BK - 1) / BK; p.accumulate = d->accumulate; p.bias = bias; p.stats = stats;
-    p.out = y; p.n_total = d->K;
+    p.out = y; p.n_total = d->K; p.gate = stats ? next_gate() : nullptr;
     const int s = d->stride;
     const char* xb = (const char*)x + (size_t)d->x_coff * 2;
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
@@ -419,7 +438,7 @@ int conv_dgrad_igemm(const urir_conv_desc* d, const void* dy, const void* w_ck, 
     p.NB = d->N; p.n_classes = s * s;
     p.o_sn = (long long)d->H * d->W * d->x_ld; p.o_sh = (long long)s * d->W * d->x_ld; p.o_sw = (long long)s * d->x_ld;
     p.kchunks = (d->K + BK - 1) / BK; p.accumulate = d->accumulate; p.bias = bias; p.stats = stats;
-    p.out = dx; p.n_total = d->C;
+    p.out = dx; p.n_total = d->C; p.gate = stats ? next_gate() : nullptr;
     int nt = 0;
     for (int pi = 0; pi < s; ++pi)
         for (int pj = 0; pj < s; ++pj) {

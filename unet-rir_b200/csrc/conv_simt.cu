@@ -219,7 +219,7 @@ static int launch_wgrad(const ConvP& p, const void* x, const void* dy, float* dw
     int CT = 256 / KT; if (CT > p.C) CT = p.C;
     const int tiles = p.R * p.S * cdiv(p.C, CT) * cdiv(p.K, KT);
     // enough pixel chunks to fill the machine a few times over, but >= 256 pixels per block
-    long long want_chunks = (148LL * 8 + tiles - 1) / tiles;
+    long long want_chunks = ((long long)sm_count() * 8 + tiles - 1) / tiles;
     long long pix = (M + want_chunks - 1) / want_chunks;
     if (pix < 256) pix = 256;
     if (pix > M) pix = M;
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) weight_prep_batched_kernel(const long lon
 
 int weight_prep_batched(const long long* table_dev, int n_entries, cudaStream_t st) {
     URIR_CHECK_ARG(n_entries <= WP_MAX_ENTRIES, "weight_prep_batched: at most %d entries", WP_MAX_ENTRIES);
-    weight_prep_batched_kernel<<<148 * 8, 256, 0, st>>>(table_dev, n_entries);
+    weight_prep_batched_kernel<<<sm_count() * 8, 256, 0, st>>>(table_dev, n_entries);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
@@ -436,14 +436,14 @@ __global__ void __launch_bounds__(256) weight_fold_bn_batched_kernel(const long 
 }
 int weight_fold_bn_batched(const long long* table_dev, int n_entries, cudaStream_t st) {
     URIR_CHECK_ARG(n_entries <= WP_MAX_ENTRIES, "weight_fold_bn_batched: at most %d entries", WP_MAX_ENTRIES);
-    weight_fold_bn_batched_kernel<<<148 * 8, 256, 0, st>>>(table_dev, n_entries);
+    weight_fold_bn_batched_kernel<<<sm_count() * 8, 256, 0, st>>>(table_dev, n_entries);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
 
 int weight_prep(const float* w, void* w_ck, void* w_kc, int taps, int C, int K, cudaStream_t st) {
     const long long n = (long long)taps * C * K;
-    int blocks = cdiv(n, 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    int blocks = cdiv(n, 256); if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     weight_prep_kernel<<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)w_ck, (__nv_bfloat16*)w_kc, taps, C, K);
     URIR_LAUNCH_OK(0);
     return URIR_OK;

@@ -230,7 +230,7 @@ int stem_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     const long long M = (long long)p.N * p.P * p.Q;
     const int J = p.R * p.S * p.C;
     if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)J * p.K, st));
-    long long chunks = 148LL * 8 / (p.K / STEM_KT);
+    long long chunks = (long long)sm_count() * 8 / (p.K / STEM_KT);
     long long pix = (M + chunks - 1) / chunks;
     if (pix < 64) pix = 64;
     dim3 grid(cdiv(M, pix), p.K / STEM_KT);

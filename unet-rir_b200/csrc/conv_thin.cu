@@ -12,6 +12,7 @@
 // (row % 8) -- consumed K-major by thin_gemm and MN-major by thin_wgrad.
 // The head's forward (wide -> thin) lives in conv_head.cu.
 #include <stdlib.h>
+#include <atomic>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -41,6 +42,7 @@ struct ThinParams {
     const __nv_bfloat16* w_ck; const float* bias;
     __nv_bfloat16* out; int out_ld, out_coff;
     float* dw;
+    unsigned int* gate;         // thin_wgrad, deterministic mode: CTAs add into dw in blockIdx order (urir_common.cuh)
     unsigned long long mag_w, mag_h;   // ceil(2^40 / tiles_w), ceil(2^40 / tiles_h): exact division of tile indices < 2^20
     short toff[TH_MAX_TAPS];    // patch pixel index offset of tap t
 };
@@ -326,6 +328,9 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
         if (warp == 0) { umma_commit_elect(bar_done); __syncwarp(); }
         mbar_wait(bar_done, 0);
         fence_after_sync();
+    }
+    gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
+    if (n_iters > 0) {
         const int j = threadIdx.x;                       // accumulator row = (tap, thin channel)
         const int tap = j >> 1, ct = j & 1;
         const bool valid = tap < p.ntaps;
@@ -343,6 +348,7 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
         }
         fence_before_sync();
     }
+    gate_leave(p.gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
     __syncthreads();
     if (warp == 0) { fence_after_sync(); tmem_dealloc(tmem_base, 32); }
 }
@@ -397,7 +403,7 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
     void (*kern)(const ThinParams) = thin_gemm_kernel<0, false>;
     if (ksz == 3) kern = thin_is_x ? thin_gemm_kernel<3, false> : thin_gemm_kernel<3, true>;
     if (ksz == 6) kern = thin_is_x ? thin_gemm_kernel<6, false> : thin_gemm_kernel<6, true>;
-    static bool attr_set[3][2] = {};
+    static std::atomic<bool> attr_set[3][2];
     if (!attr_set[ksz / 3][thin_is_x]) {
         URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         attr_set[ksz / 3][thin_is_x] = true;
@@ -410,7 +416,7 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
     // CTAs. Measured per call (B = 64): stem fprop 49 -> 41 us, head dgrad 75 -> 66 us against 8 / 4 per SM.
     int per_sm = 5;
     { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_GEMM_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0) per_sm = ov; }
-    int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
+    int gx = p.total_tiles < sm_count() * per_sm ? p.total_tiles : sm_count() * per_sm;
     dim3 grid(gx, p.CW_total / 32);
     kern<<<grid, 128, smem, st>>>(p);
     URIR_LAUNCH_OK(1);
@@ -424,7 +430,7 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     const void* wide; int wide_ld, wide_coff, wide_c;
     if (thin_is_x) { p.thin = (const float*)x; p.thin_ld = d->x_ld; p.thin_coff = d->x_coff; wide = dy; wide_ld = d->y_ld; wide_coff = d->y_coff; wide_c = d->K; }
     else { p.thin = (const float*)dy; p.thin_ld = d->y_ld; p.thin_coff = d->y_coff; wide = x; wide_ld = d->x_ld; wide_coff = d->x_coff; wide_c = d->C; }
-    p.dw = dw;
+    p.dw = dw; p.gate = next_gate();
     CUtensorMap map;
     {
         const uint64_t dims[4] = {(uint64_t)wide_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
@@ -437,7 +443,7 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     void (*kern)(const CUtensorMap, const ThinParams) = thin_wgrad_kernel<0, false>;
     if (ksz == 3) kern = thin_is_x ? thin_wgrad_kernel<3, false> : thin_wgrad_kernel<3, true>;
     if (ksz == 6) kern = thin_is_x ? thin_wgrad_kernel<6, false> : thin_wgrad_kernel<6, true>;
-    static bool attr_set[3][2] = {};
+    static std::atomic<bool> attr_set[3][2];
     if (!attr_set[ksz / 3][thin_is_x]) {
         URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
         attr_set[ksz / 3][thin_is_x] = true;
@@ -449,7 +455,7 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     const int smem = 2 * atoms * TH_ATOM + 2 * TW_B_STAGE + TH_PATCH_MAX * 8 + 128 + 1024;
     int per_sm = 2;                                    // more CTAs only add dw reductions (measured slower)
     { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_WGRAD_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0 && atoms == 1) per_sm = ov; }
-    int gx = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
+    int gx = p.total_tiles < sm_count() * per_sm ? p.total_tiles : sm_count() * per_sm;
     dim3 grid(gx, p.CW_total / 32);
     kern<<<grid, 128, smem, st>>>(map, p);
     URIR_LAUNCH_OK(1);

@@ -21,6 +21,7 @@
 // whole pixel range in TMEM and add it into dw with red.global.add.v4.f32 once at the end.
 // Warp roles (192 threads): warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer.
 #include <stdlib.h>
+#include <atomic>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -46,6 +47,7 @@ struct WhaloParams {
     int tmem_cols;
     int debug;                  // URIR_WH_DEBUG: 1 = skip the epilogue adds, 2 = do not rotate the epilogue order
     float* dw;
+    unsigned int* gate;         // deterministic mode: CTAs add into dw in blockIdx order (urir_common.cuh)
 };
 
 struct WhaloMaps { CUtensorMap a; CUtensorMap b; };
@@ -143,9 +145,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhaloMaps maps, const __grid_cons
         }
     } else if (warp < 4) {
         // ===================== epilogue: TMEM -> red.global.add into dw[tap][c][k] =====================
+        if (n_iters > 0) { mbar_wait(tmem_full_bar, 0); fence_after_sync(); }
+        gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 1, 128);
         if (n_iters > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            fence_after_sync();
             const int row = warp * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
             const int slot = row / p.Cc, c = row % p.Cc;
@@ -178,6 +180,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhaloMaps maps, const __grid_cons
             }
             fence_before_sync();
         }
+        gate_leave(p.gate, cta_linear(), cta_count(), threadIdx.x == 0, 1, 128);
     }
     __syncthreads();
     if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
@@ -193,12 +196,12 @@ bool wgrad_halo_supported(const urir_conv_desc* d, bool forced) {
     const long long tiles = (long long)d->N * cdiv(d->H, WH_TH) * cdiv(d->W, WH_TW);
     // measured at 36x40 (960 ragged tiles, K = 128 in two blocks): 41 / 68 us vs 43 / 60 us for conv_wgrad_tc -- no gain,
     // so AUTO keeps this kernel for the two wide levels only
-    return forced || tiles >= 148 * 8;
+    return forced || tiles >= sm_count() * 8;
 }
 
 template <int KN>
 static int launch_wh(const WhaloMaps& maps, const WhaloParams& p, dim3 grid, int smem, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};    // benign if two threads both set the attribute
     auto kern = conv_wgrad_halo_kernel<KN>;
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM_BUDGET + 8192)); attr_set = true; }
     URIR_CUDA_OK(launch_pdl(kern, grid, dim3(192), smem, st, maps, p));
@@ -219,7 +222,7 @@ int conv_wgrad_halo(const urir_conv_desc* d, const void* x, const void* dy, floa
     p.stages = WH_SMEM_BUDGET / p.stage_bytes;
     if (p.stages > WH_MAX_STAGES) p.stages = WH_MAX_STAGES;
     { const int cols = p.n_mma * 3 * KN; p.tmem_cols = cols <= 128 ? 128 : cols <= 256 ? 256 : 512; }
-    p.dw = dw;
+    p.dw = dw; p.gate = next_gate();
     { const char* e = getenv("URIR_WH_DEBUG"); p.debug = e ? atoi(e) : 0; }
     {   // x: dims (C, H, W, N), H the fastest pixel index of the box
         const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->H, (uint64_t)d->W, (uint64_t)d->N};
@@ -237,7 +240,7 @@ int conv_wgrad_halo(const urir_conv_desc* d, const void* x, const void* dy, floa
     }
     if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->C * d->K, st));
     const int n_cblk = d->C / p.Cc, n_kblk = d->K / KN;
-    int gx = 148 / (n_cblk * n_kblk); if (gx < 1) gx = 1;
+    int gx = sm_count() / (n_cblk * n_kblk); if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     dim3 grid(gx, n_cblk, n_kblk);
     const int smem = p.stages * p.stage_bytes + 1024 + (2 * WH_MAX_STAGES + 2) * 8 + 16 + 1024;
@@ -268,6 +271,7 @@ struct WhaloS2Params {
     int stages, stage_bytes, tx_bytes;
     int tmem_cols;
     float* dw;
+    unsigned int* gate;         // deterministic mode (urir_common.cuh)
 };
 struct WhaloS2Maps { CUtensorMap a[4]; CUtensorMap b; };
 
@@ -355,9 +359,9 @@ conv_wgrad_halo_s2_kernel(const __grid_constant__ WhaloS2Maps maps, const __grid
         }
     } else if (warp < 4) {
         // ===================== epilogue =====================
+        if (n_iters > 0) { mbar_wait(tmem_full_bar, 0); fence_after_sync(); }
+        gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 1, 128);
         if (n_iters > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            fence_after_sync();
             const int row = warp * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
             const int j = row >> 5, c = row & 31, ph = j >> 1, pw = j & 1;
@@ -385,6 +389,7 @@ conv_wgrad_halo_s2_kernel(const __grid_constant__ WhaloS2Maps maps, const __grid
             }
             fence_before_sync();
         }
+        gate_leave(p.gate, cta_linear(), cta_count(), threadIdx.x == 0, 1, 128);
     }
     __syncthreads();
     if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
@@ -397,7 +402,7 @@ bool wgrad_halo_s2_supported(const urir_conv_desc* d, bool forced) {
     if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return false;
     if (d->C % 32 || !(d->K == 64 || d->K == 128)) return false;
     const long long tiles = (long long)d->N * cdiv(d->P, WH_TH) * cdiv(d->Q, WH_TW);
-    return forced || tiles >= 148 * 4;
+    return forced || tiles >= sm_count() * 4;
 }
 
 int conv_wgrad_halo_s2(const urir_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
@@ -409,7 +414,7 @@ int conv_wgrad_halo_s2(const urir_conv_desc* d, const void* x, const void* dy, f
     p.stages = WH_SMEM_BUDGET / p.stage_bytes;
     if (p.stages > WH_MAX_STAGES) p.stages = WH_MAX_STAGES;
     p.tmem_cols = p.nh == 1 ? 256 : 512;
-    p.dw = dw;
+    p.dw = dw; p.gate = next_gate();
     for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
             const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->P, (uint64_t)d->Q, (uint64_t)d->N};
@@ -428,11 +433,11 @@ int conv_wgrad_halo_s2(const urir_conv_desc* d, const void* x, const void* dy, f
     }
     if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->C * d->K, st));
     const int n_cblk = d->C / 32;
-    int gx = 148 / n_cblk; if (gx < 1) gx = 1;
+    int gx = sm_count() / n_cblk; if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     dim3 grid(gx, n_cblk);
     const int smem = p.stages * p.stage_bytes + 1024 + (2 * WH_MAX_STAGES + 2) * 8 + 16 + 1024;
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};    // benign if two threads both set the attribute
     if (!attr_set) { URIR_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_halo_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM_BUDGET + 8192)); attr_set = true; }
     URIR_CUDA_OK(launch_pdl(conv_wgrad_halo_s2_kernel, grid, dim3(192), smem, st, maps, p));
     URIR_LAUNCH_OK(1);

@@ -12,6 +12,7 @@
 // pixel tiles (split-K); T accumulators of BLOCK_N columns live in TMEM; the epilogue adds them
 // into dw with vectorised global reductions.
 #include <stdlib.h>
+#include <atomic>
 #include "urir_common.cuh"
 #include "urir_tc.cuh"
 
@@ -39,6 +40,7 @@ struct WgradParams {
     float* dw;
     int direct;                     // 1: a single CTA owns each dw element (no pixel split) -> plain stores, no memset
     long long* trace;               // debug: per-iteration clock64 stamps of CTA (0,0,0) when non-null
+    unsigned int* gate;             // deterministic mode: the pixel splits add into dw in blockIdx order (urir_common.cuh)
     WgradTap taps[36];
 };
 
@@ -189,9 +191,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
         }
     } else if (warp < 4) {
         // ===================== epilogue: TMEM -> red.global.add into dw =====================
+        if (n_iters > 0) { mbar_wait(tmem_full_bar, 0); fence_after_sync(); }
+        gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 1, 128);
         if (n_iters > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            fence_after_sync();
             const int row = warp * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
@@ -229,6 +231,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const __grid_consta
             }
             fence_before_sync();
         }
+        gate_leave(p.gate, cta_linear(), cta_count(), threadIdx.x == 0, 1, 128);
     }
     __syncthreads();
     if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
@@ -256,7 +259,7 @@ static void choose_kbox(int OW, int OH, int NB, int* bw, int* bh, int* bn) {
 
 template <int BLOCK_N>
 static int launch_wg(const WgradMaps& maps, const WgradParams& p, dim3 grid, int smem_bytes, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};    // benign if two threads both set the attribute
     auto kern = conv_wgrad_tc_kernel<BLOCK_N>;
     if (!attr_set) {
         URIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BUDGET + 4096));
@@ -311,7 +314,7 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
     // One wave: as many pixel splits as fit on the machine at once (CTAs per SM follow from the shared-memory
     // footprint). A grid slightly above a whole number of waves (300 CTAs on 296 slots) costs a full extra wave.
     const int ctas_per_sm = smem_bytes <= 113 * 1024 ? 2 : 1;
-    int splits = (148 * ctas_per_sm) / units;
+    int splits = (sm_count() * ctas_per_sm) / units;
     if (splits > p.total_tiles) splits = p.total_tiles;
     if (splits < 1) splits = 1;
     p.tiles_per_cta = cdiv(p.total_tiles, splits);
@@ -353,6 +356,7 @@ int conv_wgrad_tc(const urir_conv_desc* d, const void* x, const void* dy, float*
     // without a pixel split every dw element has exactly one producer (all channel tiles exact): store, do not add
     p.direct = !d->accumulate && splits == 1 && d->K % BN == 0 && (d->K & 3) == 0 && (d->C % 128 == 0 || d->C == m_valid) ? 1 : 0;
     if (!p.direct && !d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)ntaps * d->C * d->K, st));
+    p.gate = p.direct ? nullptr : next_gate();
     dim3 grid(splits, p.n_mtiles * n_ntiles, tap_groups);
     if (BN == 128) return launch_wg<128>(maps, p, grid, smem_bytes, st);
     if (BN == 64) return launch_wg<64>(maps, p, grid, smem_bytes, st);

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff,
                           const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
                           const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
-                          float* __restrict__ sums, long long npix, int C) {
+                          float* __restrict__ sums, long long npix, int C, unsigned int* gate) {
     extern __shared__ float sm[];              // [4C] consts, then [256][17] reduction scratch
     float* cs = sm;
     float* red = sm + 4 * C;
@@ -127,6 +127,7 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int d
     for (int j = 0; j < 8; ++j) { red[threadIdx.x * 17 + j] = a1[j]; red[threadIdx.x * 17 + 8 + j] = a2[j]; }
     __syncthreads();
     // thread t < 2C : sums entry t ; reduce over pixel lanes
+    gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
     for (int t = threadIdx.x; t < 2 * C; t += blockDim.x) {
         const int which = t / C, ch = t % C;
         const int gg = ch >> 3, j = ch & 7;
@@ -134,6 +135,7 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int d
         for (int l = 0; l < lanes; ++l) s += red[(l * G + gg) * 17 + which * 8 + j];
         atomicAdd(sums + t, s);
     }
+    gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
 }
 
 __global__ void __launch_bounds__(256)
@@ -143,7 +145,7 @@ bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy
                          const float* __restrict__ gamma, const float* __restrict__ sums,
                          __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                         long long npix, int C) {
+                         long long npix, int C, unsigned int* gate) {
     extern __shared__ float sm[];   // scale, shift, mean, rstd, a=gamma*rstd, mg, mgx : 7C ; then [256][9] scratch
     const float inv_n = 1.f / (float)npix;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -199,12 +201,14 @@ bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy
 #pragma unroll
         for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = bsum[j];
         __syncthreads();
+        gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
         for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
             const int gg = ch >> 3, j = ch & 7;
             float s = 0.f;
             for (int l = 0; l < 256 / G; ++l) s += red[(l * G + gg) * 9 + j];
             atomicAdd(dbias + ch, s);
         }
+        gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
     }
 }
 
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_bwd_reduce_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff,
                                const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
                                const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
-                               float* __restrict__ sums, long long npix, int C, int g_shift) {
+                               float* __restrict__ sums, long long npix, int C, int g_shift, unsigned int* gate) {
     pdl_sync();
     extern __shared__ float red[];             // [256][17]
     const int G = C >> 3, lanes = 256 >> g_shift;
@@ -295,6 +299,7 @@ bn_relu_bwd_reduce_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x * 17 + j] = a1[j]; red[threadIdx.x * 17 + 8 + j] = a2[j]; }
     __syncthreads();
+    gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
     for (int t = threadIdx.x; t < 2 * C; t += blockDim.x) {
         const int which = t / C, ch = t % C;
         const int gg = ch >> 3, j = ch & 7;
@@ -302,6 +307,7 @@ bn_relu_bwd_reduce_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, 
         for (int l = 0; l < lanes; ++l) s += red[(l * G + gg) * 17 + which * 8 + j];
         atomicAdd(sums + t, s);
     }
+    gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
 }
 
 // dx = a*g + k1*x + k0 with a = gamma*rstd, k1 = -a*rstd*mean(g*xhat), k0 = -k1*mean - a*mean(g)
@@ -313,7 +319,7 @@ bn_relu_bwd_apply_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, i
                               const float* __restrict__ gamma, const float* __restrict__ sums,
                               __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                              long long npix, int C, int g_shift) {
+                              long long npix, int C, int g_shift, unsigned int* gate) {
     pdl_sync();
     extern __shared__ float red[];             // [256][9]
     const int G = C >> 3, lanes = 256 >> g_shift;
@@ -364,12 +370,14 @@ bn_relu_bwd_apply_pow2_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, i
 #pragma unroll
         for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = bsum[j];
         __syncthreads();
+        gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
         for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
             const int gg = ch >> 3, j = ch & 7;
             float s = 0.f;
             for (int l = 0; l < lanes; ++l) s += red[(l * G + gg) * 9 + j];
             atomicAdd(dbias + ch, s);
         }
+        gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
     }
 }
 
@@ -447,7 +455,7 @@ static int pow2_shift(int C) {
 // enough blocks to fill the machine, few enough that the per-block tail (atomics) stays small
 static int pow2_grid(long long npix, int lanes, int unroll, int max_per_sm) {
     long long b = (npix + (long long)lanes * unroll - 1) / ((long long)lanes * unroll);
-    const long long cap = 148LL * max_per_sm;
+    const long long cap = (long long)sm_count() * max_per_sm;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
@@ -455,7 +463,7 @@ static int pow2_grid(long long npix, int lanes, int unroll, int max_per_sm) {
 
 static int grid_for(long long work_items, int threads) {
     long long b = (work_items + threads - 1) / threads;
-    const long long cap = 148LL * 8;
+    const long long cap = (long long)sm_count() * 8;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
@@ -518,16 +526,16 @@ int bn_relu_bwd_reduce(const void* dy, int dy_ld, int dy_coff, const void* x, in
     if (const int gs = pow2_shift(C); gs >= 0) {
         const int ln = 256 >> gs;
         URIR_CUDA_OK(launch_pdl(bn_relu_bwd_reduce_pow2_kernel<4>, dim3(pow2_grid(npix, ln, 8, 2)), dim3(256), 256 * 17 * sizeof(float), st,
-            (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C, gs));
+            (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C, gs, next_gate()));
         URIR_LAUNCH_OK(0);
         return URIR_OK;
     }
     const int lanes = 256 / (C / 8);
     long long blocks = (npix + lanes - 1) / lanes;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     const size_t smem = (4 * C + 256 * 17) * sizeof(float);
     bn_relu_bwd_reduce_kernel<<<(int)blocks, 256, smem, st>>>((const __nv_bfloat16*)dy, dy_ld, dy_coff,
-                                                              (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C);
+                                                              (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, sums, npix, C, next_gate());
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
@@ -544,13 +552,13 @@ int bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int
         const int ln = 256 >> gs;
         URIR_CUDA_OK(launch_pdl(bn_relu_bwd_apply_pow2_kernel<4>, dim3(pow2_grid(npix, ln, 8, 2)), dim3(256), 256 * 9 * sizeof(float), st,
             (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, gamma, sums,
-            (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C, gs));
+            (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C, gs, dbias ? next_gate() : nullptr));
         URIR_LAUNCH_OK(0);
         return URIR_OK;
     }
     bn_relu_bwd_apply_kernel<<<grid_for(npix * (C / 8), 256), 256, (7 * C + 256 * 9) * sizeof(float), st>>>(
         (const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)x, x_ld, x_coff, ss, mr, gamma, sums,
-        (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C);
+        (__nv_bfloat16*)dx, dx_ld, dx_coff, dgamma, dbeta, dbias, npix, C, dbias ? next_gate() : nullptr);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
@@ -560,10 +568,11 @@ int bn_relu_bwd_apply(const void* dy, int dy_ld, int dy_coff, const void* x, int
 // =========================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256)
-channel_sum_kernel(const T* __restrict__ x, long long npix, int C, int ld, int coff, float* __restrict__ out) {
+channel_sum_kernel(const T* __restrict__ x, long long npix, int C, int ld, int coff, float* __restrict__ out, unsigned int* gate) {
     // thread owns channel (threadIdx.x % C) when C <= 256, strides over pixels
     const int lanes = 256 / C > 0 ? 256 / C : 1;
     __shared__ float red[256];
+    gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);     // (deterministic mode serialises the whole CTA body)
     for (int cb = 0; cb < C; cb += 256) {
         const int c = cb + threadIdx.x % (C < 256 ? C : 256);
         const int lane = threadIdx.x / (C < 256 ? C : 256);
@@ -580,6 +589,7 @@ channel_sum_kernel(const T* __restrict__ x, long long npix, int C, int ld, int c
         }
         __syncthreads();
     }
+    gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
 }
 
 int channel_sum(const void* x, int dtype, long long npix, int C, int ld, int coff, float* out, cudaStream_t st) {
@@ -587,9 +597,10 @@ int channel_sum(const void* x, int dtype, long long npix, int C, int ld, int cof
     URIR_CUDA_OK(cudaMemsetAsync(out, 0, C * sizeof(float), st));
     const int lanes = 256 / C > 0 ? 256 / C : 1;
     long long blocks = (npix + lanes - 1) / lanes;
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    if (dtype == URIR_BF16) channel_sum_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, npix, C, ld, coff, out);
-    else channel_sum_kernel<float><<<(int)blocks, 256, 0, st>>>((const float*)x, npix, C, ld, coff, out);
+    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+    unsigned int* gate = next_gate();
+    if (dtype == URIR_BF16) channel_sum_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, npix, C, ld, coff, out, gate);
+    else channel_sum_kernel<float><<<(int)blocks, 256, 0, st>>>((const float*)x, npix, C, ld, coff, out, gate);
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
@@ -601,7 +612,7 @@ int channel_sum(const void* x, int dtype, long long npix, int C, int ld, int cof
 __global__ void __launch_bounds__(256)
 ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ yp, long long npair,
                      long long npix, float w_amp, float w_ph, int sigmoid_bwd, float* __restrict__ losses,
-                     float4* __restrict__ grad, __nv_bfloat16* __restrict__ grad16, int ld16) {
+                     float4* __restrict__ grad, __nv_bfloat16* __restrict__ grad16, int ld16, unsigned int* gate) {
     const float TWO_PI = 6.283185307179586f;
     float sse = 0.f, pc = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
@@ -629,6 +640,7 @@ ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ y
     sse = warp_sum(sse); pc = warp_sum(pc);
     if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = sse; r2[threadIdx.x >> 5] = pc; }
     __syncthreads();
+    gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
     if (threadIdx.x == 0) {
         float a = 0.f, b = 0.f;
         for (int i = 0; i < 8; ++i) { a += r1[i]; b += r2[i]; }
@@ -637,6 +649,7 @@ ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ y
         atomicAdd(losses + 1, b * inv);
         atomicAdd(losses + 2, a * inv);
     }
+    gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
 }
 
 int ampphase_loss(const float* yt, const float* yp, long long npix, float w_amp, float w_ph, int sigmoid_bwd,
@@ -647,7 +660,7 @@ int ampphase_loss(const float* yt, const float* yp, long long npix, float w_amp,
     const long long npair = npix / 2;
     ampphase_loss_kernel<<<grid_for(npair, 256), 256, 0, st>>>((const float4*)yt, (const float4*)yp, npair, npix,
                                                                w_amp, w_ph, sigmoid_bwd, losses, (float4*)grad,
-                                                               (__nv_bfloat16*)grad16, ld16);
+                                                               (__nv_bfloat16*)grad16, ld16, next_gate());
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
@@ -679,6 +692,78 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
+// tf.keras.optimizers.Nadam (optimizer_v2/nadam.py; amp_phase_trainer.py:30-31 picks it for names containing "nadam"):
+//   u_t = b1 * (1 - 0.5 * 0.96^(0.004 t)),  m_schedule_t = prod_{i<=t} u_i  (kept in coef[0] across steps)
+//   g' = g / (1 - m_schedule_t);  m = b1 m + (1-b1) g;  m' = m / (1 - m_schedule_t * u_{t+1})
+//   v = b2 v + (1-b2) g^2;  v' = v / (1 - b2^t);  w -= lr * ((1 - u_t) g' + u_{t+1} m') / (sqrt(v') + eps)
+// nadam_prepare (one thread) advances the schedule product on the device, so a captured graph follows it.
+// coef = [m_schedule, c_g = (1-u_t)/(1-ms_t), c_m = u_{t+1}/(1-ms_t*u_{t+1}), 1/(1-b2^t)]; a fresh state has coef[0] = 1.
+__global__ void nadam_prepare_kernel(float* __restrict__ coef, const int* __restrict__ step_dev, float b1, float b2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double t = (double)(*step_dev + 1);
+    const double u_t = (double)b1 * (1.0 - 0.5 * pow(0.96, 0.004 * t));
+    const double u_t1 = (double)b1 * (1.0 - 0.5 * pow(0.96, 0.004 * (t + 1.0)));
+    const double ms = (*step_dev == 0 ? 1.0 : (double)coef[0]) * u_t;
+    const double ms_next = ms * u_t1;
+    coef[0] = (float)ms;
+    coef[1] = (float)((1.0 - u_t) / (1.0 - ms));
+    coef[2] = (float)(u_t1 / (1.0 - ms_next));
+    coef[3] = (float)(1.0 / (1.0 - pow((double)b2, t)));
+}
+__global__ void __launch_bounds__(256)
+nadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+             const float* __restrict__ lr_dev, const float* __restrict__ coef, float b1, float b2, float eps) {
+    const float lr = *lr_dev, cg = coef[1], cm = coef[2], cv = coef[3];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gg = g[i];
+        const float mm = b1 * m[i] + (1.f - b1) * gg, vv = b2 * v[i] + (1.f - b2) * gg * gg;
+        m[i] = mm; v[i] = vv;
+        p[i] -= lr * (cg * gg + cm * mm) / (sqrtf(vv * cv) + eps);
+    }
+}
+
+// tensorflow_addons LAMB (trainer.py:37-38; defaults b1 .9, b2 .999, eps 1e-6, weight decay 0): per VARIABLE trust ratio
+//   u = m_hat / (sqrt(v_hat) + eps) (+ wd * w);  r = ||w|| / ||u|| (1 when either norm is 0);  w -= lr * r * u.
+// table[e] = {offset, count} of variable e in the flat buffers. Pass 1 (grid.y = variable) updates m, v, stores u in
+// `upd` and accumulates the two squared norms into norms[2e], norms[2e+1] (caller-zeroed); pass 2 applies.
+__global__ void __launch_bounds__(256)
+lamb_stage1_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   float* __restrict__ upd, const long long* __restrict__ table, float* __restrict__ norms,
+                   const int* __restrict__ step_dev, float b1, float b2, float eps, float wd) {
+    const long long off = table[2 * blockIdx.y], cnt = table[2 * blockIdx.y + 1];
+    const float t = (float)(*step_dev + 1);
+    const float c1 = 1.f / (1.f - powf(b1, t)), c2 = 1.f / (1.f - powf(b2, t));
+    float sw = 0.f, su = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = off + i;
+        const float gg = g[j], w = p[j];
+        const float mm = b1 * m[j] + (1.f - b1) * gg, vv = b2 * v[j] + (1.f - b2) * gg * gg;
+        m[j] = mm; v[j] = vv;
+        const float u = (mm * c1) / (sqrtf(vv * c2) + eps) + wd * w;
+        upd[j] = u;
+        sw = fmaf(w, w, sw); su = fmaf(u, u, su);
+    }
+    __shared__ float r1[8], r2[8];
+    sw = warp_sum(sw); su = warp_sum(su);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = sw; r2[threadIdx.x >> 5] = su; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a += r1[i]; b += r2[i]; }
+        atomicAdd(norms + 2 * blockIdx.y, a); atomicAdd(norms + 2 * blockIdx.y + 1, b);
+    }
+}
+__global__ void __launch_bounds__(256)
+lamb_stage2_kernel(float* __restrict__ p, const float* __restrict__ upd, const long long* __restrict__ table,
+                   const float* __restrict__ norms, const float* __restrict__ lr_dev) {
+    const long long off = table[2 * blockIdx.y], cnt = table[2 * blockIdx.y + 1];
+    const float wn = sqrtf(norms[2 * blockIdx.y]), un = sqrtf(norms[2 * blockIdx.y + 1]);
+    const float ratio = (wn > 0.f && un > 0.f) ? wn / un : 1.f;
+    const float s = *lr_dev * ratio;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x)
+        p[off + i] -= s * upd[off + i];
+}
+
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, const float* __restrict__ lr_dev) {
     const float lr = *lr_dev;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -707,7 +792,7 @@ sumsq_kernel(const float* __restrict__ x, long long n, float scale, float* __res
 // L2 kernel regulariser of every regularised tensor in ONE launch (main_training.py:232-233):
 // table[e] = {param fp32 ptr, grad fp32 ptr, n} (int64 each); out[0] += coef * sum p^2 ; grad += 2 * coef * p.
 __global__ void __launch_bounds__(256)
-l2_reg_batched_kernel(const long long* __restrict__ table, float coef, float* __restrict__ out) {
+l2_reg_batched_kernel(const long long* __restrict__ table, float coef, float* __restrict__ out, unsigned int* gate) {
     const long long* e = table + 3 * blockIdx.y;
     const float* p = reinterpret_cast<const float*>(e[0]);
     float* g = reinterpret_cast<float*>(e[1]);
@@ -729,8 +814,17 @@ l2_reg_batched_kernel(const long long* __restrict__ table, float coef, float* __
         s = fmaf(v, v, s);
         g[i] = fmaf(c2, v, g[i]);
     }
+    __shared__ float r[8];
     s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(out, s * coef);
+    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = s;
+    __syncthreads();
+    gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int i = 0; i < 8; ++i) a += r[i];
+        if (a != 0.f) atomicAdd(out, a * coef);
+    }
+    gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
 }
 
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long n8) {
@@ -771,6 +865,23 @@ int adam(float* p, const float* g, float* m, float* v, long long n, const float*
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }
+int nadam(float* p, const float* g, float* m, float* v, long long n, const float* lr, const int* step, float* coef,
+          float b1, float b2, float eps, cudaStream_t st) {
+    nadam_prepare_kernel<<<1, 32, 0, st>>>(coef, step, b1, b2);
+    URIR_LAUNCH_OK(0);
+    nadam_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, coef, b1, b2, eps);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+int lamb(float* p, const float* g, float* m, float* v, float* upd, const long long* table, int n_vars, float* norms,
+         const float* lr, const int* step, float b1, float b2, float eps, float wd, cudaStream_t st) {
+    URIR_CUDA_OK(cudaMemsetAsync(norms, 0, sizeof(float) * 2 * (size_t)n_vars, st));
+    lamb_stage1_kernel<<<dim3(64, n_vars), 256, 0, st>>>(p, g, m, v, upd, table, norms, step, b1, b2, eps, wd);
+    URIR_LAUNCH_OK(0);
+    lamb_stage2_kernel<<<dim3(64, n_vars), 256, 0, st>>>(p, upd, table, norms, lr);
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
 int sgd(float* p, const float* g, long long n, const float* lr, cudaStream_t st) {
     sgd_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, n, lr);
     URIR_LAUNCH_OK(0);
@@ -790,7 +901,7 @@ int sumsq(const float* x, long long n, float scale, float* out, int accumulate, 
 }
 int l2_reg_batched(const long long* table_dev, int n_entries, float coef, float* out, cudaStream_t st) {
     URIR_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
-    l2_reg_batched_kernel<<<dim3(148 * 2, n_entries), 256, 0, st>>>(table_dev, coef, out);
+    l2_reg_batched_kernel<<<dim3(sm_count() * 2, n_entries), 256, 0, st>>>(table_dev, coef, out, next_gate());
     URIR_LAUNCH_OK(0);
     return URIR_OK;
 }

@@ -26,6 +26,9 @@ void count_launch(int kind);   // kind: 0 = SIMT/bandwidth kernel, 1 = tcgen05 k
                         cudaGetErrorString(_e)); ::urir::count_launch(kind); } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached; 148 on B200): persistent grids and the
+// dispatch gates ("enough tiles per SM") are sized from it, never from a literal
+int sm_count();
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------
 // Kernels launched through launch_pdl() may become resident while their predecessor in the stream is still
@@ -47,7 +50,51 @@ static inline cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block,
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
 }
 
+// ---- deterministic mode (URIR_DETERMINISTIC=1 / urir_set_deterministic) -----------------------
+// Every cross-CTA floating-point reduction of the library ends in atomicAdd / red.global from each CTA, whose
+// arrival order -- and therefore the rounding of the sum -- changes from run to run. In deterministic mode each
+// such kernel gets a "gate": a device counter through which its CTAs commit their partial results in blockIdx
+// order (CTA i spins until the counter reads i, adds, publishes i + 1; the last CTA resets it to 0 so CUDA-graph
+// replays can reuse it). Lower-numbered CTAs are dispatched first and never wait on higher ones, so the chain
+// cannot deadlock; a bounded spin traps instead of hanging if that assumption were ever violated.
+// next_gate() hands out the slots round-robin (host side, nullptr when the mode is off): kernels that may run
+// concurrently on two streams of one step get distinct slots.
+unsigned int* next_gate();
+bool deterministic();
+
 // ---- device helpers ---------------------------------------------------------------------
+// gate_enter / gate_leave bracket the global atomics of a CTA. `nthreads` threads (all of which call both, with the
+// same arguments) synchronise on named barrier `bar_id` (0 = the whole CTA's __syncthreads barrier when nthreads ==
+// blockDim.x); `leader` is true for exactly one of them.
+__device__ __forceinline__ void gate_bar(int bar_id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void gate_enter(unsigned int* gate, unsigned int turn, bool leader, int bar_id, int nthreads) {
+    if (gate == nullptr) return;
+    if (leader) {
+        unsigned int v;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gate) : "memory");
+            if (v == turn) break;
+            if (clock64() - t0 > (1ll << 31)) asm volatile("trap;");
+        }
+    }
+    gate_bar(bar_id, nthreads);
+}
+__device__ __forceinline__ void gate_leave(unsigned int* gate, unsigned int turn, unsigned int total, bool leader, int bar_id,
+                                           int nthreads) {
+    if (gate == nullptr) return;
+    __threadfence();
+    gate_bar(bar_id, nthreads);
+    if (leader) {
+        const unsigned int nxt = (turn + 1 == total) ? 0u : turn + 1;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(gate), "r"(nxt) : "memory");
+    }
+}
+__device__ __forceinline__ unsigned int cta_linear() { return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); }
+__device__ __forceinline__ unsigned int cta_count() { return gridDim.x * gridDim.y * gridDim.z; }
+
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }

@@ -35,6 +35,23 @@ __global__ void embedding_bwd_kernel(const int* __restrict__ idx, const T* __res
     }
 }
 
+// deterministic mode: one block per vocabulary row scans the token list in order (no atomics; rows nobody indexes
+// just get their zero) -- n_tok is B * 32, so the scan is tiny
+template <typename T>
+__global__ void embedding_bwd_ordered_kernel(const int* __restrict__ idx, const T* __restrict__ dx,
+                                             float* __restrict__ dtable, long long n_tok, int D, int vocab) {
+    const int row = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (long long tok = 0; tok < n_tok; ++tok) {
+            int id = idx[tok];
+            id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+            if (id == row) acc += ld_as_f32(dx + tok * D + d);
+        }
+        dtable[(size_t)row * D + d] = acc;
+    }
+}
+
 // ---- Dense + Dropout on the tensor cores -----------------------------------------------------
 // Dense(8192 -> 1440) over a batch is a 1x1 convolution over B "pixels": forward = conv fprop (A = x K-major,
 // B = w^T [N][Kd] K-major), dx = conv dgrad (B = w [Kd][N]), dw = conv wgrad (both operands MN-major, the
@@ -81,6 +98,12 @@ int embedding_fwd(const int* idx, const float* table, void* out, int B, int T, i
     return URIR_OK;
 }
 int embedding_bwd(const int* idx, const void* dx, int dx_dtype, float* dtable, int B, int T, int D, int vocab, cudaStream_t st) {
+    if (deterministic()) {
+        if (dx_dtype == URIR_BF16) embedding_bwd_ordered_kernel<__nv_bfloat16><<<vocab, 256, 0, st>>>(idx, (const __nv_bfloat16*)dx, dtable, (long long)B * T, D, vocab);
+        else embedding_bwd_ordered_kernel<float><<<vocab, 256, 0, st>>>(idx, (const float*)dx, dtable, (long long)B * T, D, vocab);
+        URIR_LAUNCH_OK(0);
+        return URIR_OK;
+    }
     URIR_CUDA_OK(cudaMemsetAsync(dtable, 0, sizeof(float) * (size_t)vocab * D, st));
     const long long n = (long long)B * T * D;
     if (dx_dtype == URIR_BF16) embedding_bwd_kernel<__nv_bfloat16><<<cdiv(n, 256), 256, 0, st>>>(idx, (const __nv_bfloat16*)dx, dtable, (long long)B * T, D, vocab);

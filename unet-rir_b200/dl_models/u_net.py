@@ -10,7 +10,8 @@ embedding ids, exactly the DataGenerator batch contract (datageneratorv2.py:88-1
 tensors on the GPU (use `.cpu().numpy()` where the reference used `.numpy()`).
 
 Deviations, all deliberate and visible:
-  * weights are saved as a torch state dict (`weights.pt`); h5py / Keras `weights.h5` do not exist here.
+  * weights are saved as a torch state dict (`weights.pt`); h5py / Keras `weights.h5` do not exist here. Weights
+    trained with the reference come in through `load_weights("x.npz")` (tools/export_tf_weights.py, keras_weights.py).
   * `_save_parameters` also stores `kernels`. The reference omits it (u_net.py:180-187), so its own
     `UNet.load` rebuilds with `BatchNorm` shifted into the `kernels` slot -- a latent bug we do not copy.
   * all four block modes (0 convolutional_block_1 ... 3 residual_block_2) are wired on the device with
@@ -111,7 +112,13 @@ class UNetModel:
         torch.save(self.engine.state_dict(), path)
 
     def load_weights(self, path):
-        self.engine.load_state_dict(torch.load(path, map_location="cpu"))
+        """`.pt`: a state dict saved by save_weights; `.npz`: weights trained with the reference under TensorFlow,
+        exported by tools/export_tf_weights.py (keras_weights.read_keras_npz maps them onto the plan)."""
+        if str(path).endswith(".npz"):
+            from ..keras_weights import read_keras_npz
+            self.engine.load_state_dict(read_keras_npz(path, self.engine.plan))
+        else:
+            self.engine.load_state_dict(torch.load(path, map_location="cpu"))
 
     def count_params(self):
         return sum(v.numel() for v in self.variables)

@@ -135,6 +135,10 @@ class UNetEngine:
         self._bufs = {}
         self.dropout_seed = seed
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # Dropout's own stream position: advanced by every training forward that draws a mask (a device-side
+        # increment right after the mask launch, so CUDA-graph replays, optimisers that never touch step_dev
+        # (Nadam, an external torch optimiser) and repeated forwards all get fresh masks)
+        self.drop_ctr_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.losses_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -234,14 +238,23 @@ class UNetEngine:
                 dst = self.state[k]
             if tuple(v.shape) != tuple(dst.shape):
                 raise ValueError(f"{k}: shape {tuple(v.shape)} != {tuple(dst.shape)}")
-            dst.copy_(torch.as_tensor(v, dtype=torch.float32))
+            with torch.no_grad():           # the views may be autograd leaves (UNetModel.trainable_variables)
+                dst.copy_(torch.as_tensor(v, dtype=torch.float32))
         self.refresh_operands()
 
     def refresh_operands(self):
         """fp32 masters -> bf16 operand layouts (after load / after every optimiser step)."""
+        self._p_version = self.P._version
         L.call("weight_prep_batched", self.wprep_table.data_ptr(), self.wprep_table.shape[0])
         for name, buf in self.wup2.items():
             L.call("weight_prep_up2", self.param[name + ".w"].data_ptr(), buf.data_ptr(), buf.shape[1] // 4, buf.shape[2])
+
+    def sync_operands(self):
+        """Refreshes the bf16 operand copies when the fp32 masters were modified through torch (an external
+        optimiser stepping `trainable_variables`, a manual `param[...].copy_`): views share P's version counter.
+        Kernel-side updates (adam_step etc.) refresh the operands themselves."""
+        if self.P._version != getattr(self, "_p_version", -1):
+            self.refresh_operands()
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, B):
@@ -519,6 +532,7 @@ class UNetEngine:
         """
         b = self.stage(spec_in, emb)
         B = spec_in.shape[0]
+        self.sync_operands()
         if not training and self.eval_cuda_graph:
             # inference (rir_generation.py:160-170 runs batches of 4): ~60 small launches, host-bound when issued one
             # by one, so the eval forward of each batch size is captured once (after a warm-up call) and replayed.
@@ -563,7 +577,8 @@ class UNetEngine:
                     mask = b["mask"]
                 elif dropout:
                     L.call("dropout_mask", b["mask"].data_ptr(), b["mask"].numel(), PL.DROPOUT_RATE,
-                           self.dropout_seed, self.step_dev.data_ptr())
+                           self.dropout_seed, self.drop_ctr_dev.data_ptr())
+                    L.call("step_increment", self.drop_ctr_dev.data_ptr())
                     mask = b["mask"]
             self._fwd_mask = mask
             L.call("dense_fwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
@@ -740,6 +755,29 @@ class UNetEngine:
     def adam_step(self, beta1=0.9, beta2=0.999, eps=1e-7):
         L.call("adam", self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.n_flat,
                self.lr_dev.data_ptr(), self.step_dev.data_ptr(), beta1, beta2, eps)
+        L.call("step_increment", self.step_dev.data_ptr())
+        self.refresh_operands()
+
+    def nadam_step(self, beta1=0.9, beta2=0.999, eps=1e-7):
+        """tf.keras.optimizers.Nadam on the flat buffers (amp_phase_trainer.py:30-31); the momentum-schedule product
+        lives in device memory, so the step is graph capturable like adam_step."""
+        if getattr(self, "nadam_coef", None) is None:
+            self.nadam_coef = torch.ones(4, dtype=torch.float32, device=self.device)
+        L.call("nadam", self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.n_flat,
+               self.lr_dev.data_ptr(), self.step_dev.data_ptr(), self.nadam_coef.data_ptr(), beta1, beta2, eps)
+        L.call("step_increment", self.step_dev.data_ptr())
+        self.refresh_operands()
+
+    def lamb_step(self, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0):
+        """tensorflow_addons LAMB (trainer.py:37-38): per-variable trust ratio over the 77 trainable tensors."""
+        if getattr(self, "_lamb_table", None) is None:
+            rows = [[o, n] for o, n in self.offsets.values()]
+            self._lamb_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+            self._lamb_upd = torch.empty_like(self.P)
+            self._lamb_norms = torch.zeros(2 * len(rows), dtype=torch.float32, device=self.device)
+        L.call("lamb", self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self._lamb_upd.data_ptr(),
+               self._lamb_table.data_ptr(), self._lamb_table.shape[0], self._lamb_norms.data_ptr(), self.lr_dev.data_ptr(),
+               self.step_dev.data_ptr(), beta1, beta2, eps, weight_decay)
         L.call("step_increment", self.step_dev.data_ptr())
         self.refresh_operands()
 

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import math
 import os
+import random
 import time
 
 import numpy as np
@@ -73,20 +74,26 @@ def lr_schedule(lr0, epoch, start=80):
 
 
 class DistributedTrainer:
-    """One replica of the synchronous data-parallel train step."""
+    """One replica of the synchronous data-parallel train step.
+
+    The whole step -- forward, loss, the three backward segments, the three NCCL all-reduces of the gradient buckets
+    (each issued on NCCL's stream as soon as its segment is enqueued, joined before the optimiser), the L2 regulariser
+    and Adam -- is ONE CUDA graph per shard size (URIR_DP_GRAPH=segments restores round 1's four graphs with eagerly
+    launched collectives, =off runs everything eagerly). World 1 runs the same body without the collectives."""
 
     def __init__(self, model: UNet, per_replica_batch=16, alpha=0.9, lr=5e-7, loss="dp", world=None,
-                 use_cuda_graph=True, dropout=True):
+                 use_cuda_graph=True, dropout=True, rank=None):
         self.model = model
         self.eng = model.model.engine
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
         self.per_replica_batch = per_replica_batch
         self.global_batch = per_replica_batch * self.world
         self.alpha, self.lr, self.loss = alpha, lr, loss
         self.use_cuda_graph, self.dropout = use_cuda_graph, dropout
         self.buckets = gradient_buckets(self.eng.offsets, self.eng.n_flat)
-        self._graphs = None
-        self._calls = 0
+        self.graph_mode = os.environ.get("URIR_DP_GRAPH", "one") if use_cuda_graph else "off"
+        self._graphs = {}            # shard size B -> "warm" | CUDAGraph | [four segment graphs]
         self.overlap = os.environ.get("URIR_DP_OVERLAP", "1") != "0"
         # Dense layer (56 % of all parameters): all-gather its two small operands and form the global-batch kernel
         # gradient locally instead of all-reducing 47 MB of fp32 gradient (see engine.dense_grad_from_gathered)
@@ -96,6 +103,8 @@ class DistributedTrainer:
         self._o_dense = o["vec.dense.w"][0]
         self._o_after_dense = o["vec.dense.b"][0] + o["vec.dense.b"][1]
         self._gathered = None
+        # MirroredStrategy gives every replica its own Dropout mask: mix the rank into the mask stream's seed
+        self.eng.dropout_seed = (self.eng.dropout_seed + 0x9E3779B1 * self.rank) & 0x7FFFFFFFFFFFFFFF
         self.eng.set_lr(lr)
 
     # loss weights: w_amp * sum sq err + w_ph * sum (1 - cos)
@@ -130,53 +139,75 @@ class DistributedTrainer:
             self.eng.l2_loss_and_grad(1.0)
         self.eng.adam_step()
 
-    def _run(self, B):
-        segs = (self._seg_forward_loss_decoder, self._seg_bottleneck, self._seg_encoder, self._seg_optimizer)
-        if self.use_cuda_graph and self._graphs is None and self._calls == 1:
-            torch.cuda.synchronize()
-            graphs = []
-            for s in segs:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    s(B)
-                graphs.append(g)
-            self._graphs = graphs
-        works = []
-        for i, s in enumerate(segs):
+    def _segments(self):
+        return (self._seg_forward_loss_decoder, self._seg_bottleneck, self._seg_encoder, self._seg_optimizer)
+
+    def _reduce_bucket(self, i, B, works, state):
+        """All-reduce of gradient bucket i (async, on NCCL's stream) right after backward segment i was enqueued."""
+        e = self.eng
+        lo, hi = self.buckets[i]
+        if not self.gather_dense or i == 0:
+            works.append(dist.all_reduce(e.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        elif i == 1:
+            # bottleneck bucket = [embedding | Dense kernel, bias | projection]: gather the Dense operands,
+            # reduce the projection now; the embedding table rides with the (adjacent) encoder bucket
+            state["gathers"] = self._gather_dense_operands(B)
+            works.append(dist.all_reduce(e.G[self._o_after_dense:hi], op=dist.ReduceOp.SUM, async_op=True))
+        else:
+            # Dense kernel gradient of the global batch on the side stream, beside the encoder's backward
+            e.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(e.side):
+                for w in state["gathers"]:
+                    w.wait()
+                e.dense_grad_from_gathered(*self._gathered)
+            works.append(dist.all_reduce(e.G[0:self._o_dense], op=dist.ReduceOp.SUM, async_op=True))
+            torch.cuda.current_stream().wait_stream(e.side)
+
+    def _step_body(self, B, graphs=None):
+        """The whole step in stream order; `graphs` = four captured segment graphs to replay instead of issuing."""
+        works, state = [], {}
+        for i, seg in enumerate(self._segments()):
             if i == 3:
                 if self.world > 1 and not self.overlap:
-                    # one all-reduce of the whole flat gradient after backward: nothing runs beside the persistent
-                    # one-CTA-per-SM conv kernels (an NCCL kernel resident on a few SMs forces their static tile
-                    # schedule into a second wave)
+                    # one all-reduce of the whole flat gradient after backward (nothing runs beside the conv kernels)
                     works.append(dist.all_reduce(self.eng.G, op=dist.ReduceOp.SUM, async_op=True))
                 for w in works:
                     w.wait()
-            if self._graphs is not None:
-                self._graphs[i].replay()
+            if graphs is not None:
+                graphs[i].replay()
             else:
-                s(B)
+                seg(B)
             if i < 3 and self.world > 1 and self.overlap:
-                lo, hi = self.buckets[i]
-                if not self.gather_dense:
-                    works.append(dist.all_reduce(self.eng.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
-                elif i == 0:
-                    works.append(dist.all_reduce(self.eng.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
-                elif i == 1:
-                    # bottleneck bucket = [embedding | Dense kernel, bias | projection]: gather the Dense operands,
-                    # reduce the projection now; the embedding table rides with the (adjacent) encoder bucket
-                    gathers = self._gather_dense_operands(B)
-                    works.append(dist.all_reduce(self.eng.G[self._o_after_dense:hi], op=dist.ReduceOp.SUM, async_op=True))
-                else:
-                    # Dense kernel gradient of the global batch on the side stream, beside the encoder's backward
-                    e = self.eng
-                    with torch.cuda.stream(e.side):
-                        for w in gathers:
-                            w.wait()
-                        e.dense_grad_from_gathered(*self._gathered)
-                    works.append(dist.all_reduce(e.G[0:self._o_dense], op=dist.ReduceOp.SUM, async_op=True))
-            if i == 2 and self.gather_dense:
-                torch.cuda.current_stream().wait_stream(self.eng.side)
-        self._calls += 1
+                self._reduce_bucket(i, B, works, state)
+
+    def _run(self, B):
+        st = self._graphs.get(B)
+        if self.graph_mode == "off":
+            self._step_body(B)
+        elif st is None:                         # first call for this shard size: eager (kernel attributes, NCCL warm-up)
+            self._step_body(B)
+            self._graphs[B] = "warm"
+        elif st == "warm":                       # second call: capture, then run
+            torch.cuda.synchronize()
+            if self.graph_mode == "segments":
+                graphs = []
+                for seg in self._segments():
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        seg(B)
+                    graphs.append(g)
+                self._graphs[B] = graphs
+                self._step_body(B, graphs)
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body(B)
+                self._graphs[B] = g
+                g.replay()
+        elif isinstance(st, list):
+            self._step_body(B, st)
+        else:
+            st.replay()
 
     def _gather_dense_operands(self, B):
         x, dy = self.eng.dense_operands(B)
@@ -208,36 +239,155 @@ class DistributedTrainer:
             loss = loss + e.reg_dev[0] / self.world      # reg_dev = sum(l2); each replica's share is 1/replicas
         return loss
 
-    def set_epoch(self, epoch):
-        self.eng.set_lr(lr_schedule(self.lr, epoch))
+    def test_step(self, spec_in, emb, spec_out):
+        """The reference's test_step (main_training.py:293-316): a forward with training=True (its literal argument:
+        BatchNormalization uses -- and updates -- batch statistics, Dropout is active), then the two validation metrics
+        of the shard: mean squared amplitude error and mean 1 - cos of the wrapped phase difference.
+        Returns (loss_amplitude, loss_phase) as 0-d device tensors."""
+        e = self.eng
+        dev = e.device
+        B = int(spec_in.shape[0])
+        spec_in = torch.as_tensor(spec_in).to(dev, torch.float32, non_blocking=True)
+        emb = torch.as_tensor(emb).to(dev, torch.int32, non_blocking=True)
+        y = torch.as_tensor(spec_out).to(dev, torch.float32, non_blocking=True).contiguous()
+        e.sync_operands()
+        out = e.forward(spec_in, emb, training=True, dropout=self.dropout)
+        n = B * e.input_shape[0] * e.input_shape[1]
+        res = torch.empty(4, dtype=torch.float32, device=dev)
+        L.call("ampphase_loss", y.data_ptr(), out.data_ptr(), n, 1.0 / n, 1.0 / n, 0, res.data_ptr(), None, None, 0)
+        return res[2], res[1]
+
+    def set_epoch(self, epoch, start=80):
+        self.eng.set_lr(lr_schedule(self.lr, epoch, start))
+
+    # ---- tf.train.Checkpoint(optimizer=..., model=...) contents (main_training.py:171)
+    def checkpoint_state(self):
+        e = self.eng
+        return {"model": e.state_dict(), "adam_m": e.M.detach().cpu().clone(), "adam_v": e.V.detach().cpu().clone(),
+                "step": int(e.step_dev.item()), "lr": float(e.lr_dev.item())}
+
+    def load_checkpoint_state(self, st):
+        e = self.eng
+        e.load_state_dict(st["model"])
+        with torch.no_grad():
+            e.M.copy_(st["adam_m"]); e.V.copy_(st["adam_v"])
+        e.step_dev.fill_(int(st["step"]))
+        e.set_lr(st["lr"])
 
 
-def main(n_epochs=2, steps_per_epoch=8, per_replica_batch=16, lr=5e-7, alpha=0.9, seed=500):
-    """Synthetic-data stand-in for the reference's `__main__` (the dataset directory of
-    main_training.py:75 does not exist here): same model, loss, optimiser and schedule."""
+class CheckpointManager:
+    """tf.train.CheckpointManager(checkpoint, directory, max_to_keep=2) (main_training.py:171-172): numbered saves
+    `ckpt-<n>.pt`, the oldest deleted beyond max_to_keep; `latest_checkpoint` / `restore_latest` for a restart."""
+
+    def __init__(self, trainer: DistributedTrainer, directory, max_to_keep=2):
+        self.trainer, self.directory, self.max_to_keep = trainer, directory, max_to_keep
+        os.makedirs(directory, exist_ok=True)
+        self._kept = sorted((f for f in os.listdir(directory) if f.startswith("ckpt-") and f.endswith(".pt")),
+                            key=lambda f: int(f[5:-3]))
+        self._n = int(self._kept[-1][5:-3]) if self._kept else 0
+
+    @property
+    def latest_checkpoint(self):
+        return os.path.join(self.directory, self._kept[-1]) if self._kept else None
+
+    def save(self):
+        self._n += 1
+        name = f"ckpt-{self._n}.pt"
+        torch.save(self.trainer.checkpoint_state(), os.path.join(self.directory, name))
+        self._kept.append(name)
+        while len(self._kept) > self.max_to_keep:
+            os.remove(os.path.join(self.directory, self._kept.pop(0)))
+        return os.path.join(self.directory, name)
+
+    def restore_latest(self):
+        path = self.latest_checkpoint
+        if path is not None:
+            self.trainer.load_checkpoint_state(torch.load(path, map_location="cpu"))
+        return path
+
+
+def _global_mean(values, world):
+    """tf.keras.metrics.Mean over every replica's updates (ON_READ sum aggregation, main_training.py:237-242)."""
+    if not values:
+        return float("nan")
+    t = torch.stack([v.reshape(()).float() for v in values]).mean()
+    if world > 1:
+        dist.all_reduce(t)
+        t = t / world
+    return float(t)
+
+
+def train_loop(trainer: DistributedTrainer, train_generator, val_generator, n_epochs, manager=None,
+               lr_exp_decay=(True, 80), rank=0, world=1, max_steps=None, verbose=True):
+    """The epoch loop of main_training.py:332-391: LR decay from epoch lr_exp_decay[1], one pass over the training
+    generator (each rank takes its contiguous slice of every global batch, :114), one pass over the validation
+    generator through test_step (training=True, as written there), a checkpoint every second epoch (`epoch % 2 == 0`),
+    the reference's four console lines. Returns one dict per epoch."""
+    history = []
+    t_start = time.time()
+    for epoch in range(n_epochs):
+        t0 = time.time()
+        if lr_exp_decay[0]:
+            trainer.set_epoch(epoch, lr_exp_decay[1])
+        n_train = len(train_generator) if max_steps is None else min(len(train_generator), max_steps)
+        n_val = len(val_generator) if max_steps is None else min(len(val_generator), max_steps)
+        losses, amp, ph = [], [], []
+        for i in range(n_train):
+            spec_in, emb, spec_out = shard_batch(train_generator[i][:3], rank, world)
+            losses.append(trainer.train_step(spec_in, emb, spec_out))
+            ld = trainer.eng.losses_dev.clone()
+            amp.append(ld[2]); ph.append(ld[1])
+        total = torch.stack(losses).sum() if losses else torch.zeros((), device=trainer.eng.device)
+        if world > 1:
+            dist.all_reduce(total)                      # strategy.reduce(SUM, per_replica_losses) (:326-327)
+        train_loss = float(total) / max(n_train, 1)
+        v_amp, v_ph = [], []
+        for i in range(n_val):
+            spec_in, emb, spec_out = shard_batch(val_generator[i][:3], rank, world)
+            a, p = trainer.test_step(spec_in, emb, spec_out)
+            v_amp.append(a); v_ph.append(p)
+        saved = None
+        if manager is not None and epoch % 2 == 0 and rank == 0:
+            saved = manager.save()
+        row = {"epoch": epoch + 1, "loss": train_loss, "train_mse": _global_mean(amp, world),
+               "train_phase": _global_mean(ph, world), "val_mse": _global_mean(v_amp, world),
+               "val_phase": _global_mean(v_ph, world), "lr": float(trainer.eng.lr_dev.item()), "checkpoint": saved,
+               "seconds": time.time() - t0}
+        history.append(row)
+        random.seed(0x5EED + epoch)      # every rank must reshuffle the global batches identically (on_epoch_end uses `random`)
+        for g in (train_generator, val_generator):
+            if hasattr(g, "on_epoch_end"):
+                g.on_epoch_end()
+        if verbose and rank == 0:
+            print("Epoch {}, Loss: {}, Epoch time: {}\nTrain | MSE Loss: {}, Phase Loss: {}\n"
+                  "Val   | MSE Loss: {}, Phase Loss: {}\nlr    | {}".format(
+                      row["epoch"], row["loss"], row["seconds"], row["train_mse"], row["train_phase"], row["val_mse"],
+                      row["val_phase"], row["lr"]))
+    if verbose and rank == 0:
+        print("Training complete, took " + str(time.time() - t_start))
+    return history
+
+
+def main(n_epochs=2, steps_per_epoch=8, per_replica_batch=16, lr=5e-7, alpha=0.9, seed=500, file_name=None,
+         lr_exp_decay=(True, 80)):
+    """Synthetic-data stand-in for the reference's `__main__` (the dataset directory of main_training.py:75 does not
+    exist here): same model, loss, optimiser, schedule, validation pass and checkpoint cadence."""
     from .dataset import Dataset
     from .datageneratorv2 import DataGenerator
     rank, world, local = init_distributed()
     model = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3,
                  name="U-Net")
-    trainer = DistributedTrainer(model, per_replica_batch, alpha, lr, world=world)
-    dataset = Dataset(None, "synthetic", n_synthetic=per_replica_batch * world * steps_per_epoch * 2, seed=seed)
-    gen = DataGenerator(dataset, batch_size=per_replica_batch * world, partition="train", shuffle=True)
-    for epoch in range(n_epochs):
-        t0 = time.time()
-        trainer.set_epoch(epoch)
-        total, nb = 0.0, 0
-        for i in range(min(len(gen), steps_per_epoch)):
-            spec_in, emb, spec_out = shard_batch(gen[i], rank, world)
-            loss = trainer.train_step(spec_in, emb, spec_out)
-            if world > 1:
-                dist.all_reduce(loss)
-            total += float(loss); nb += 1
-        gen.on_epoch_end()
-        if rank == 0:
-            print(f"Epoch {epoch + 1}, Loss: {total / max(nb, 1):.6f}, Epoch time: {time.time() - t0:.2f}")
+    trainer = DistributedTrainer(model, per_replica_batch, alpha, lr, world=world, rank=rank)
+    gb = per_replica_batch * world
+    dataset = Dataset(None, "synthetic", n_synthetic=int(gb * steps_per_epoch / 0.7) + 4 * gb, seed=seed)
+    train_generator = DataGenerator(dataset, batch_size=gb, partition="train", shuffle=True)
+    val_generator = DataGenerator(dataset, batch_size=gb, partition="val", shuffle=True)
+    manager = CheckpointManager(trainer, file_name, max_to_keep=2) if file_name else None
+    history = train_loop(trainer, train_generator, val_generator, n_epochs, manager, lr_exp_decay, rank, world,
+                         max_steps=steps_per_epoch)
     if world > 1:
         dist.destroy_process_group()
+    return history
 
 
 if __name__ == "__main__":

@@ -128,7 +128,13 @@ class PostProcess:
         return self.normalizer.denormalize(stft, phase)
 
     def istft(self, denorm_f, denorm_p, n_fft, win_length, hop_length):
-        """amp, phase (n_bins, n_frames), already un-padded and denormalised -> self.waveform."""
+        """amp, phase (n_bins, n_frames), already un-padded and denormalised -> self.waveform; Griffin-Lim phase
+        retrieval from the magnitudes alone when algorithm == 'gl' (postprocess.py:128-131)."""
+        if self.algorithm == 'gl':
+            a = np.asarray(denorm_f, dtype=np.float32)
+            self.waveform = griffinlim_batch(a[None], n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+                                             padded=a.shape)[0].cpu().numpy()
+            return
         feat = np.stack([np.asarray(denorm_f, dtype=np.float32), np.asarray(denorm_p, dtype=np.float32)], axis=-1)
         self.waveform = post_process_batch(feat, feat.shape[:2], n_fft, win_length, hop_length,
                                            normalized=False)[0].cpu().numpy()
