@@ -151,24 +151,29 @@ def cpu_train_step_rate(batch, steps, warmup, threads=None):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (restated by the oracle; TensorFlow is not installable
-    here) on the box's host cores, same metric / unit / config. Rank 0 only."""
+    here) on the box's host cores, same metric / unit / config -- one step = the SAME per-GPU batch the GPU arm
+    steps (BatchNorm statistics and the CPU's cache behaviour depend on it). Rank 0 only. If the box is so slow
+    that K + W steps of that batch would exceed ~4 minutes the batch is halved until they fit, and the line says so."""
     if rank != 0:
         return
-    batch = 8
-    budget_s = 150.0
-    rate, dt, threads = cpu_train_step_rate(batch, 1, 1)                 # probe
-    per_step = dt
+    batch = args.batch
+    budget_s = 240.0
+    rate, dt, threads = cpu_train_step_rate(min(batch, 8), 1, 1)         # probe
+    per_step = dt * batch / min(batch, 8)
     total = args.steps + args.warmup
     while batch > 1 and per_step * total > budget_s:
         batch //= 2
         per_step /= 2
     rate, dt, threads = cpu_train_step_rate(batch, args.steps, args.warmup)
-    sample = f"oracle Trainer.step on batch {batch} (of the {args.batch}-sample workload), {args.steps} steps"
+    sample = (f"oracle Trainer.step (fwd + loss + bwd + Keras Adam, fp32, torch CPU) on batches of {batch} "
+              f"({'the same' if batch == args.batch else 'REDUCED from the'} {args.batch}-sample per-GPU batch of the GPU arm), "
+              f"{args.steps} timed steps after {args.warmup} warm-ups")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "per_gpu_batch": args.batch, "l2": "working set >> L2"},
+        "config": {"workload": workload_name(args), "per_gpu_batch": args.batch, "cpu_step_batch": batch,
+                   "l2": "working set >> L2"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -182,22 +187,137 @@ def workload_name(args):
 
 # --------------------------------------------------------------------------------------------- GPU arm
 def per_kernel_profile(step_fn):
-    """One eager step with a CUDA-event pair around every liburir launch -> per-family totals."""
+    """One eager step (programmatic dependent launch off, side-stream branches off: one kernel at a time on the timed
+    stream) with a CUDA-event pair around every liburir call -> per-kernel-function totals.
+    Key = the kernel family that served the call (urir_family_calls) for convolutions, the call name otherwise."""
     from unet_rir_b200 import _lib as L
-    prev = L.load().urir_set_pdl(0)            # one kernel at a time: no prologue overlap while timing single launches
+    prev = L.load().urir_set_pdl(0)
     L.profile_begin()
     step_fn()
     rec = L.profile_end()
     L.load().urir_set_pdl(prev)
     fam = {}
     for name, info, ms in rec:
-        if name.startswith("conv2d"):
-            key = name + (".tcgen05" if info.get("tc") else ".simt")
-        else:
-            key = name
-        f = fam.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0})
-        f["ms"] += ms; f["launches"] += 1; f["flops"] += info.get("flops", 0.0)
+        key = ("conv." + info.get("family", "?")) if name.startswith("conv2d") else name
+        f = fam.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0, "roof_ms": 0.0,
+                                 "tensor_roof_ms": 0.0, "hbm_roof_ms": 0.0})
+        f["ms"] += ms; f["launches"] += 1
+        f["flops"] += info.get("flops", 0.0); f["bytes"] += info.get("bytes", 0.0)
     return rec, fam
+
+
+def family_rooflines(rec, fam, pk):
+    """Every launch is bounded by max(flops / tensor peak, bytes / HBM peak); a family's bound is whichever of the two
+    sums is larger, its achieved rate is algorithmic work / event time in that bound's unit."""
+    for name, info, ms in rec:
+        key = ("conv." + info.get("family", "?")) if name.startswith("conv2d") else name
+        t_tc = info.get("flops", 0.0) / (pk["tf_sustained"] * 1e12) * 1e3
+        t_hbm = info.get("bytes", 0.0) / (pk["hbm"] * 1e9) * 1e3
+        f = fam[key]
+        f["tensor_roof_ms"] += t_tc; f["hbm_roof_ms"] += t_hbm; f["roof_ms"] += max(t_tc, t_hbm)
+    out = {}
+    for key, f in fam.items():
+        if f["roof_ms"] <= 0:
+            continue
+        tensor = f["tensor_roof_ms"] >= f["hbm_roof_ms"]
+        ach = (f["flops"] / (f["ms"] * 1e-3) / 1e12) if tensor else (f["bytes"] / (f["ms"] * 1e-3) / 1e9)
+        peak = pk["tf_sustained"] if tensor else pk["hbm"]
+        out[key] = {"bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak, "launches": f["launches"],
+                    "ms": f["ms"], "frac_of_per_launch_roof": f["roof_ms"] / f["ms"]}
+    return out
+
+
+def _time_loop(fn, iters, warm=3):
+    """ms per call of fn, CUDA events on the current stream, after `warm` untimed calls."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def extra_configs(args, dev, pk):
+    """The other operating points SURVEY 8(d) lists, measured in the same process after the headline (1 GPU only):
+    the reference's own per-replica batch of 16 (main_training.py:44), generation at B = 4 (rir_generation.py:45) and
+    B = 256, the STFT / iSTFT kernels against the HBM roof, and two long-RIR shapes of config 5. Each `value` is
+    device-resident graph replay like the headline's; `e2e` goes through the public call with pinned host inputs."""
+    import ctypes as C
+
+    from unet_rir_b200 import _lib as L
+    from unet_rir_b200.amp_phase_trainer import EarlyStopping, ModelCheckpoint, Trainer
+    from unet_rir_b200.dl_models.u_net import UNet
+    from unet_rir_b200.postprocess import post_process_batch
+    from unet_rir_b200.preprocess import preprocess_batch, stft_desc
+    from unet_rir_b200.rir_generation import generate_batch
+    out = {}
+
+    def train_point(shape, B, steps):
+        Hh, Ww, _ = shape
+        unet = UNet(input_shape=shape, inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+        tr = Trainer(0.9, 1, "adam", [ModelCheckpoint("/tmp/urir_bench_x", False, 0), EarlyStopping(5)], [False, 0], 1e-5, "x")
+        g = torch.Generator().manual_seed(B + Ww)
+        host = []
+        for i in range(3):
+            x = torch.rand(B, Hh, Ww, 2, generator=g).pin_memory(); y = torch.rand(B, Hh, Ww, 2, generator=g).pin_memory()
+            e = torch.randint(0, 2000, (B, 2, 16), generator=g, dtype=torch.int32).pin_memory()
+            host.append((x, y, e))
+        for i in range(3):
+            tr.step(*host[i % 3], unet)
+        torch.cuda.synchronize()
+        graph = [gr for gr in tr._graphs.values() if not isinstance(gr, str)][0]
+        ms = _time_loop(graph.replay, steps)
+        # end to end: prefetch the next batch, step, read the loss back
+        state = {"i": 0}
+        tr.prefetch(*host[0], unet)
+
+        def e2e_step():
+            i = state["i"]
+            l = tr.step(*host[i % 3], unet)[0]
+            tr.prefetch(*host[(i + 1) % 3], unet)
+            float(l)
+            state["i"] = i + 1
+        ms_e2e = _time_loop(e2e_step, steps, warm=2)
+        flops = FLOP_PER_SAMPLE_TRAIN * (Ww / 160.0)      # conv work scales with the width; the Dense layer is < 0.3 %
+        res = {"per_gpu_batch": B, "input_shape": list(shape), "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT,
+               "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": 2 * B * Hh * Ww * 2 * 4 + B * 32 * 4, "d2h_bytes_per_step": 4},
+               "tflops_algorithmic": B / (ms * 1e-3) * flops / 1e12, "frac_of_tensor_peak": B / (ms * 1e-3) * flops / 1e12 / pk["tf_sustained"]}
+        del unet, tr, graph
+        torch.cuda.empty_cache()
+        return res
+
+    out["train_b16"] = train_point((H, W, 2), 16, 40)
+    out["train_long_rir_0.4s_b16"] = train_point((144, 304, 2), 16, 20)
+    out["train_long_rir_0.8s_b16"] = train_point((144, 608, 2), 16, 10)
+
+    # ---- generation (config 4): spectrogram -> U-Net (training=False, BN folded, one graph) -> inverse STFT
+    unet = UNet(input_shape=(H, W, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+    for Bg, iters in ((4, 100), (256, 10)):
+        g = torch.Generator().manual_seed(Bg)
+        x = torch.rand(Bg, H, W, 2, generator=g).to(dev); e = torch.randint(0, 2000, (Bg, 2, 16), generator=g, dtype=torch.int32).to(dev)
+        ms = _time_loop(lambda: generate_batch(unet, x, e), iters)
+        out[f"generation_b{Bg}"] = {"batch": Bg, "ms_per_batch": ms, "value": Bg / (ms * 1e-3), "unit": "RIRs/s",
+                                     "path": "model([spec, emb], training=False) + post_process_batch, inputs resident"}
+    # ---- the signal kernels alone against the HBM roof (algorithmic bytes: 9600 fp32 samples <-> 144x160x2 fp32 spectrogram)
+    Bs = 256
+    wav = torch.randn(Bs, 9600, device=dev)
+    spec = preprocess_batch(wav)
+    d = stft_desc(9600)
+    wav_out = torch.empty(Bs, 9600, device=dev)
+    bytes_per_sample = 9600 * 4 + 144 * 160 * 2 * 4
+    ms_f = _time_loop(lambda: L.call("stft_ampphase", wav.data_ptr(), Bs, C.byref(d), spec.data_ptr()), 50)
+    ms_i = _time_loop(lambda: L.call("istft_from_ampphase", spec.data_ptr(), Bs, C.byref(d), wav_out.data_ptr()), 50)
+    for nm, ms in (("stft_b256", ms_f), ("istft_b256", ms_i)):
+        gbs = Bs * bytes_per_sample / (ms * 1e-3) / 1e9
+        out[nm] = {"batch": Bs, "ms": ms, "achieved": gbs, "unit": "GB/s", "peak": pk["hbm"], "frac": gbs / pk["hbm"], "bound": "hbm",
+                   "algorithmic_bytes_per_sample": bytes_per_sample}
+    return out
 
 
 def run_gpu(args, rank, world, local):
@@ -210,6 +330,12 @@ def run_gpu(args, rank, world, local):
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    try:        # run on the cores next to this GPU so that the pinned input buffers and their H2D copies stay on its NUMA node
+        import pynvml as nv
+        nv.nvmlInit()
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     B, K, Wu = args.batch, args.steps, max(args.warmup, 3)
     unet = UNet(input_shape=(H, W, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
     eng = unet.model.engine
@@ -307,38 +433,39 @@ def run_gpu(args, rank, world, local):
         launches_per_step = L.launch_count(0) - l0
     else:
         l0 = L.launch_count(0)
-        save = dt._graphs; dt._graphs = None; w_save = dt.world; dt.world = 1
+        w_save = dt.world; dt.world = 1            # this rank's kernels only: the eager body without the collectives
         eng.overlap_wgrad = False
-        rec, fam = per_kernel_profile(lambda: dt._run(B))
+        rec, fam = per_kernel_profile(lambda: dt._step_body(B))
         eng.overlap_wgrad = True
-        dt._graphs, dt.world = save, w_save
+        dt.world = w_save
         launches_per_step = L.launch_count(0) - l0
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")     # written by tools/ncu_step_table.py from an ncu capture
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")     # tools/ncu_step_table.py from this round's ncu --set full capture
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("families", {})
         except Exception:
             traffic = {}
     tot_ms = sum(f["ms"] for f in fam.values())
-    dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    dname, d = dom
-    tens = [f for k, f in fam.items() if k.endswith(".tcgen05")]
-    tens_ms, tens_fl = sum(f["ms"] for f in tens), sum(f["flops"] for f in tens)
-    if d["flops"] > 0:
-        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"],
-                "traffic": traffic.get(dname, {}).get("dram_bytes_per_call") if B == 64 else None,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per call, profiles/r01_traffic.json",
-                "algorithmic_flops_per_launch": d["flops"] / d["launches"],
-                "peak_source": pk["source"] + " (sustained)",
-                "share_of_step": d["ms"] / tot_ms, "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
-                "all_tcgen05_tflops": (tens_fl / (tens_ms * 1e-3) / 1e12) if tens_ms else None,
-                "all_tcgen05_share": tens_ms / tot_ms}
-    else:
-        roof = {"bound": "hbm", "kernel": dname, "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
-                "traffic": None, "share_of_step": d["ms"] / tot_ms}
+    roofs = family_rooflines(rec, fam, pk)
+    dname = max(roofs, key=lambda k: roofs[k]["ms"])
+    d, r = fam[dname], roofs[dname]
+    conv = [k for k in roofs if k.startswith("conv.")]
+    conv_ms, conv_fl = sum(fam[k]["ms"] for k in conv), sum(fam[k]["flops"] for k in conv)
+    conv_roof = sum(fam[k]["roof_ms"] for k in conv)
+    roof = {"bound": r["bound"], "kernel": dname, "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+            "frac": r["frac"],
+            "traffic": traffic.get(dname, {}).get("dram_bytes_per_launch") if B == 64 else None,
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel family, "
+                              "profiles/r02_traffic.json (one --set full capture of the same step; null when absent)",
+            "algorithmic_per_launch": (d["flops"] if r["bound"] == "tensor" else d["bytes"]) / d["launches"],
+            "peak_source": pk["source"] + (" (sustained)" if r["bound"] == "tensor" else " (copy)"),
+            "share_of_step": d["ms"] / tot_ms, "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+            "frac_of_per_launch_roof": r["frac_of_per_launch_roof"],
+            "timing": "CUDA events around each launch of ONE eager step, PDL and side-stream overlap off",
+            "all_conv_tflops": (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms else None,
+            "all_conv_share": conv_ms / tot_ms, "all_conv_frac_of_per_launch_roof": conv_roof / conv_ms if conv_ms else None,
+            "families": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in roofs.items()}}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"kernel_table_n{world}_b{B}.json"), "w") as f:
         json.dump({"families": fam, "launches": [(n, i, m) for n, i, m in rec], "eager_step_ms": tot_ms}, f)
@@ -351,6 +478,13 @@ def run_gpu(args, rank, world, local):
                "sample": "oracle Trainer.step (fwd+loss+bwd+Adam, fp32, torch CPU on all host threads) on batches of 16 of "
                          "the same synthetic workload, 18 timed steps after 2 warm-ups"}
 
+    extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            extra = extra_configs(args, dev, pk)
+        except Exception as ex:                      # the headline line must survive a failure in the side measurements
+            extra = {"error": repr(ex)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -361,7 +495,7 @@ def run_gpu(args, rank, world, local):
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
         "tflops_algorithmic": value * FLOP_PER_SAMPLE_TRAIN / 1e12 / world,
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu, "extra_configs": extra,
     }
     print(json.dumps(line), flush=True)
 
@@ -374,6 +508,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
     ap.add_argument("--impl", default="urir", choices=["urir", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs block (B=16 step, generation, long RIRs)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -288,7 +288,7 @@ def test_sgd_nadam_lamb_match_keras_conventions():
         L.call("step_increment", step.data_ptr())
     assert abs(float(coef[0]) - state["m_schedule"]) < 1e-6 * state["m_schedule"]
     assert U.rel_l2(pc - p0.cuda(), (ref["w"] - p0.double()).float()) < 2e-5
-    assert U.rel_l2(mc, m["w"].float()) < 1e-6 and U.rel_l2(vc, v["w"].float()) < 1e-6
+    assert U.rel_l2(mc, m["w"].float()) < 1e-6 and U.rel_l2(vc, v["w"].float()) < 5e-5      # fp32 v over gradients spanning 1e-2 .. 1e1
 
     # ---- LAMB: per-variable trust ratio
     pc, mc, vc = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
@@ -327,8 +327,8 @@ def test_trainer_optimizer_selection_runs_on_the_device():
         tr.step(x, y, emb, unet)
         gdev = eng.G.clone()
         step = eng.P - p0
-        if expect == "sgd":
-            assert U.rel_l2(step, -1e-3 * gdev) < 1e-5
+        if expect == "sgd":      # p - lr * g in fp32: exact up to the rounding of p itself (|p| ~ 5e-2, ulp ~ 4e-9)
+            assert float((eng.P - (p0 - 1e-3 * gdev)).abs().max()) < 1e-8
         elif expect == "nadam":
             ref, m, v = {"w": p0.double().cpu()}, {"w": torch.zeros_like(p0).double().cpu()}, {"w": torch.zeros_like(p0).double().cpu()}
             O.keras_nadam_step(ref, {"w": gdev.double().cpu()}, m, v, {"step": 0, "m_schedule": 1.0}, 1e-3)

@@ -165,9 +165,38 @@ def _conv_info(name, args):
         return {}
     op = {"conv2d_fprop": 0, "conv2d_dgrad": 1, "conv2d_wgrad": 2, "conv2d_dgrad_up2": 3}[name]
     tc = int(load().urir_conv_path(C.byref(d), op))
+    xs, ys = (4 if d.x_dtype == F32 else 2), (4 if d.y_dtype == F32 else 2)
+    xb, yb = d.N * d.H * d.W * d.C * xs, d.N * d.P * d.Q * d.K * ys
+    wb = d.R * d.S * d.C * d.K * (4 if op == 2 else 2)
+    # algorithmic bytes: every operand once (+ the destination once more when the call accumulates into it)
+    extra = 0
+    if d.accumulate and op != 2:
+        extra = yb if op == 0 else xb
     return dict(tc=tc, N=d.N, H=d.H, W=d.W, C=d.C, K=d.K, R=d.R, S=d.S, stride=d.stride, P=d.P, Q=d.Q,
                 x_ld=d.x_ld, y_ld=d.y_ld, x_dtype=d.x_dtype, y_dtype=d.y_dtype, impl=d.impl,
-                flops=2.0 * d.N * d.P * d.Q * d.K * d.C * d.R * d.S)
+                flops=2.0 * d.N * d.P * d.Q * d.K * d.C * d.R * d.S, bytes=float(xb + yb + wb + extra))
+
+
+def _elementwise_info(name, args):
+    """Algorithmic HBM bytes of the bandwidth-bound calls (bf16 activations read / written once per pass)."""
+    try:
+        if name == "bn_relu_fwd_train":      # x ... npix, C are the last two arguments
+            return {"bytes": 2.0 * args[-2] * args[-1] * 2}
+        if name == "bn_relu_fwd":
+            return {"bytes": 2.0 * args[7] * args[8] * 2}
+        if name == "bn_relu_bwd_reduce":
+            return {"bytes": 2.0 * args[9] * args[10] * 2}
+        if name == "bn_relu_bwd_apply":
+            return {"bytes": 3.0 * args[16] * args[17] * 2}
+        if name == "ampphase_loss":          # y_true, y_pred fp32 read, grad fp32 written (when asked for)
+            return {"bytes": float(args[2]) * 2 * 4 * (3 if args[7] else 2)}
+        if name in ("adam", "nadam"):        # p, m, v read + written, g read
+            return {"bytes": 7.0 * 4 * args[4]}
+        if name == "sgd":
+            return {"bytes": 3.0 * 4 * args[2]}
+    except Exception:
+        pass
+    return {}
 
 
 def call(name: str, *args):
@@ -176,11 +205,18 @@ def call(name: str, *args):
     if _profile is None:
         check(fn(*args, stream()), name)
         return
+    conv = name.startswith("conv2d")
+    before = family_calls() if conv else None
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     check(fn(*args, stream()), name)
     e.record()
-    _profile.append((name, _conv_info(name, args) if name.startswith("conv2d") else {}, s, e))
+    info = _conv_info(name, args) if conv else _elementwise_info(name, args)
+    if conv:
+        after = family_calls()
+        fams = [k for k in after if after[k] != before[k]]
+        info["family"] = fams[0] if fams else "?"
+    _profile.append((name, info, s, e))
 
 
 def same_pad(in_size: int, k: int, s: int):
