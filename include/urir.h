@@ -46,6 +46,9 @@ extern "C" {
 #define URIR_IMPL_HALO   3    /* persistent halo-tile tcgen05 kernel (stride-1 fprop/dgrad)
                                  or URIR_ERR_UNSUP; AUTO picks it for the wide resolutions  */
 
+#define URIR_IMPL_DEEP   4    /* persistent padded-sequence tcgen05 kernel of the deep stride-1 3x3 layers (>= 128
+                                 channels either side) or URIR_ERR_UNSUP; AUTO prefers it wherever it applies          */
+
 #define URIR_ACT_NONE    0
 #define URIR_ACT_SIGMOID 1
 #define URIR_ACT_RELU    2    /* inference: BatchNorm folded into weights / bias, ReLU in the epilogue */

@@ -471,3 +471,73 @@ def test_stride2_wgrad_through_parity_planes(case):
     dw = torch.full((3, 3, Cc, K), 3.0, device="cuda")
     U.run_wgrad(d, xw, dy.cuda().to(torch.bfloat16), dw)
     assert U.rel_l2(dw, gw) < F32_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: the persistent padded-sequence kernel of the deep stride-1 layers (conv_deep.cu, URIR_IMPL_DEEP)
+# ------------------------------------------------------------------------------------------------
+DEEP_CASES = [
+    # (N, H, W, C, K): every deep stride-1 3x3 layer of the canonical net (E3b..E5b, D2a/b, D3a/b) at reduced batch,
+    # chosen so that CTAs get 0, 1 and several M tiles, tiles span images, and two rounds occur (36x40 with 12 images)
+    (3, 9, 10, 512, 512),
+    (64, 9, 10, 512, 512),          # the benchmark's bottleneck layer as is: 55 M tiles x 4 N tiles
+    (5, 18, 20, 256, 256),
+    (16, 18, 20, 512, 256),
+    (12, 36, 40, 256, 128),         # 148 CTAs x 5-6 tiles: two rounds of three
+    (2, 36, 40, 128, 128),
+    (2, 36, 76, 128, 256),          # long-RIR width (config 5): Wp = 77
+]
+
+
+@pytest.mark.parametrize("case", DEEP_CASES, ids=[str(c) for c in DEEP_CASES])
+def test_deep_kernel_fprop_dgrad(case):
+    N, H, W, Cc, K = case
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, 3, 1, seed=N + H)
+    xg, dyg = x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16)
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    bg = bias.cuda()
+    d = U.conv_desc(N, H, W, Cc, K, 3, 1, impl=L.IMPL_DEEP)
+    fam0 = L.family_calls()["deep"]
+    # AUTO picks this kernel for these shapes
+    da = U.conv_desc(N, H, W, Cc, K, 3, 1, impl=L.IMPL_AUTO)
+    assert L.load().urir_conv_path(C.byref(da), 0) == 1
+    y = torch.full((N, H, W, K), 7.0, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2 * K, device="cuda")
+    U.run_fprop(d, xg, w_ck, w_kc, bg, y, stats)
+    ref = _oracle_fprop(x, w, bias, 1)
+    assert U.rel_l2(y.float(), ref) < BF16_TOL, U.rel_l2(y.float(), ref)
+    assert U.rel_l2(stats[:K], ref.sum(dim=(0, 1, 2))) < 5e-3 or U.max_abs(stats[:K], ref.sum(dim=(0, 1, 2))) < 1e-2 * (N ** 0.5)
+    assert U.rel_l2(stats[K:], (ref ** 2).sum(dim=(0, 1, 2))) < F32_TOL * 10
+    # bit-comparable with the one-tile-per-CTA tcgen05 kernel (same bf16 operands, fp32 accumulation, one rounding)
+    y2 = torch.empty_like(y)
+    U.run_fprop(U.conv_desc(N, H, W, Cc, K, 3, 1, impl=L.IMPL_TC), xg, w_ck, w_kc, bg, y2, None)
+    assert U.rel_l2(y.float(), y2.float()) < 2e-3
+    # dgrad, with the bias-gradient statistics
+    xr = x.clone().requires_grad_(True)
+    yr = _oracle_fprop(xr, w, None, 1)
+    (gx,) = torch.autograd.grad(yr, [xr], dy)
+    dx = torch.full((N, H, W, Cc), 7.0, dtype=torch.bfloat16, device="cuda")
+    dstats = torch.zeros(2 * Cc, device="cuda")
+    U.run_dgrad(d, dyg, w_ck, w_kc, None, dx, dstats)
+    assert U.rel_l2(dx.float(), gx) < BF16_TOL, U.rel_l2(dx.float(), gx)
+    assert U.max_abs(dstats[:Cc], gx.sum(dim=(0, 1, 2))) < 2e-3 * float(gx.abs().sum(dim=(0, 1, 2)).max())
+    assert L.family_calls()["deep"] - fam0 == 2
+
+
+def test_deep_kernel_concat_slices_and_relu():
+    """Reads a channel slice of a wider buffer and writes into one (skip-concat halves, u_net.py:308), ReLU epilogue of
+    the BatchNorm-folded inference path, AUTO dispatch."""
+    N, H, W, Cc, K = 4, 18, 20, 256, 256
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, 3, 1, seed=5)
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    xbuf = torch.zeros(N, H, W, 2 * Cc, dtype=torch.bfloat16, device="cuda")
+    xbuf[..., Cc:] = x.cuda().to(torch.bfloat16)
+    xbuf[..., :Cc] = 9.0                                         # must not be read
+    ybuf = torch.full((N, H, W, 2 * K), 3.0, dtype=torch.bfloat16, device="cuda")
+    d = U.conv_desc(N, H, W, Cc, K, 3, 1, x_ld=2 * Cc, x_coff=Cc, y_ld=2 * K, y_coff=0, impl=L.IMPL_AUTO, act=L.ACT_RELU)
+    fam0 = L.family_calls()["deep"]
+    U.run_fprop(d, xbuf, w_ck, w_kc, bias.cuda(), ybuf, None)
+    assert L.family_calls()["deep"] == fam0 + 1
+    ref = torch.relu(_oracle_fprop(x, w, bias, 1))
+    assert U.rel_l2(ybuf[..., :K].float(), ref) < BF16_TOL
+    assert float((ybuf[..., K:].float() - 3.0).abs().max()) == 0.0

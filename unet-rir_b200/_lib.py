@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liburir.so")
 
 F32, BF16 = 0, 1
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_HALO = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_HALO, IMPL_DEEP = 0, 1, 2, 3, 4
 ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
 
 

@@ -4,7 +4,7 @@ set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="$here/../liburir.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-srcs=(capi.cu conv_simt.cu conv_stem.cu conv_igemm.cu conv_wgrad_tc.cu conv_thin.cu conv_head.cu conv_halo.cu conv_wgrad_halo.cu elementwise.cu vector_block.cu stft.cu)
+srcs=(capi.cu conv_simt.cu conv_stem.cu conv_igemm.cu conv_wgrad_tc.cu conv_thin.cu conv_head.cu conv_halo.cu conv_deep.cu conv_wgrad_halo.cu elementwise.cu vector_block.cu stft.cu)
 mkdir -p "$here/build"
 pids=()
 for s in "${srcs[@]}"; do
