@@ -522,12 +522,15 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-    try:
-        run_gpu(args, rank, world, local)
-    finally:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+    run_gpu(args, rank, world, local)
+    if world > 1:
+        # the captured DP-step graphs hold NCCL kernels; tearing the communicator down behind them can hang
+        # (tools/dp_parity.py, round 2). The line is printed: leave without NCCL's teardown.
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -87,7 +87,7 @@ bool halo_s2_fprop_supported(const urir_conv_desc*, bool forced);
 int conv_halo_s2_fprop(const urir_conv_desc*, const void*, const void*, const float*, void*, float*, cudaStream_t);
 int conv_halo_up2(const urir_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int weight_prep_up2(const float*, void*, int, int, cudaStream_t);
-bool deep_supported(const urir_conv_desc*, int op);
+bool deep_supported(const urir_conv_desc*, int op, bool wide_ok);
 int conv_deep(const urir_conv_desc*, int op, const void*, const void*, const float*, void*, float*, cudaStream_t);
 bool head_fprop_supported(const urir_conv_desc*);
 int head_fprop(const urir_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
@@ -175,9 +175,9 @@ int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, 
     if (w_kc && d->stride == 2 && d->impl != URIR_IMPL_SIMT && d->impl != URIR_IMPL_TC && !env_force_simt() &&
         halo_s2_fprop_supported(d, d->impl == URIR_IMPL_HALO))
         return fam(URIR_FAM_HALO_S2_FPROP, conv_halo_s2_fprop(d, x, w_kc, bias, y, stats, st));
-    if (d->impl == URIR_IMPL_DEEP && !(w_kc && deep_supported(d, 0)))
+    if (d->impl == URIR_IMPL_DEEP && !(w_kc && deep_supported(d, 0, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the deep-layer tcgen05 path");
-    if (w_kc && (d->impl == URIR_IMPL_DEEP || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && deep_supported(d, 0))))
+    if (w_kc && (d->impl == URIR_IMPL_DEEP || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && deep_supported(d, 0, !halo_supported(d, 0, false)))))
         return fam(URIR_FAM_DEEP, conv_deep(d, 0, x, w_kc, bias, y, stats, st));
     if (d->impl == URIR_IMPL_HALO && !(w_kc && halo_supported(d, 0, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_fprop: shape not supported by the halo-tile tcgen05 path");
@@ -198,9 +198,9 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
     cudaStream_t st = (cudaStream_t)stream;
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && !bias && thin_supported(d, 1))
         return fam(URIR_FAM_THIN_GEMM, thin_gemm(d, dy, w_ck, nullptr, dx, false, st));                 // the 2-channel head
-    if (d->impl == URIR_IMPL_DEEP && !(w_ck && deep_supported(d, 1)))
+    if (d->impl == URIR_IMPL_DEEP && !(w_ck && deep_supported(d, 1, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the deep-layer tcgen05 path");
-    if (w_ck && (d->impl == URIR_IMPL_DEEP || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && deep_supported(d, 1))))
+    if (w_ck && (d->impl == URIR_IMPL_DEEP || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && deep_supported(d, 1, !halo_supported(d, 1, false)))))
         return fam(URIR_FAM_DEEP, conv_deep(d, 1, dy, w_ck, bias, dx, stats, st));
     if (d->impl == URIR_IMPL_HALO && !(w_ck && halo_supported(d, 1, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the halo-tile tcgen05 path");
@@ -246,7 +246,7 @@ int urir_conv_path(const urir_conv_desc* d, int op) {
     if (op == 3) return (d && d->impl != URIR_IMPL_SIMT && !(d->impl == URIR_IMPL_AUTO && env_force_simt()) && halo_up2_supported(d)) ? 1 : 0;
     if (!d || d->impl == URIR_IMPL_SIMT || (d->impl == URIR_IMPL_AUTO && env_force_simt())) return 0;
     if (thin_supported(d, op)) return 1;
-    if (op < 2 && deep_supported(d, op)) return 1;
+    if (op < 2 && deep_supported(d, op, true)) return 1;
     if (op < 2 && halo_supported(d, op, d->impl == URIR_IMPL_HALO)) return 1;
     if (op == 0 && halo_s2_fprop_supported(d, d->impl == URIR_IMPL_HALO)) return 1;
     if (op == 2 && wgrad_halo_supported(d, d->impl == URIR_IMPL_HALO)) return 1;

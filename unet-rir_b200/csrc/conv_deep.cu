@@ -339,7 +339,8 @@ static void deep_split(int Wp, int* w_stages, int* a_slots) {
 }
 
 // op 0: fprop (GEMM-K = C, GEMM-N = K), op 1: dgrad (GEMM-K = K, GEMM-N = C)
-bool deep_supported(const urir_conv_desc* d, int op) {
+// wide_ok: also admit widths above URIR_DEEP_WMAX (forced, or no halo-tile kernel takes the layer)
+bool deep_supported(const urir_conv_desc* d, int op, bool wide_ok) {
     { static int off = -1; if (off < 0) { const char* e = getenv("URIR_NO_DEEP"); off = (e && e[0] == '1') ? 1 : 0; } if (off) return false; }
     if (d->stride != 1 || d->R != 3 || d->S != 3 || d->pad_top != 1 || d->pad_left != 1 || d->P != d->H || d->Q != d->W) return false;
     if (d->x_dtype != URIR_BF16 || d->y_dtype != URIR_BF16 || d->accumulate) return false;
@@ -354,7 +355,7 @@ bool deep_supported(const urir_conv_desc* d, int op) {
     // at 36x40 and above the halo-tile kernel (resident weights of one N tile) measured faster: 40 / 70 us against 54 / 95
     // for 128 -> 128 / 256 -> 128 at 36x40, B = 64 (profiles/r02_deep_kernel.txt); this kernel takes the levels below
     { static int wmax = -1; if (wmax < 0) { const char* e = getenv("URIR_DEEP_WMAX"); wmax = e ? atoi(e) : 24; }
-      if (d->W > wmax && d->impl != URIR_IMPL_DEEP) return false; }
+      if (d->W > wmax && !wide_ok) return false; }
     if ((long long)d->N * (d->H + 1) * Wp + 2LL * Wp + 256 >= (1LL << 30)) return false;
     return true;
 }

@@ -386,6 +386,10 @@ def main(n_epochs=2, steps_per_epoch=8, per_replica_batch=16, lr=5e-7, alpha=0.9
     history = train_loop(trainer, train_generator, val_generator, n_epochs, manager, lr_exp_decay, rank, world,
                          max_steps=steps_per_epoch)
     if world > 1:
+        # graphs that captured NCCL kernels must go before the communicator does (teardown behind them can hang)
+        trainer._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
     return history
 
