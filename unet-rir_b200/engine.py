@@ -633,10 +633,13 @@ class UNetEngine:
         o, n = slots[key]
         return self.bstat_arena[o:o + n]
 
-    def _backward_body(self, B, segment=None, dense_dw=True):
+    def _backward_body(self, B, segment=None, dense_dw=True, join=True):
         """segment: None = everything; 0 = head + decoder, 1 = bottleneck / vector block, 2 = encoder
         (the order gradients become final, used for bucketed all-reduce overlap). dense_dw=False leaves the Dense
-        kernel / bias gradients to dense_grad_from_gathered (data-parallel: gather operands, not gradients)."""
+        kernel / bias gradients to dense_grad_from_gathered (data-parallel: gather operands, not gradients).
+        join=False: do not make the main stream wait for the side-stream gradient kernels at the end of segments 0 / 1
+        (the caller orders its consumer -- the bucket's all-reduce -- after BOTH streams itself, so the next segment's
+        dgrad chain keeps overlapping the weight / Dense gradients exactly as in the unsegmented step)."""
         b = self._buffers(B)
         k = self.kernels
         if segment in (None, 0):
@@ -674,7 +677,7 @@ class UNetEngine:
                 self._conv_fprop(f"dec{j}.up", g_up, g_x_in, k, 2, stats=st2, bias=False)   # ConvT dgrad
                 if j == 2:
                     self.grad["vec.proj.b"].copy_(st2[:x_in.C])
-            if segment == 0:
+            if segment == 0 and join:
                 self._join_side()
         if segment in (None, 1):
             # bottleneck: z = e5 + proj(v16)
@@ -690,7 +693,7 @@ class UNetEngine:
                        b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
                 L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), L.BF16,
                        self.grad["vec.emb"].data_ptr(), B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
-            if segment == 1:
+            if segment == 1 and join:
                 self._join_side()
         if segment in (None, 2):
             # encoder, level 5 up to level 1

@@ -103,6 +103,13 @@ class DistributedTrainer:
         self._o_dense = o["vec.dense.w"][0]
         self._o_after_dense = o["vec.dense.b"][0] + o["vec.dense.b"][1]
         self._gathered = None
+        # A bucket's all-reduce must see the weight / Dense gradients the side stream produces, but the MAIN stream need not:
+        # the collective is issued from an auxiliary stream that waits for both, and the next segment's dgrad chain keeps
+        # running beside those gradient kernels as in the single-GPU step (URIR_DP_JOIN=1 restores round 1's joins, which
+        # serialised e.g. the Dense gradient in front of the whole encoder backward: +0.25 ms per step at world 1).
+        self._segment_join = (os.environ.get("URIR_DP_JOIN", "0") == "1" or self.graph_mode == "segments" or self.gather_dense
+                              or not self.overlap)
+        self._aux = torch.cuda.Stream(device=self.eng.device)
         # MirroredStrategy gives every replica its own Dropout mask: mix the rank into the mask stream's seed
         self.eng.dropout_seed = (self.eng.dropout_seed + 0x9E3779B1 * self.rank) & 0x7FFFFFFFFFFFFFFF
         self.eng.set_lr(lr)
@@ -124,10 +131,10 @@ class DistributedTrainer:
         wa, wp = self._weights(B)
         L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), B * e.input_shape[0] * e.input_shape[1],
                wa, wp, 1, e.losses_dev.data_ptr(), b["g_out"].data_ptr(), None, 0)
-        e._backward_body(B, segment=0)
+        e._backward_body(B, segment=0, join=self._segment_join)
 
     def _seg_bottleneck(self, B):
-        self.eng._backward_body(B, segment=1, dense_dw=not self.gather_dense)
+        self.eng._backward_body(B, segment=1, dense_dw=not self.gather_dense, join=self._segment_join)
 
     def _seg_encoder(self, B):
         self.eng._backward_body(B, segment=2)
@@ -146,6 +153,14 @@ class DistributedTrainer:
         """All-reduce of gradient bucket i (async, on NCCL's stream) right after backward segment i was enqueued."""
         e = self.eng
         lo, hi = self.buckets[i]
+        if not self._segment_join and not self.gather_dense:
+            main = torch.cuda.current_stream()
+            self._aux.wait_stream(main)
+            self._aux.wait_stream(e.side)
+            with torch.cuda.stream(self._aux):
+                works.append(dist.all_reduce(e.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            state["aux"] = True
+            return
         if not self.gather_dense or i == 0:
             works.append(dist.all_reduce(e.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
         elif i == 1:
@@ -173,6 +188,9 @@ class DistributedTrainer:
                     works.append(dist.all_reduce(self.eng.G, op=dist.ReduceOp.SUM, async_op=True))
                 for w in works:
                     w.wait()
+                if state.get("aux"):
+                    torch.cuda.current_stream().wait_stream(self._aux)
+                self.eng._join_side()
             if graphs is not None:
                 graphs[i].replay()
             else:
