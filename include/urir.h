@@ -229,6 +229,12 @@ int urir_ampphase_loss(const float* y_true, const float* y_pred, long long npix,
                        float w_ph, int sigmoid_bwd, float* losses, float* grad, void* grad_bf16,
                        int grad_bf16_ld, void* stream);
 
+/* The generic trainer's loss (trainer.py:146-156): squared error over BOTH channels. y_true, y_pred fp32 [npix, 2].
+ * losses[4] (overwritten) = [w * SSE(amp and phase), mean(1 - cos) of the phase channel, mean sq err of the amp channel,
+ * mean sq err over both]; grad (optional) = 2 w (y_pred - y_true), times y(1-y) when sigmoid_bwd != 0. */
+int urir_mse2_loss(const float* y_true, const float* y_pred, long long npix, float w, int sigmoid_bwd, float* losses,
+                   float* grad, void* stream);
+
 /* ---- optimiser (amp_phase_trainer.py:30-35,139 ; Keras conventions) ------ */
 /* flat Adam over n contiguous fp32 elements; lr and step (0-based count of completed steps)
  * are read from device memory so a captured graph follows the LR schedule. */

@@ -6,6 +6,7 @@ sources with `ast` (no reference source is copied into the repo), executes them,
 outputs on seeded inputs:
   * preprocess.py : Normalizer.normalize / denormalize, TensorPadder.pad_amp_phase / un_pad, sigmoid
   * amp_phase_trainer.py : ModelCheckpoint.checkpoint / EarlyStopping.stop_count decision traces
+  * trainer.py : the generic trainer's ModelCheckpoint(min_delta) / EarlyStopping decision trace
 The U-Net graph (Keras), the STFT (librosa) and the losses (tf ops) cannot be executed here; for those the
 oracle is a restatement (parity unpinned, see oracle/*.py headers).
 
@@ -65,7 +66,18 @@ def main():
         stop = es.stop_count(improve=imp)
         trace.append({"train": t, "val": v, "improve": bool(imp), "stop": bool(stop), "count": es.count,
                       "val_min": mc.val_loss_min, "train_min": mc.train_loss_min, "saved": fm.saved})
-    json.dump({"patience": 3, "trace": trace}, open(os.path.join(OUT, "callbacks_golden.json"), "w"), indent=1)
+    # trainer.py: the generic trainer's ModelCheckpoint(min_delta) (:175-205) on a trace with sub-min_delta improvements
+    cb2 = lift(os.path.join(REF, "trainer.py"), {"ModelCheckpoint", "EarlyStopping"})
+    val2 = [12.0, 9.5, 9.49995, 9.4999, 9.3, 9.29995, 9.4, 9.29991, 9.2998, 9.0]
+    mc2, es2, fm2 = cb2["ModelCheckpoint"]("ckpt", True, 0), cb2["EarlyStopping"](3), FakeModel()
+    trace2 = []
+    for i, v in enumerate(val2):
+        imp = mc2.checkpoint(train_loss=float(10 - i), val_loss=v, model=fm2)
+        stop = es2.stop_count(improve=imp)
+        trace2.append({"train": float(10 - i), "val": v, "improve": bool(imp), "stop": bool(stop), "count": es2.count,
+                       "val_min": mc2.val_loss_min, "train_min": mc2.train_loss_min, "saved": fm2.saved})
+    json.dump({"patience": 3, "trace": trace, "generic_trainer": {"patience": 3, "min_delta": 0.0001, "trace": trace2}},
+              open(os.path.join(OUT, "callbacks_golden.json"), "w"), indent=1)
     # rooms.py: the 16-int embedding of every (room, zone, array type, loudspeaker, microphone) combination sampled
     rm = lift(os.path.join(REF, "rooms.py"), {"Quadrilateral", "Room", "UTSRoom", "return_room"})
     rooms = {"AnechoicRoom": (490, 722, 490, 722, 90, 90, 90, 90, 529, [245, 361], 45),

@@ -340,3 +340,42 @@ def test_trainer_optimizer_selection_runs_on_the_device():
         for _ in range(2):                      # capture + replay stay finite
             l = tr.step(x, y, emb, unet)[0]
         assert bool(torch.isfinite(l))
+
+
+def test_generic_trainer_mse_loss_and_lamb_step():
+    """trainer.py: loss = squared error over both channels, differentiated as the SUM of the per-pixel channel means
+    (tape.gradient of a non-scalar), optimiser 'lamb' -> tensorflow_addons LAMB. One step against torch autograd of the same
+    scalar through the oracle graph (on the device's forward state) and the oracle's LAMB."""
+    from unet_rir_b200.dl_models.u_net import UNet
+    from unet_rir_b200.trainer import EarlyStopping, ModelCheckpoint, Trainer
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(2, 144, 160, 2, generator=g); y = torch.rand(2, 144, 160, 2, generator=g)
+    emb = torch.randint(0, 2000, (2, 2, 16), generator=g, dtype=torch.int32)
+    # the loss kernel alone
+    yp = torch.rand(2, 144, 160, 2, generator=g)
+    out = torch.empty(4, device="cuda"); grad = torch.empty(2, 144, 160, 2, device="cuda")
+    L.call("mse2_loss", y.cuda().data_ptr(), yp.cuda().data_ptr(), 2 * 144 * 160, 0.5, 1, out.data_ptr(), grad.data_ptr())
+    d = yp - y
+    assert abs(float(out[0]) - 0.5 * float((d ** 2).sum())) < 1e-4 * float((d ** 2).sum())
+    assert abs(float(out[3]) - float((d ** 2).mean())) < 1e-6 and abs(float(out[2]) - float((d[..., 0] ** 2).mean())) < 1e-6
+    assert abs(float(out[1]) - float((1 - torch.cos(2 * math.pi * d[..., 1])).mean())) < 1e-5
+    assert U.rel_l2(grad.cpu(), d * yp * (1 - yp)) < 1e-5
+    # one LAMB step through the trainer
+    unet = UNet(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32, kernels=3)
+    eng = unet.model.engine
+    tr = Trainer(0.9, 1, "lamb", [ModelCheckpoint("/tmp/urir_gt", False, 0), EarlyStopping(5)], [False, 0], 1e-3, "gt")
+    assert tr.optimizer == "lamb"
+    tr.dropout = False
+    p0 = {n: eng.param[n].detach().cpu().clone() for n in eng.trainable_names()}
+    loss, lp, ls = tr.step(x, y, emb, unet)
+    outp = eng._buffers(2)["out"].cpu()
+    assert abs(float(loss) - float(((outp - y) ** 2).mean())) < 1e-5
+    ref = {n: p0[n].double() for n in p0}
+    m = {n: torch.zeros_like(t) for n, t in ref.items()}
+    v = {n: torch.zeros_like(t) for n, t in ref.items()}
+    O.tfa_lamb_step(ref, {n: eng.grad[n].double().cpu() for n in ref}, m, v, 1, 1e-3)
+    for n in ("enc3.blk.c1.w", "dec2.fuse.w", "vec.dense.w", "head.w", "enc1.blk.bn1.gamma"):
+        got, want = eng.param[n].detach().cpu() - p0[n], (ref[n] - p0[n].double()).float()
+        assert U.rel_l2(got, want) < 2e-3, (n, U.rel_l2(got, want))
+    for _ in range(2):
+        assert bool(torch.isfinite(tr.step(x, y, emb, unet)[0]))

@@ -193,3 +193,27 @@ def test_room_embeddings_match_reference_rooms_py():
         assert [float(v) for v in got] == c["embedding"], c
     assert R.return_room([994]) == "Large" and R.return_room([1]) is None
     assert max(max(c["embedding"]) for c in d["cases"]) < 2000          # fits Embedding(2000, 256), u_net.py:257
+
+
+def test_generic_trainer_callbacks_match_reference_trace():
+    """trainer.py:175-205 executed from the reference source (tests/golden/make_golden.py): `improve` needs min_delta, the
+    running minimum / saving do not."""
+    import json
+    from unet_rir_b200.trainer import EarlyStopping, ModelCheckpoint
+    tr = json.load(open(os.path.join(GOLD, "callbacks_golden.json")))["generic_trainer"]
+
+    class FakeModel:
+        saved = 0
+
+        def save(self, path):
+            self.saved += 1
+
+    mc, es, fm = ModelCheckpoint("ckpt", True, 0, tr["min_delta"]), EarlyStopping(tr["patience"]), FakeModel()
+    seen = set()
+    for row in tr["trace"]:
+        imp = mc.checkpoint(train_loss=row["train"], val_loss=row["val"], model=fm)
+        stop = es.stop_count(improve=imp)
+        assert (bool(imp), bool(stop), es.count, mc.val_loss_min, mc.train_loss_min, fm.saved) == \
+               (row["improve"], row["stop"], row["count"], row["val_min"], row["train_min"], row["saved"])
+        seen.add((row["improve"], row["saved"] > 0))
+    assert any(not r["improve"] and r["val_min"] == r["val"] for r in tr["trace"])     # a saved-but-not-improved epoch occurs

@@ -68,6 +68,7 @@ _PROTOS = {
     "urir_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "urir_dropout_mask": (_i, [_vp, _ll, _f, _u64, _vp, _vp]),
     "urir_ampphase_loss": (_i, [_vp, _vp, _ll, _f, _f, _i, _vp, _vp, _vp, _i, _vp]),
+    "urir_mse2_loss": (_i, [_vp, _vp, _ll, _f, _i, _vp, _vp, _vp]),
     "urir_adam": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _f, _f, _vp]),
     "urir_sgd": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "urir_nadam": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _f, _f, _f, _vp]),

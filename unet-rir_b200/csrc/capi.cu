@@ -107,6 +107,7 @@ int bn_relu_bwd_apply(const void*, int, int, const void*, int, int, const float*
                       void*, int, int, float*, float*, float*, long long, int, int, cudaStream_t);
 int channel_sum(const void*, int, long long, int, int, int, float*, cudaStream_t);
 int ampphase_loss(const float*, const float*, long long, float, float, int, float*, float*, void*, int, cudaStream_t);
+int mse2_loss(const float*, const float*, long long, float, int, float*, float*, cudaStream_t);
 int adam(float*, const float*, float*, float*, long long, const float*, const int*, float, float, float, cudaStream_t);
 int sgd(float*, const float*, long long, const float*, cudaStream_t);
 int nadam(float*, const float*, float*, float*, long long, const float*, const int*, float*, float, float, float, cudaStream_t);
@@ -336,6 +337,12 @@ int urir_ampphase_loss(const float* y_true, const float* y_pred, long long npix,
     URIR_CHECK_ARG(y_true && y_pred && losses, "ampphase_loss: null tensor");
     return ampphase_loss(y_true, y_pred, npix, w_amp, w_ph, sigmoid_bwd, losses, grad, grad_bf16, grad_bf16_ld,
                          (cudaStream_t)stream);
+}
+
+int urir_mse2_loss(const float* y_true, const float* y_pred, long long npix, float w, int sigmoid_bwd, float* losses,
+                   float* grad, void* stream) {
+    URIR_CHECK_ARG(y_true && y_pred && losses, "mse2_loss: null tensor");
+    return mse2_loss(y_true, y_pred, npix, w, sigmoid_bwd, losses, grad, (cudaStream_t)stream);
 }
 
 int urir_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, const int32_t* step_dev,

@@ -652,6 +652,52 @@ ampphase_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ y
     gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
 }
 
+// Mean-squared error over BOTH channels, the loss of the generic trainer (trainer.py:146-156: `loss =
+// amplitude_loss(y_true, y_pred)`), with the amp / phase metrics it reports beside it.
+// losses = [w * SSE(all), mean(1 - cos) of the phase channel, mean sq err of the amp channel, mean sq err of all];
+// grad = 2 w (p - t) (times p (1 - p) with sigmoid_bwd).
+__global__ void __launch_bounds__(256)
+mse2_loss_kernel(const float4* __restrict__ yt, const float4* __restrict__ yp, long long npair, long long npix, float w,
+                 int sigmoid_bwd, float* __restrict__ losses, float4* __restrict__ grad, unsigned int* gate) {
+    const float TWO_PI = 6.283185307179586f;
+    float sa = 0.f, sp = 0.f, pc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += (long long)gridDim.x * blockDim.x) {
+        const float4 t = __ldg(yt + i), p = __ldg(yp + i);
+        const float d0 = p.x - t.x, d1 = p.y - t.y, d2 = p.z - t.z, d3 = p.w - t.w;
+        sa += d0 * d0 + d2 * d2; sp += d1 * d1 + d3 * d3;
+        pc += (1.f - cosf(TWO_PI * d1)) + (1.f - cosf(TWO_PI * d3));
+        if (grad) {
+            float4 g = make_float4(2.f * w * d0, 2.f * w * d1, 2.f * w * d2, 2.f * w * d3);
+            if (sigmoid_bwd) { g.x *= p.x * (1.f - p.x); g.y *= p.y * (1.f - p.y); g.z *= p.z * (1.f - p.z); g.w *= p.w * (1.f - p.w); }
+            grad[i] = g;
+        }
+    }
+    __shared__ float r1[8], r2[8], r3[8];
+    sa = warp_sum(sa); sp = warp_sum(sp); pc = warp_sum(pc);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = sa; r2[threadIdx.x >> 5] = sp; r3[threadIdx.x >> 5] = pc; }
+    __syncthreads();
+    gate_enter(gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int i = 0; i < 8; ++i) { a += r1[i]; b += r2[i]; c += r3[i]; }
+        const float inv = 1.f / (float)npix;
+        atomicAdd(losses + 0, w * (a + b));
+        atomicAdd(losses + 1, c * inv);
+        atomicAdd(losses + 2, a * inv);
+        atomicAdd(losses + 3, (a + b) * inv * 0.5f);
+    }
+    gate_leave(gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
+}
+int mse2_loss(const float* yt, const float* yp, long long npix, float w, int sigmoid_bwd, float* losses, float* grad, cudaStream_t st) {
+    URIR_CHECK_ARG(npix > 0 && npix % 2 == 0, "mse2_loss: npix must be even");
+    URIR_CUDA_OK(cudaMemsetAsync(losses, 0, 4 * sizeof(float), st));
+    const long long npair = npix / 2;
+    mse2_loss_kernel<<<grid_for(npair, 256), 256, 0, st>>>((const float4*)yt, (const float4*)yp, npair, npix, w, sigmoid_bwd,
+                                                           losses, (float4*)grad, next_gate());
+    URIR_LAUNCH_OK(0);
+    return URIR_OK;
+}
+
 int ampphase_loss(const float* yt, const float* yp, long long npix, float w_amp, float w_ph, int sigmoid_bwd,
                   float* losses, float* grad, void* grad16, int ld16, cudaStream_t st) {
     URIR_CHECK_ARG(npix > 0 && npix % 2 == 0, "ampphase_loss: npix must be even");
