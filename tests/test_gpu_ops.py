@@ -354,7 +354,8 @@ def test_generic_trainer_mse_loss_and_lamb_step():
     # the loss kernel alone
     yp = torch.rand(2, 144, 160, 2, generator=g)
     out = torch.empty(4, device="cuda"); grad = torch.empty(2, 144, 160, 2, device="cuda")
-    L.call("mse2_loss", y.cuda().data_ptr(), yp.cuda().data_ptr(), 2 * 144 * 160, 0.5, 1, out.data_ptr(), grad.data_ptr())
+    yd, ypd = y.cuda(), yp.cuda()           # named: a temporary's storage would be recycled for the second .cuda()
+    L.call("mse2_loss", yd.data_ptr(), ypd.data_ptr(), 2 * 144 * 160, 0.5, 1, out.data_ptr(), grad.data_ptr())
     d = yp - y
     assert abs(float(out[0]) - 0.5 * float((d ** 2).sum())) < 1e-4 * float((d ** 2).sum())
     assert abs(float(out[3]) - float((d ** 2).mean())) < 1e-6 and abs(float(out[2]) - float((d[..., 0] ** 2).mean())) < 1e-6
