@@ -83,15 +83,29 @@ def conv2d_transpose_same(x_nchw, w_hwoi, b, stride):
 # ----------------------------------------------------------------------------------------
 # Parameter inventory (Keras creation order == model.trainable_variables order)
 # ----------------------------------------------------------------------------------------
+# What the sibling DiffUNet (dl_models/diff_u_net.py:205-322) changes in the graph: 2x2 strided / transposed kernels
+# (:272-279, :300-307), 3x3 fuse convolution (:312), Embedding(1500, 128) -> Dense(H5 W5 16 F0) -> Dropout(.5) added to the
+# bottleneck without a 1x1 projection (:261-270, :230-231), linear 1x1 head (:256-257).
+def arch_table(arch, number_filters_0, kernels):
+    if arch == "unet":
+        return dict(down_k=kernels, up_k=kernels, fuse_k=kernels, head_k=6, head_sigmoid=True, emb_vocab=2000, emb_dim=256,
+                    vec_ch=16, proj=True)
+    if arch == "diff":
+        return dict(down_k=2, up_k=2, fuse_k=3, head_k=1, head_sigmoid=False, emb_vocab=1500, emb_dim=128,
+                    vec_ch=16 * number_filters_0, proj=False)
+    raise ValueError(arch)
+
+
 def layer_plan(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0,
-               number_filters_0=32, kernels=6, BatchNorm=True):
+               number_filters_0=32, kernels=6, BatchNorm=True, arch="unet"):
     """Returns the ordered list of (name, shape, kind) for every variable of the model.
 
     kind in {conv_w, convT_w, bias, gamma, beta, moving_mean, moving_var, emb, dense_w}.
     Order follows layer creation order in UNet._build (u_net.py:201-251), which is the order of
     `model.trainable_variables` that Trainer.step walks (amp_phase_trainer.py:137-139).
     """
-    F0, k = number_filters_0, kernels
+    F0 = number_filters_0
+    A = arch_table(arch, number_filters_0, kernels)
     plan = []
 
     def conv(name, kh, cin, cout):
@@ -128,24 +142,25 @@ def layer_plan(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0,
     mults = [1, 2, 4, 8, 16]
     for i, m in enumerate(mults):
         n = F0 * m
-        conv(f"enc{i+1}.down", k, cin, n)
+        conv(f"enc{i+1}.down", A["down_k"], cin, n)
         block(f"enc{i+1}.blk", n, n)
         cin = n
     H5 = input_shape[0] // 16
     W5 = input_shape[1] // 16
-    dim = H5 * W5 * 16
-    plan.append(("vec.emb", (2000, 256), "emb"))
-    plan.append(("vec.dense.w", (inf_vector_shape[0] * inf_vector_shape[1] * 256, dim), "dense_w"))
+    dim = H5 * W5 * A["vec_ch"]
+    plan.append(("vec.emb", (A["emb_vocab"], A["emb_dim"]), "emb"))
+    plan.append(("vec.dense.w", (inf_vector_shape[0] * inf_vector_shape[1] * A["emb_dim"], dim), "dense_w"))
     plan.append(("vec.dense.b", (dim,), "bias"))
-    conv("vec.proj", 1, 16, F0 * 16)
+    if A["proj"]:
+        conv("vec.proj", 1, A["vec_ch"], F0 * 16)
     for j, m in zip([2, 3, 4, 5], [8, 4, 2, 1]):
         n = F0 * m
-        convT(f"dec{j}.up", k, cin, n)
+        convT(f"dec{j}.up", A["up_k"], cin, n)
         # concat([skip(n), up(n)]) -> conv(kernels)+BN+ReLU (u_net.py:308-310) -> mode block
-        conv(f"dec{j}.fuse", k, 2 * n, n); bn(f"dec{j}.fuse_bn", n)
+        conv(f"dec{j}.fuse", A["fuse_k"], 2 * n, n); bn(f"dec{j}.fuse_bn", n)
         block(f"dec{j}.blk", n, n)
         cin = n
-    conv("head", 6, cin, 2)
+    conv("head", A["head_k"], cin, 2)
     return plan
 
 
@@ -197,7 +212,7 @@ class UNetOracle:
 
     def __init__(self, input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0,
                  number_filters_0=32, kernels=6, BatchNorm=True, bn_moving_var_unbiased=False,
-                 emulate_bf16=False):
+                 emulate_bf16=False, arch="unet"):
         # emulate_bf16: evaluate the SAME graph under the device path's storage contract -- conv / Dense
         # operands (activations, kernels) and every stored activation rounded to bfloat16, fp32
         # accumulation, fp32 BatchNorm statistics taken before the rounding (straight-through in
@@ -212,7 +227,9 @@ class UNetOracle:
         self.kernels = kernels
         self.BatchNorm = BatchNorm
         self.bn_unbiased = bn_moving_var_unbiased
-        self.plan = layer_plan(input_shape, inf_vector_shape, mode, number_filters_0, kernels, BatchNorm)
+        self.arch = arch
+        self.A = arch_table(arch, number_filters_0, kernels)
+        self.plan = layer_plan(input_shape, inf_vector_shape, mode, number_filters_0, kernels, BatchNorm, arch)
         self.taps = None   # optional dict collecting intermediates for per-layer parity
         # optional dict name -> tensor: forward VALUES to substitute (straight-through) at every stored
         # tensor and BatchNorm statistic. With the device path's own forward state plugged in, autograd
@@ -311,8 +328,9 @@ class UNetOracle:
         if training and dropout_mask is not None:              # Dropout(.3), inverted
             x = x * dropout_mask
         x = self._sub("vec.dense.out", self._r(x))
-        x = x.reshape(B, H5, W5, 16).permute(0, 3, 1, 2)       # Reshape((H5, W5, 16)) NHWC
-        x = conv2d_same(x, self._r(p["vec.proj.w"]), p["vec.proj.b"], 1)
+        x = x.reshape(B, H5, W5, self.A["vec_ch"]).permute(0, 3, 1, 2)       # Reshape((H5, W5, 16)) NHWC
+        if self.A["proj"]:
+            x = conv2d_same(x, self._r(p["vec.proj.w"]), p["vec.proj.b"], 1)
         return x
 
     # -- forward ----------------------------------------------------------------------
@@ -339,6 +357,8 @@ class UNetOracle:
         d5 = self._decoding_block(d4, e1, p, 5, training, new_stats)
         out = conv2d_same(d5, self._r(p["head.w"]), p["head.b"], 1)   # UpSampling2D((1,1)) = identity
         self._tap("head", out)
+        if not self.A["head_sigmoid"]:                                # DiffUNet: activation='linear'
+            return out.permute(0, 2, 3, 1)
         return torch.sigmoid(out).permute(0, 2, 3, 1)
 
     def l2_losses(self, params):

@@ -217,3 +217,24 @@ def test_generic_trainer_callbacks_match_reference_trace():
                (row["improve"], row["stop"], row["count"], row["val_min"], row["train_min"], row["saved"])
         seen.add((row["improve"], row["saved"] > 0))
     assert any(not r["improve"] and r["val_min"] == r["val"] for r in tr["trace"])     # a saved-but-not-improved epoch occurs
+
+
+def test_diffunet_plan_known_answers():
+    """DiffUNet (dl_models/diff_u_net.py:205-322): the oracle's and the package's variable inventories agree and add up to
+    the hand-computed parameter count (see tests/test_gpu_diffunet.py for the breakdown); the oracle graph runs and its
+    linear head leaves the sigmoid range."""
+    import numpy as np
+    import torch
+    from oracle import unet_oracle as O
+    from unet_rir_b200 import plan as PL
+    om = O.UNetOracle(input_shape=(144, 160, 2), kernels=2, arch="diff")
+    mine = PL.layer_plan((144, 160, 2), (2, 16), 0, 32, 2, True, arch="diff")
+    assert [(n, tuple(s), k) for n, s, k in mine] == [(n, tuple(s), k) for n, s, k in om.plan]
+    assert sum(int(np.prod(s)) for n, s, k in om.plan if k in O.TRAINABLE_KINDS) == 195_874_786
+    assert sum(1 for n, s, k in om.plan if k in O.TRAINABLE_KINDS) == 75
+    # UNet's own inventory is untouched by the arch switch (20,958,914 parameters including the BN moving statistics)
+    assert sum(int(np.prod(s)) for n, s, k in PL.layer_plan(kernels=3)) == 20_958_914
+    p = O.init_params(om.plan, seed=1)
+    g = torch.Generator().manual_seed(0)
+    y = om.forward(p, torch.rand(1, 144, 160, 2, generator=g), torch.randint(0, 1500, (1, 2, 16), generator=g, dtype=torch.int32))
+    assert y.shape == (1, 144, 160, 2) and (float(y.min()) < 0 or float(y.max()) > 1)

@@ -152,7 +152,7 @@ class Trainer:
         n = B * H * W
         b = eng._buffers(B)
         eng._forward_body(B, training=True, dropout=self.dropout)
-        L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), n, 1.0 / n, 1.0 / n, 1,
+        L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), n, 1.0 / n, 1.0 / n, int(eng.head_sigmoid),
                eng.losses_dev.data_ptr(), b["g_out"].data_ptr(), None, 0)
         eng._backward_body(B)
         if self.optimizer == 'adam':
@@ -329,7 +329,7 @@ def fit_mse(unet, x_train1, x_train2, y_train, x_val1, x_val2, y_val, batch_size
             out = eng.forward(xb, eb, training=True)
             diff = out - yb
             n = diff.numel()
-            eng.backward((2.0 / n) * diff * out * (1.0 - out))
+            eng.backward((2.0 / n) * diff * out * (1.0 - out) if eng.head_sigmoid else (2.0 / n) * diff)
             eng.adam_step()
             tl.append((diff * diff).mean())
             it += 1

@@ -51,7 +51,8 @@ class _UNetFn(torch.autograd.Function):
     def backward(ctx, gout):
         (out,) = ctx.saved_tensors
         eng = ctx.model.engine
-        eng.backward((gout * out * (1.0 - out)).contiguous())      # through the fused sigmoid head
+        # through the fused sigmoid head (the sibling DiffUNet's head is linear)
+        eng.backward((gout * out * (1.0 - out)).contiguous() if eng.head_sigmoid else gout.contiguous())
         return (None, None, None, None) + tuple(eng.grad[n] for n in eng.trainable_names())
 
 

@@ -114,7 +114,7 @@ class InputPrefetcher:
 class UNetEngine:
     def __init__(self, input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0,
                  number_filters_0=32, kernels=6, BatchNorm=True, device="cuda", seed=500,
-                 impl=L.IMPL_AUTO, bn_unbiased_moving_var=False):
+                 impl=L.IMPL_AUTO, bn_unbiased_moving_var=False, arch="unet"):
         if mode not in (0, 1, 2, 3):
             raise ValueError("mode must be 0 (convolutional_block_1), 1 (convolutional_block_2), 2 (residual_block_1) "
                              "or 3 (residual_block_2)  (u_net.py:280-287)")
@@ -127,10 +127,14 @@ class UNetEngine:
         self.device = torch.device(device)
         self.impl = impl
         self.bn_unbiased = int(bn_unbiased_moving_var)
-        self.plan = PL.layer_plan(input_shape, inf_vector_shape, mode, number_filters_0, kernels, BatchNorm)
+        # arch "unet" = dl_models/u_net.py, "diff" = dl_models/diff_u_net.py (plan.ARCHS lists what differs)
+        self.arch = arch
+        self.A = PL.arch_params(arch, number_filters_0, kernels)
+        self.head_sigmoid = bool(self.A["head_sigmoid"])
+        self.plan = PL.layer_plan(input_shape, inf_vector_shape, mode, number_filters_0, kernels, BatchNorm, arch)
         self.T = inf_vector_shape[0] * inf_vector_shape[1]
         self.H5, self.W5 = H // 16, W // 16
-        self.dense_n = self.H5 * self.W5 * PL.VEC_CH
+        self.dense_n = self.H5 * self.W5 * self.A["vec_ch"]
         self._build_params(seed)
         self._bufs = {}
         self.dropout_seed = seed
@@ -194,7 +198,7 @@ class UNetEngine:
         # w_up2 operand of the stride-2 layers (3x3 only): Conv2DTranspose forward and strided-conv dgrad as one
         # 2x2 problem on the half-resolution grid (urir_conv2d_dgrad_up2); allocated where the kernel applies
         self.wup2 = {}
-        if self.kernels == 3:
+        if self.A["down_k"] == 3 and self.A["up_k"] == 3:
             H, W, _ = self.input_shape
             for name, shape, kind in self.plan:
                 if kind == "convT_w" or (kind == "conv_w" and name.endswith(".down.w") and not name.startswith("enc1.")):
@@ -295,9 +299,12 @@ class UNetEngine:
                         b[f"{key}.{nm}"] = act(h, w, n)
                         if nm != "a2" and nm != "a3":
                             b[f"g_{key}.{nm}"] = act(h, w, n)
-        b["embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=bf, device=dev)
-        b["g_embflat"] = torch.zeros(B, self.T * PL.EMB_DIM, dtype=bf, device=dev)
-        b["v16"] = act(self.H5, self.W5, PL.VEC_CH); b["g_v16"] = act(self.H5, self.W5, PL.VEC_CH)
+        b["embflat"] = torch.zeros(B, self.T * self.A["emb_dim"], dtype=bf, device=dev)
+        b["g_embflat"] = torch.zeros(B, self.T * self.A["emb_dim"], dtype=bf, device=dev)
+        b["v16"] = act(self.H5, self.W5, self.A["vec_ch"])
+        # without the 1x1 projection (diff_u_net.py:261-270) the Dense output is added to e5 directly, so its gradient
+        # IS the bottleneck gradient
+        b["g_v16"] = act(self.H5, self.W5, self.A["vec_ch"]) if self.A["proj"] else b["g_z"]
         b["g_v16_eff"] = torch.zeros(B, self.dense_n, dtype=bf, device=dev)
         b["mask"] = torch.ones(B, self.dense_n, dtype=torch.float32, device=dev)
         self._bufs[B] = b
@@ -558,7 +565,7 @@ class UNetEngine:
 
     def _forward_body(self, B, training, dropout=True, injected_mask=False):
         b = self._buffers(B)
-        k = self.kernels
+        kd, ku, kf, A = self.A["down_k"], self.A["up_k"], self.A["fuse_k"], self.A
         if training:
             self.stats_arena.zero_()
         elif self.fold_bn_eval:
@@ -570,19 +577,19 @@ class UNetEngine:
             self.side.wait_stream(main)
         with torch.cuda.stream(self.side if fork else main):
             L.call("embedding_fwd", b["emb"].data_ptr(), self.param["vec.emb"].data_ptr(), b["embflat"].data_ptr(),
-                   B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+                   B, self.T, A["emb_dim"], A["emb_vocab"])
             mask = None
             if training:
                 if injected_mask:
                     mask = b["mask"]
                 elif dropout:
-                    L.call("dropout_mask", b["mask"].data_ptr(), b["mask"].numel(), PL.DROPOUT_RATE,
+                    L.call("dropout_mask", b["mask"].data_ptr(), b["mask"].numel(), A["dropout"],
                            self.dropout_seed, self.drop_ctr_dev.data_ptr())
                     L.call("step_increment", self.drop_ctr_dev.data_ptr())
                     mask = b["mask"]
             self._fwd_mask = mask
             L.call("dense_fwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
-                   self.param["vec.dense.b"].data_ptr(), L.ptr(mask), b["v16"].data_ptr(), B, self.T * PL.EMB_DIM,
+                   self.param["vec.dense.b"].data_ptr(), L.ptr(mask), b["v16"].data_ptr(), B, self.T * A["emb_dim"],
                    self.dense_n)
         # ---- encoder (encoding_block, u_net.py:265-289)
         x = View(b["x_in"])
@@ -590,14 +597,17 @@ class UNetEngine:
             n = self.F0 * 2 ** (i - 1)
             t, r = View(b[f"t{i}"]), View(b[f"r{i}"])
             e = View(b[f"cat{i}"], 0, n) if i < 5 else View(b["z"])
-            self._conv_fprop(f"enc{i}.down", x, t, k, 1 if i == 1 else 2)
+            self._conv_fprop(f"enc{i}.down", x, t, kd, 1 if i == 1 else 2)
             self._blk_fwd(f"enc{i}", f"enc{i}.blk", t, r, e, training)
             x = e
         # ---- Add (u_net.py:229): z = e5 + proj(v16)
         if fork:
             main.wait_stream(self.side)
         z = View(b["z"])
-        self._conv_fprop("vec.proj", View(b["v16"]), z, 1, 1, accumulate=1)
+        if A["proj"]:
+            self._conv_fprop("vec.proj", View(b["v16"]), z, 1, 1, accumulate=1)
+        else:
+            self._add(z, View(b["v16"]), z)
         # ---- decoder (decoding_block, u_net.py:291-321)
         x = z
         for j in (2, 3, 4, 5):
@@ -605,12 +615,12 @@ class UNetEngine:
             n = self.F0 * 2 ** (i - 1)
             cat = View(b[f"cat{i}"])
             up = View(b[f"cat{i}"], n, n)
-            self._conv_dgrad(f"dec{j}.up", x, up, k, 2, bias=True)     # Conv2DTranspose forward
-            self._cbr_fwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"f{i}"]), k, training)
+            self._conv_dgrad(f"dec{j}.up", x, up, ku, 2, bias=True)     # Conv2DTranspose forward
+            self._cbr_fwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"f{i}"]), kf, training)
             self._blk_fwd(f"dec{j}", f"dec{j}.blk", View(b[f"f{i}"]), View(b[f"rb{i}"]), View(b[f"d{i}"]), training)
             x = View(b[f"d{i}"])
-        # ---- head: Conv2D(2, 6x6, same) + sigmoid (u_net.py:247-249)
-        self._conv_fprop("head", x, View(b["out"]), 6, 1, act=L.ACT_SIGMOID)
+        # ---- head: Conv2D(2, 6x6, same) + sigmoid (u_net.py:247-249) / Conv2D(2, 1x1, linear) (diff_u_net.py:257)
+        self._conv_fprop("head", x, View(b["out"]), A["head_k"], 1, act=L.ACT_SIGMOID if self.head_sigmoid else L.ACT_NONE)
         self._last_B = B
         return b["out"]
 
@@ -641,7 +651,8 @@ class UNetEngine:
         (the caller orders its consumer -- the bucket's all-reduce -- after BOTH streams itself, so the next segment's
         dgrad chain keeps overlapping the weight / Dense gradients exactly as in the unsegmented step)."""
         b = self._buffers(B)
-        k = self.kernels
+        kd, ku, kf, A = self.A["down_k"], self.A["up_k"], self.A["fuse_k"], self.A
+        hk = A["head_k"]
         if segment in (None, 0):
             self.bstat_arena.zero_()
             self.sums_arena.zero_()
@@ -653,10 +664,10 @@ class UNetEngine:
             g_out = View(b["g_out"])
             d1 = View(b["d1"])
             # head
-            self._conv_wgrad("head", d1, g_out, 6, 1)
+            self._conv_wgrad("head", d1, g_out, hk, 1)
             with self._side_branch():
                 L.call("channel_sum", g_out.ptr(), L.F32, g_out.npix, 2, 2, 0, self.grad["head.b"].data_ptr())
-            self._conv_dgrad("head", g_out, View(b["g_d1"]), 6, 1)
+            self._conv_dgrad("head", g_out, View(b["g_d1"]), hk, 1)
             # decoder, top (level 1) down to level 4
             for j in (5, 4, 3, 2):
                 i = 6 - j
@@ -666,33 +677,34 @@ class UNetEngine:
                               View(b[f"g_d{i}"]), View(b[f"g_rb{i}"]), View(b[f"g_f{i}"]))
                 st = self._bstat(f"dec{j}.cat", 2 * n)
                 self._cbr_bwd(f"dec{j}.fuse", f"dec{j}.fuse_bn", cat, View(b[f"rf{i}"]), View(b[f"g_f{i}"]),
-                              View(b[f"g_rf{i}"]), k, g_x=g_cat, g_x_stats=st)
+                              View(b[f"g_rf{i}"]), kf, g_x=g_cat, g_x_stats=st)
                 # Conv2DTranspose: bias grad = channel sums of its output gradient (right half of g_cat)
                 self.grad[f"dec{j}.up.b"].copy_(st[n:2 * n])
                 g_up = View(b[f"g_cat{i}"], n, n)
                 x_in = View(b[f"d{i + 1}"]) if j > 2 else View(b["z"])
                 g_x_in = View(b[f"g_d{i + 1}"]) if j > 2 else View(b["g_z"])
-                self._conv_wgrad(f"dec{j}.up", g_up, x_in, k, 2)
-                st2 = self._bstat("z", x_in.C) if j == 2 else None
-                self._conv_fprop(f"dec{j}.up", g_up, g_x_in, k, 2, stats=st2, bias=False)   # ConvT dgrad
-                if j == 2:
+                self._conv_wgrad(f"dec{j}.up", g_up, x_in, ku, 2)
+                st2 = self._bstat("z", x_in.C) if (j == 2 and A["proj"]) else None
+                self._conv_fprop(f"dec{j}.up", g_up, g_x_in, ku, 2, stats=st2, bias=False)   # ConvT dgrad
+                if st2 is not None:
                     self.grad["vec.proj.b"].copy_(st2[:x_in.C])
             if segment == 0 and join:
                 self._join_side()
         if segment in (None, 1):
             # bottleneck: z = e5 + proj(v16)
             g_z = View(b["g_z"])
-            self._conv_wgrad("vec.proj", View(b["v16"]), g_z, 1, 1)
-            self._conv_dgrad("vec.proj", g_z, View(b["g_v16"]), 1, 1)
+            if A["proj"]:
+                self._conv_wgrad("vec.proj", View(b["v16"]), g_z, 1, 1)
+                self._conv_dgrad("vec.proj", g_z, View(b["g_v16"]), 1, 1)
             # the Dense / Embedding gradients only feed the optimiser: side stream, next to the encoder's dgrad chain
             with self._side_branch():
                 L.call("dense_bwd", b["embflat"].data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
                        b["g_v16"].data_ptr(), L.ptr(self._fwd_mask), b["g_v16_eff"].data_ptr(),
                        self.grad["vec.dense.w"].data_ptr() if dense_dw else None,
                        self.grad["vec.dense.b"].data_ptr() if dense_dw else None,
-                       b["g_embflat"].data_ptr(), B, self.T * PL.EMB_DIM, self.dense_n)
+                       b["g_embflat"].data_ptr(), B, self.T * A["emb_dim"], self.dense_n)
                 L.call("embedding_bwd", b["emb"].data_ptr(), b["g_embflat"].data_ptr(), L.BF16,
-                       self.grad["vec.emb"].data_ptr(), B, self.T, PL.EMB_DIM, PL.EMB_VOCAB)
+                       self.grad["vec.emb"].data_ptr(), B, self.T, A["emb_dim"], A["emb_vocab"])
             if segment == 1 and join:
                 self._join_side()
         if segment in (None, 2):
@@ -711,11 +723,11 @@ class UNetEngine:
                 if i > 1:
                     e_prev = View(b[f"cat{i - 1}"], 0, n // 2)
                     g_e_prev = View(b[f"g_cat{i - 1}"], 0, n // 2)
-                    self._conv_wgrad(f"enc{i}.down", e_prev, g_t, k, 2)
-                    self._conv_dgrad(f"enc{i}.down", g_t, g_e_prev, k, 2, accumulate=1)
+                    self._conv_wgrad(f"enc{i}.down", e_prev, g_t, kd, 2)
+                    self._conv_dgrad(f"enc{i}.down", g_t, g_e_prev, kd, 2, accumulate=1)
                     g_e = g_e_prev
                 else:
-                    self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, k, 1)
+                    self._conv_wgrad("enc1.down", View(b["x_in"]), g_t, kd, 1)
             self._join_side()
 
     def dense_operands(self, B):
@@ -731,7 +743,7 @@ class UNetEngine:
         rows = x_all.shape[0]
         L.call("dense_bwd", x_all.data_ptr(), self.dense_w16.data_ptr(), self.dense_w16_t.data_ptr(),
                dy_all.data_ptr(), None, None, self.grad["vec.dense.w"].data_ptr(),
-               self.grad["vec.dense.b"].data_ptr(), None, rows, self.T * PL.EMB_DIM, self.dense_n)
+               self.grad["vec.dense.b"].data_ptr(), None, rows, self.T * self.A["emb_dim"], self.dense_n)
 
     # ------------------------------------------------------------------ loss + optimiser
     def loss_and_grad(self, y_true, w_amp, w_ph, need_grad=True):
@@ -740,7 +752,8 @@ class UNetEngine:
         b = self._buffers(self._last_B)
         b["y_true"].copy_(y_true.reshape(b["y_true"].shape))
         npix = b["out"].numel() // 2
-        L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), npix, float(w_amp), float(w_ph), 1,
+        L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), npix, float(w_amp), float(w_ph),
+               int(self.head_sigmoid),
                self.losses_dev.data_ptr(), b["g_out"].data_ptr() if need_grad else None, None, 0)
         return self.losses_dev
 

@@ -130,7 +130,7 @@ class DistributedTrainer:
         e._forward_body(B, training=True, dropout=self.dropout)
         wa, wp = self._weights(B)
         L.call("ampphase_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), B * e.input_shape[0] * e.input_shape[1],
-               wa, wp, 1, e.losses_dev.data_ptr(), b["g_out"].data_ptr(), None, 0)
+               wa, wp, int(e.head_sigmoid), e.losses_dev.data_ptr(), b["g_out"].data_ptr(), None, 0)
         e._backward_body(B, segment=0, join=self._segment_join)
 
     def _seg_bottleneck(self, B):

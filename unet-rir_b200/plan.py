@@ -21,11 +21,35 @@ DROPOUT_RATE = 0.3                      # Dropout(.3)             u_net.py:260
 BN_EPS, BN_MOMENTUM = 1e-3, 0.99        # Keras BatchNormalization defaults (u_net.py:368)
 L2_COEF = 1e-3                          # kernel_regularizer=l2(0.001) (u_net.py:274,302)
 
+# The two sibling graphs built on this plan. None = "the constructor's `kernels` argument".
+#   unet: dl_models/u_net.py:201-263   -- k x k strided / transposed / fuse convolutions, Embedding(2000, 256),
+#         Dense -> Dropout(.3) -> Reshape(H5, W5, 16) -> 1x1 projection, 6x6 sigmoid head
+#   diff: dl_models/diff_u_net.py:205-276 -- 2x2 strided / transposed convolutions (:272-279, :300-307), 3x3 fuse
+#         convolution (:312), Embedding(1500, 128), Dense straight to (H5, W5, 16 F0) -> Dropout(.5) (:261-270, no
+#         projection), linear 1x1 head (:257)
+ARCHS = {
+    "unet": dict(down_k=None, up_k=None, fuse_k=None, head_k=6, head_sigmoid=True, emb_vocab=EMB_VOCAB, emb_dim=EMB_DIM,
+                 vec_ch=VEC_CH, proj=True, dropout=DROPOUT_RATE),
+    "diff": dict(down_k=2, up_k=2, fuse_k=3, head_k=1, head_sigmoid=False, emb_vocab=1500, emb_dim=128,
+                 vec_ch=None, proj=False, dropout=0.5),
+}
+
+
+def arch_params(arch, number_filters_0, kernels):
+    a = dict(ARCHS[arch])
+    for key in ("down_k", "up_k", "fuse_k"):
+        if a[key] is None:
+            a[key] = kernels
+    if a["vec_ch"] is None:
+        a["vec_ch"] = number_filters_0 * 16
+    return a
+
 
 def layer_plan(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, number_filters_0=32,
-               kernels=6, BatchNorm=True):
+               kernels=6, BatchNorm=True, arch="unet"):
     """-> list of (name, shape, kind)."""
-    F0, k = number_filters_0, kernels
+    F0 = number_filters_0
+    A = arch_params(arch, number_filters_0, kernels)
     plan = []
 
     def conv(name, kh, cin, cout):
@@ -53,22 +77,23 @@ def layer_plan(input_shape=(144, 160, 2), inf_vector_shape=(2, 16), mode=0, numb
     cin = input_shape[2]
     for i, m in enumerate([1, 2, 4, 8, 16]):
         n = F0 * m
-        conv(f"enc{i + 1}.down", k, cin, n)
+        conv(f"enc{i + 1}.down", A["down_k"], cin, n)
         block(f"enc{i + 1}.blk", n, n)
         cin = n
     H5, W5 = input_shape[0] // 16, input_shape[1] // 16
-    dim = H5 * W5 * VEC_CH
-    plan.append(("vec.emb", (EMB_VOCAB, EMB_DIM), "emb"))
-    plan.append(("vec.dense.w", (inf_vector_shape[0] * inf_vector_shape[1] * EMB_DIM, dim), "dense_w"))
+    dim = H5 * W5 * A["vec_ch"]
+    plan.append(("vec.emb", (A["emb_vocab"], A["emb_dim"]), "emb"))
+    plan.append(("vec.dense.w", (inf_vector_shape[0] * inf_vector_shape[1] * A["emb_dim"], dim), "dense_w"))
     plan.append(("vec.dense.b", (dim,), "bias"))
-    conv("vec.proj", 1, VEC_CH, F0 * 16)
+    if A["proj"]:
+        conv("vec.proj", 1, A["vec_ch"], F0 * 16)
     for j, m in zip([2, 3, 4, 5], [8, 4, 2, 1]):
         n = F0 * m
-        convT(f"dec{j}.up", k, cin, n)
-        conv(f"dec{j}.fuse", k, 2 * n, n); bn(f"dec{j}.fuse_bn", n)
+        convT(f"dec{j}.up", A["up_k"], cin, n)
+        conv(f"dec{j}.fuse", A["fuse_k"], 2 * n, n); bn(f"dec{j}.fuse_bn", n)
         block(f"dec{j}.blk", n, n)
         cin = n
-    conv("head", 6, cin, 2)
+    conv("head", A["head_k"], cin, 2)
     return plan
 
 

@@ -33,7 +33,7 @@ class Trainer(_A.Trainer):
         b = eng._buffers(B)
         eng._forward_body(B, training=True, dropout=self.dropout)
         # gradient of sum over pixels of mean over the two channels of the squared error: 0.5 * SSE
-        L.call("mse2_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), n, 0.5, 1, eng.losses_dev.data_ptr(), b["g_out"].data_ptr())
+        L.call("mse2_loss", b["y_true"].data_ptr(), b["out"].data_ptr(), n, 0.5, int(eng.head_sigmoid), eng.losses_dev.data_ptr(), b["g_out"].data_ptr())
         eng._backward_body(B)
         if self.optimizer == 'adam':
             eng.adam_step()
