@@ -238,6 +238,131 @@ thin_gemm_kernel(const __grid_constant__ ThinParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// thin_expand_mma: the same product as thin_gemm with the im2col rows never materialised.
+// These two launches (stem fprop, head dgrad) move 106 MB for 1.7 / 6.8 GFLOP: they are HBM-bound by two orders of
+// magnitude, and the tcgen05 version above spent its time building the im2col tile in shared memory, waiting for one tiny
+// UMMA per tile and reading TMEM back (41 / 61 us against a 16 us traffic floor, tensor pipe 3-6 % busy). With a
+// K index of (tap, thin channel) a warp-level m16n8k16 A fragment register IS one halo-patch pixel -- the two channels
+// of pixel + tap as a bf16 pair -- so a warp takes a 16-pixel row segment, reads its A operand straight out of the
+// bf16 halo patch (4 shared-memory words per K step, no staging of the 18 / 72-wide rows), keeps the whole weight
+// matrix as B fragments in registers (MMA columns permuted so that a lane's accumulators are 8 consecutive channels:
+// 16-byte stores, 512 contiguous bytes per warp instruction). 8 warps = the 8 x 16 tile; the halo patches of the next
+// three tiles are in flight as cp.async copies into a shared-memory ring (one tile's iteration is a few hundred cycles,
+// a DRAM round trip several times that: with a one-tile prefetch the kernel ran at the load latency); two CTAs per SM.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int TE_NBUF = 4;             // patch ring: tiles in flight per CTA (each tile's iteration is far shorter than a DRAM round trip)
+
+__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int KSZ, bool FLIP>
+__global__ void __launch_bounds__(256, 2)
+thin_expand_mma_kernel(const __grid_constant__ ThinParams p) {
+    constexpr int NT = KSZ * KSZ, PW = TH_BW + KSZ - 1, PH = TH_BH + KSZ - 1, KS = (2 * NT + 15) / 16, NP = PH * PW;
+    static_assert(NP <= 512, "two patch pixels per thread");
+    __shared__ float2 patch[TE_NBUF][NP];                   // (channel 0, channel 1) of a halo-patch pixel, fp32 as in HBM
+    __shared__ uint32_t patch16[2][NP];                     // the current tile's patch as bf16 pairs = MMA A-fragment registers
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int n0 = blockIdx.y * 32;
+
+    // B fragments of the whole [2 NT x 32] weight matrix: K step ks, 8-channel group nt, halves h (taps 8 ks + t + 4 h)
+    uint32_t bfrag[KS][4][2];
+    int aoff[KS][2];                                        // patch offset of this thread's two taps per K step, -1 = padding
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int tap = 8 * ks + t + 4 * h;
+            const int r = tap / KSZ, sx = tap - r * KSZ;
+            aoff[ks][h] = tap < NT ? (FLIP ? (KSZ - 1 - r) * PW + (KSZ - 1 - sx) : r * PW + sx) : -1;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint32_t v = 0u;
+                if (tap < NT) {
+                    const int n = n0 + 8 * (g >> 1) + 2 * nt + (g & 1);   // MMA column (nt, g) = this channel: see the store
+                    const uint32_t lo = __bfloat16_as_ushort(p.w_ck[thin_widx(p, tap, 0, n)]);
+                    const uint32_t hi = __bfloat16_as_ushort(p.w_ck[thin_widx(p, tap, 1, n)]);
+                    v = lo | (hi << 16);
+                }
+                bfrag[ks][nt][h] = v;
+            }
+        }
+    float bias2[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        bias2[nt][0] = p.bias ? __ldg(p.bias + n0 + 8 * t + 2 * nt) : 0.f;
+        bias2[nt][1] = p.bias ? __ldg(p.bias + n0 + 8 * t + 2 * nt + 1) : 0.f;
+    }
+    // this thread's two patch pixels (tile independent)
+    int py[2], px[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = threadIdx.x + 256 * q;
+        py[q] = i < NP ? i / PW : -1; px[q] = i - (i / PW) * PW;
+    }
+    // asynchronous copy of the halo patch of `tile` into ring slot `buf` (zero fill outside the image = SAME padding);
+    // always one commit group per call so that the wait counts stay uniform
+    auto fetch_patch = [&](int tile, int buf) {
+        if (tile < p.total_tiles) {
+            int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (py[q] >= 0) {
+                    const int gh = h0 + p.oh0 + py[q], gw = w0 + p.ow0 + px[q];
+                    const bool in = gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+                    const float* src = p.thin + ((size_t)(n * p.H + (in ? gh : 0)) * p.W + (in ? gw : 0)) * p.thin_ld + p.thin_coff;
+                    cp_async8_zfill(&patch[buf][threadIdx.x + 256 * q], src, in);
+                }
+        }
+        cp_async_commit();
+    };
+
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < TE_NBUF - 1; ++i) fetch_patch(tile + i * (int)gridDim.x, i);
+    for (int it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        cp_async_wait<TE_NBUF - 2>();                                // this thread's part of tile `it` has landed:
+#pragma unroll
+        for (int q = 0; q < 2; ++q)                                  // ... convert it once (the taps re-read every pixel up to 36 times)
+            if (py[q] >= 0) {
+                const float2 v = patch[it % TE_NBUF][threadIdx.x + 256 * q];
+                patch16[it & 1][threadIdx.x + 256 * q] = pack_bf16x2(v.x, v.y);
+            }
+        __syncthreads();                                             // everybody's part is there; slot (it - 1) % NBUF is free again
+        fetch_patch(tile + (TE_NBUF - 1) * (int)gridDim.x, (it + TE_NBUF - 1) % TE_NBUF);
+        const uint32_t* pa = patch16[it & 1] + warp * PW + g;        // pixel (row = warp, column = g / g + 8) of the tile
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][2] = bias2[nt][0]; acc[nt][1] = acc[nt][3] = bias2[nt][1]; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+            if (aoff[ks][0] >= 0) { a0 = pa[aoff[ks][0]]; a1 = pa[aoff[ks][0] + 8]; }
+            if (aoff[ks][1] >= 0) { a2 = pa[aoff[ks][1]]; a3 = pa[aoff[ks][1] + 8]; }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_16816(acc[nt], a0, a1, a2, a3, bfrag[ks][nt][0], bfrag[ks][nt][1]);
+        }
+        int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+        // accumulator columns (nt, 2t / 2t+1) were given the channels 8t + 2nt / + 1: a lane holds 8 consecutive channels of
+        // pixel g and of pixel g + 8 -> two 16-byte stores, a warp instruction covers 8 whole pixels (512 contiguous bytes)
+        __nv_bfloat16* o = p.out + ((size_t)(n * p.H + h0 + warp) * p.W + w0 + g) * p.out_ld + p.out_coff + n0 + 8 * t;
+        *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(acc[0][0], acc[0][1]), pack_bf16x2(acc[1][0], acc[1][1]),
+                                                  pack_bf16x2(acc[2][0], acc[2][1]), pack_bf16x2(acc[3][0], acc[3][1]));
+        *reinterpret_cast<uint4*>(o + (size_t)8 * p.out_ld) = make_uint4(pack_bf16x2(acc[0][2], acc[0][3]), pack_bf16x2(acc[1][2], acc[1][3]),
+                                                                          pack_bf16x2(acc[2][2], acc[2][3]), pack_bf16x2(acc[3][2], acc[3][3]));
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // thin_wgrad: dW[(tap, ct), n0 .. n0+32) += sum over this CTA's tiles of im2col(thin)^T * wide
 // A = the im2col tile read MN-major (M = J padded to 128 over 2 atoms, K = 128 pixels in 8 steps of 16);
 // B = the wide bf16 tile {32 ch x 16 x 8 pixels} brought by TMA as 128 rows of 64 B (MN-major, 64B swizzle).
@@ -400,6 +525,17 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
     else { p.thin_ld = d->y_ld; p.thin_coff = d->y_coff; p.out_ld = d->x_ld; p.out_coff = d->x_coff; }
     // square 3x3 / 6x6 kernels (the stem and the head of the model) get compile-time tap offsets; anything else the generic path
     const int ksz = (d->R == d->S && (d->R == 3 || d->R == 6)) ? d->R : 0;
+    { static int umma = -1; if (umma < 0) { const char* e = getenv("URIR_THIN_UMMA"); umma = (e && e[0] == '1') ? 1 : 0; }
+      if (ksz && !umma) {                 // register-im2col warp-MMA kernel (see thin_expand_mma_kernel); URIR_THIN_UMMA=1: the tcgen05 one
+          void (*k2)(const ThinParams) = ksz == 3 ? (thin_is_x ? thin_expand_mma_kernel<3, false> : thin_expand_mma_kernel<3, true>)
+                                                  : (thin_is_x ? thin_expand_mma_kernel<6, false> : thin_expand_mma_kernel<6, true>);
+          int per_sm = ksz == 3 ? 3 : 2;      // 78 / 128 registers
+          { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_MMA_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0) per_sm = ov; }
+          const int gx = p.total_tiles < sm_count() * per_sm ? p.total_tiles : sm_count() * per_sm;
+          k2<<<dim3(gx, p.CW_total / 32), 256, 0, st>>>(p);
+          URIR_LAUNCH_OK(0);
+          return URIR_OK;
+      } }
     void (*kern)(const ThinParams) = thin_gemm_kernel<0, false>;
     if (ksz == 3) kern = thin_is_x ? thin_gemm_kernel<3, false> : thin_gemm_kernel<3, true>;
     if (ksz == 6) kern = thin_is_x ? thin_gemm_kernel<6, false> : thin_gemm_kernel<6, true>;
