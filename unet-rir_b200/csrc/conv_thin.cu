@@ -39,6 +39,7 @@ struct ThinParams {
     int CW_total;               // channels of the wide side in the weight tensor
     int thin_is_x;              // 1: thin tensor is the conv input (stem); 0: it is the conv output side (head)
     const float* thin; int thin_ld, thin_coff;
+    const __nv_bfloat16* wide; int wide_ld, wide_coff;   // thin_wgrad_mma: the 32-channel-group side, read with plain copies
     const __nv_bfloat16* w_ck; const float* bias;
     __nv_bfloat16* out; int out_ld, out_coff;
     float* dw;
@@ -479,6 +480,154 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap wide_map, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// thin_wgrad_mma: the same reduction as thin_wgrad on warp-level MMAs, without building im2col rows.
+// D[channel, (tap, ct)] += wide^T[channel, pixel] * im2col[pixel, (tap, ct)], GEMM-K = the 16 pixels of one tile row per
+// warp. A (wide^T) comes out of the NHWC tile with ldmatrix.trans; a B fragment register is two horizontally adjacent
+// pixels of one thin channel at a tap offset, i.e. one 32-bit word of a channel-planar bf16 copy of the halo patch --
+// kept in two alignments (pairs starting at even / odd columns) so that every tap offset is an aligned word. Both
+// tensors arrive through 4-deep cp.async rings (wide tile 8 KB, patch <= 2.2 KB per slot). 8 warps = the 8 tile rows,
+// accumulators (2 x NTL m16n8 tiles) in registers for the CTA's whole tile range, folded across the warps in shared
+// memory in a fixed order and added to dW once per CTA (gated in deterministic mode like thin_wgrad).
+// ---------------------------------------------------------------------------------------------
+constexpr int TWM_NBUF = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_row)) : "memory");
+}
+
+template <int KSZ, bool FLIP>
+__global__ void __launch_bounds__(256, 2)
+thin_wgrad_mma_kernel(const __grid_constant__ ThinParams p) {
+    constexpr int NT = KSZ * KSZ, PW = TH_BW + KSZ - 1, PH = TH_BH + KSZ - 1, NP = PH * PW;
+    constexpr int J = 2 * NT, NTL = (J + 7) / 8, JP = NTL * 8;       // (tap, thin channel) columns in n-tiles of 8
+    constexpr int PITCH = (PW + 2) / 2;                              // 32-bit words (pixel pairs) per plane row
+    constexpr int PLANE = PH * PITCH;
+    static_assert(NP <= 512, "two patch pixels per thread");
+    static_assert(32 * JP * 4 <= TWM_NBUF * 8192, "the reduction buffer aliases the wide ring");
+    __shared__ __align__(128) uint8_t wide_s[TWM_NBUF][128 * 64];    // [tile pixel][32 ch], 16-byte chunks XOR-swizzled with (pixel / 2) % 4
+    __shared__ float2 patch[TWM_NBUF][NP];
+    __shared__ uint32_t planes[2][4 * PLANE];                        // [buffer][(thin channel, alignment)][row][pair]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int n0 = blockIdx.y * 32;
+
+    // B fragment word offsets: n-tile nt, column g -> (tap, ct) = ((8 nt + g) / 2, g & 1); half h = pixels 2t + 8h, + 1
+    int boff[NTL][2];
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+        const int j = nt * 8 + g, tap = j >> 1, ct = j & 1;
+        const int r = tap / KSZ, sx = tap - r * KSZ;
+        const int dr = FLIP ? KSZ - 1 - r : r, ds = FLIP ? KSZ - 1 - sx : sx;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int x = 2 * t + 8 * h + ds, al = x & 1;
+            boff[nt][h] = tap < NT ? (ct * 2 + al) * PLANE + (warp + dr) * PITCH + ((x - al) >> 1) : -1;
+        }
+    }
+    // A fragments: ldmatrix.x4.trans row addresses (matrix = lane / 8: pixels 0-7 / 8-15 of the warp's row x channel octet)
+    int aoff[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int mat = lane >> 3, P = warp * 16 + (mat >> 1) * 8 + (lane & 7), chunk = 2 * mt + (mat & 1);
+        aoff[mt] = P * 64 + ((chunk ^ ((P >> 1) & 3)) << 4);
+    }
+    int py[2], px[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = threadIdx.x + 256 * q;
+        py[q] = i < NP ? i / PW : -1; px[q] = i - (i / PW) * PW;
+    }
+    auto fetch = [&](int tile, int buf) {
+        if (tile < p.total_tiles) {
+            int n, h0, w0; thin_tile_coords(p, tile, n, h0, w0);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = threadIdx.x + 256 * q, P = idx >> 2, c = idx & 3;
+                const __nv_bfloat16* src = p.wide + ((size_t)(n * p.H + h0 + (P >> 4)) * p.W + w0 + (P & 15)) * p.wide_ld + p.wide_coff + n0 + c * 8;
+                cp_async16(&wide_s[buf][P * 64 + ((c ^ ((P >> 1) & 3)) << 4)], src);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (py[q] >= 0) {
+                    const int gh = h0 + p.oh0 + py[q], gw = w0 + p.ow0 + px[q];
+                    const bool in = gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+                    const float* src = p.thin + ((size_t)(n * p.H + (in ? gh : 0)) * p.W + (in ? gw : 0)) * p.thin_ld + p.thin_coff;
+                    cp_async8_zfill(&patch[buf][threadIdx.x + 256 * q], src, in);
+                }
+        }
+        cp_async_commit();
+    };
+
+    float acc[2][NTL][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < TWM_NBUF - 1; ++i) fetch(tile + i * (int)gridDim.x, i);
+    for (int it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        cp_async_wait<TWM_NBUF - 2>();
+        {   // this thread's patch pixels -> the four bf16 planes of buffer it & 1
+            unsigned short* pl = reinterpret_cast<unsigned short*>(planes[it & 1]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (py[q] >= 0) {
+                    const float2 v = patch[it % TWM_NBUF][threadIdx.x + 256 * q];
+                    const unsigned short b0 = __bfloat16_as_ushort(f2bf(v.x)), b1 = __bfloat16_as_ushort(f2bf(v.y));
+                    const int e = py[q] * 2 * PITCH + px[q];
+                    pl[e] = b0; pl[4 * PLANE + e] = b1;                                       // pairs from even columns
+                    if (px[q] > 0) { pl[2 * PLANE + e - 1] = b0; pl[6 * PLANE + e - 1] = b1; }   // pairs from odd columns
+                }
+        }
+        __syncthreads();
+        fetch(tile + (TWM_NBUF - 1) * (int)gridDim.x, (it + TWM_NBUF - 1) % TWM_NBUF);
+        uint32_t a[2][4];
+        ldmatrix_x4_trans(a[0], wide_s[it % TWM_NBUF] + aoff[0]);
+        ldmatrix_x4_trans(a[1], wide_s[it % TWM_NBUF] + aoff[1]);
+        const uint32_t* pw = planes[it & 1];
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) {
+            uint32_t b0 = 0u, b1 = 0u;
+            if (boff[nt][0] >= 0) { b0 = pw[boff[nt][0]]; b1 = pw[boff[nt][1]]; }
+            mma_16816(acc[0][nt], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+            mma_16816(acc[1][nt], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // fold the 8 warps' accumulators in warp order (no floating-point atomics: the sum does not depend on timing)
+    float* red = reinterpret_cast<float*>(&wide_s[0][0]);           // [32 channels][JP]
+#pragma unroll 1
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float* d = red + (16 * mt + g + 8 * (e >> 1)) * JP + 8 * nt + 2 * t + (e & 1);
+                        *d = w == 0 ? acc[mt][nt][e] : *d + acc[mt][nt][e];
+                    }
+        }
+        __syncthreads();
+    }
+    gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
+    for (int idx = threadIdx.x; idx < 32 * J; idx += 256) {
+        const int j = idx >> 5, ch = idx & 31;
+        atomicAdd(p.dw + thin_widx(p, j >> 1, j & 1, n0 + ch), red[ch * JP + j]);
+    }
+    gate_leave(p.gate, cta_linear(), cta_count(), threadIdx.x == 0, 0, blockDim.x);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static bool thin_geometry_ok(const urir_conv_desc* d) {
@@ -567,6 +716,20 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
     if (thin_is_x) { p.thin = (const float*)x; p.thin_ld = d->x_ld; p.thin_coff = d->x_coff; wide = dy; wide_ld = d->y_ld; wide_coff = d->y_coff; wide_c = d->K; }
     else { p.thin = (const float*)dy; p.thin_ld = d->y_ld; p.thin_coff = d->y_coff; wide = x; wide_ld = d->x_ld; wide_coff = d->x_coff; wide_c = d->C; }
     p.dw = dw; p.gate = next_gate();
+    p.wide = (const __nv_bfloat16*)wide; p.wide_ld = wide_ld; p.wide_coff = wide_coff;
+    const int ksz_mma = (d->R == d->S && (d->R == 3 || d->R == 6)) ? d->R : 0;
+    { static int umma = -1; if (umma < 0) { const char* e = getenv("URIR_THIN_UMMA"); umma = (e && e[0] == '1') ? 1 : 0; }
+      if (ksz_mma && !umma) {               // warp-MMA kernel (thin_wgrad_mma_kernel); URIR_THIN_UMMA=1: the tcgen05 one below
+          void (*k2)(const ThinParams) = ksz_mma == 3 ? (thin_is_x ? thin_wgrad_mma_kernel<3, false> : thin_wgrad_mma_kernel<3, true>)
+                                                      : (thin_is_x ? thin_wgrad_mma_kernel<6, false> : thin_wgrad_mma_kernel<6, true>);
+          if (!d->accumulate) URIR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.ntaps * d->C * d->K, st));
+          int per_sm = 2;
+          { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_WGRAD_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0) per_sm = ov; }
+          const int gx = p.total_tiles < sm_count() * per_sm ? p.total_tiles : sm_count() * per_sm;
+          k2<<<dim3(gx, p.CW_total / 32), 256, 0, st>>>(p);
+          URIR_LAUNCH_OK(0);
+          return URIR_OK;
+      } }
     CUtensorMap map;
     {
         const uint64_t dims[4] = {(uint64_t)wide_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
