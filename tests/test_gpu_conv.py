@@ -541,3 +541,60 @@ def test_deep_kernel_concat_slices_and_relu():
     ref = torch.relu(_oracle_fprop(x, w, bias, 1))
     assert U.rel_l2(ybuf[..., :K].float(), ref) < BF16_TOL
     assert float((ybuf[..., K:].float() - 3.0).abs().max()) == 0.0
+
+
+DEEP_S2_CASES = [
+    # (N, H, W, C, K): the deep strided layers of the canonical net (E4a 36x40 128 -> 256, E5a 18x20 256 -> 512; the
+    # decoder's Conv2DTranspose layers are the same shapes run as dgrad), reduced batch and the benchmark's batch
+    (3, 18, 20, 256, 512),
+    (64, 18, 20, 256, 512),
+    (5, 36, 40, 128, 256),
+    (64, 36, 40, 128, 256),
+    (2, 36, 76, 128, 128),          # long-RIR width (config 5), one channel tile
+]
+
+
+@pytest.mark.parametrize("case", DEEP_S2_CASES, ids=[str(c) for c in DEEP_S2_CASES])
+def test_deep_kernel_stride2(case):
+    """conv_deep.cu on the half-resolution grid: stride-2 fprop from the four parity planes of x (strided tensor maps,
+    4 / 2 / 2 / 1 taps each) and stride-2 dgrad as four output-parity classes over the same dy tiles -- with the
+    Conv2DTranspose bias, into a concat half, and accumulating into an existing gradient (encoder skip). Forced through
+    URIR_IMPL_DEEP: AUTO keeps conv_igemm for these layers (measured not slower, see deep_supported)."""
+    N, H, W, Cc, K = case
+    x, w, bias, dy, P, Q = _inputs(N, H, W, Cc, K, 3, 2, seed=N + W)
+    w_ck, w_kc = U.prep_weights(w.cuda())
+    fam0 = L.family_calls()["deep"]
+    d = U.conv_desc(N, H, W, Cc, K, 3, 2, x_ld=2 * Cc, x_coff=Cc, impl=L.IMPL_DEEP)
+    xw = torch.randn(N, H, W, 2 * Cc).to(torch.bfloat16).cuda()
+    xw[..., Cc:] = x.cuda().to(torch.bfloat16)
+    y = torch.full((N, P, Q, K), 7.0, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2 * K, device="cuda")
+    U.run_fprop(d, xw, w_ck, w_kc, bias.cuda(), y, stats)
+    ref = _oracle_fprop(x, w, bias, 2)
+    assert U.rel_l2(y.float(), ref) < BF16_TOL, U.rel_l2(y.float(), ref)
+    assert U.max_abs(stats[:K], ref.sum(dim=(0, 1, 2))) < 2e-3 * float(ref.abs().sum(dim=(0, 1, 2)).max())
+    assert U.rel_l2(stats[K:], (ref ** 2).sum(dim=(0, 1, 2))) < F32_TOL * 10
+    assert L.family_calls()["deep"] - fam0 == 1
+    # dgrad = Conv2DTranspose forward: bias added, written into the right half of a concat buffer
+    xr = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(_oracle_fprop(xr, w, None, 2), [xr], dy)
+    cb = torch.randn(Cc)
+    dyg = dy.cuda().to(torch.bfloat16)
+    cat = torch.full((N, H, W, 2 * Cc), 3.0, dtype=torch.bfloat16, device="cuda")
+    d = U.conv_desc(N, H, W, Cc, K, 3, 2, x_ld=2 * Cc, x_coff=Cc, impl=L.IMPL_DEEP)
+    U.run_dgrad(d, dyg, w_ck, w_kc, cb.cuda(), cat)
+    assert L.family_calls()["deep"] - fam0 == 2
+    assert U.rel_l2(cat[..., Cc:].float(), gx + cb) < BF16_TOL, U.rel_l2(cat[..., Cc:].float(), gx + cb)
+    assert float((cat[..., :Cc].float() - 3.0).abs().max()) == 0.0
+    # dgrad accumulating into the skip gradient (left half)
+    g = torch.Generator().manual_seed(3)
+    old = U.bf16_round(torch.randn(N, H, W, Cc, generator=g))
+    cat[..., :Cc] = old.cuda().to(torch.bfloat16)
+    d = U.conv_desc(N, H, W, Cc, K, 3, 2, x_ld=2 * Cc, x_coff=0, impl=L.IMPL_DEEP, accumulate=1)
+    U.run_dgrad(d, dyg, w_ck, w_kc, None, cat)
+    assert L.family_calls()["deep"] - fam0 == 3
+    assert U.rel_l2(cat[..., :Cc].float(), gx + old) < BF16_TOL, U.rel_l2(cat[..., :Cc].float(), gx + old)
+    # same bf16 operands through the one-tile-per-CTA kernel
+    dx2 = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    U.run_dgrad(U.conv_desc(N, H, W, Cc, K, 3, 2, impl=L.IMPL_TC), dyg, w_ck, w_kc, cb.cuda(), dx2)
+    assert U.rel_l2(cat[..., Cc:].float(), dx2.float()) < 2e-3

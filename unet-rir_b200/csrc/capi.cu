@@ -199,9 +199,10 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
     cudaStream_t st = (cudaStream_t)stream;
     if (d->impl != URIR_IMPL_SIMT && !env_force_simt() && w_ck && !stats && !bias && thin_supported(d, 1))
         return fam(URIR_FAM_THIN_GEMM, thin_gemm(d, dy, w_ck, nullptr, dx, false, st));                 // the 2-channel head
-    if (d->impl == URIR_IMPL_DEEP && !(w_ck && deep_supported(d, 1, true)))
+    const bool deep_dg_ok = !(stats && d->stride == 2);            // no statistics epilogue on the stride-2 classes
+    if (d->impl == URIR_IMPL_DEEP && !(w_ck && deep_dg_ok && deep_supported(d, 1, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the deep-layer tcgen05 path");
-    if (w_ck && (d->impl == URIR_IMPL_DEEP || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && deep_supported(d, 1, !halo_supported(d, 1, false)))))
+    if (w_ck && (d->impl == URIR_IMPL_DEEP || (d->impl == URIR_IMPL_AUTO && !env_force_simt() && deep_dg_ok && deep_supported(d, 1, !halo_supported(d, 1, false)))))
         return fam(URIR_FAM_DEEP, conv_deep(d, 1, dy, w_ck, bias, dx, stats, st));
     if (d->impl == URIR_IMPL_HALO && !(w_ck && halo_supported(d, 1, true)))
         return fail(URIR_ERR_UNSUP, "conv2d_dgrad: shape not supported by the halo-tile tcgen05 path");
