@@ -398,6 +398,15 @@ def run_gpu(args, rank, world, local):
     value = B * world / (ms_step * 1e-3)
 
     # ---- end to end: pinned host inputs -> Trainer.step -> loss read back, every step
+    # (three untimed steps through the same prefetch / step / read-back sequence first: the copy stream, its events and the
+    # pinned staging path are otherwise touched for the first time inside the timed region -- one fresh-box run measured
+    # 5.6 ms / step here against 3.8 - 3.9 on every other box)
+    prefetch(*host[0])
+    for i in range(3):
+        last = step_host(*host[i % n_host])
+        prefetch(*host[(i + 1) % n_host])
+        _ = float(last)
+    step_host(*host[3 % n_host])               # consumes the last prefetch: the timed loop starts from a clean state
     barrier()
     ev0.record()
     last = None
