@@ -25,9 +25,14 @@ calls = []
 _orig_call = L.call
 def _counting_call(name, *args):
     n0 = L.launch_count(0)
+    f0 = L.family_calls() if name.startswith("conv2d") else None
     _orig_call(name, *args)
     info = L._conv_info(name, args) if name.startswith("conv2d") else {}
-    calls.append({"name": name, "tc": info.get("tc"), "kernels": L.launch_count(0) - n0})
+    fam = None
+    if f0 is not None:
+        f1 = L.family_calls()
+        fam = next((k for k in f1 if f1[k] != f0[k]), None)
+    calls.append({"name": name, "tc": info.get("tc"), "family": fam, "kernels": L.launch_count(0) - n0})
 L.call = _counting_call
 import unet_rir_b200.engine as _E, unet_rir_b200.amp_phase_trainer as _T
 torch.cuda.profiler.start()

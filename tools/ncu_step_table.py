@@ -63,13 +63,15 @@ if len(sys.argv) > 3:
         i = 0
         for c in calls:
             ks = ours[i:i + c["kernels"]]; i += c["kernels"]
-            key = c["name"] + ((".tcgen05" if c.get("tc") else ".simt") if c["name"].startswith("conv2d") else "")
+            # bench.py's family key: the kernel family that served a convolution call, the call name otherwise
+            key = ("conv." + c["family"]) if c.get("family") else c["name"] + ((".tcgen05" if c.get("tc") else ".simt") if c["name"].startswith("conv2d") else "")
             f = out["families"].setdefault(key, {"calls": 0, "kernels": 0, "us": 0.0, "dram_bytes": 0.0})
             f["calls"] += 1; f["kernels"] += len(ks)
             f["us"] += sum(k["gpu__time_duration.sum"] for k in ks)
             f["dram_bytes"] += sum(k.get("dram__bytes_read.sum", 0) + k.get("dram__bytes_write.sum", 0) for k in ks)
         for f in out["families"].values():
             f["dram_bytes_per_call"] = f["dram_bytes"] / max(f["calls"], 1)
+            f["dram_bytes_per_launch"] = f["dram_bytes"] / max(f["kernels"], 1)
     else:
         out["error"] = f"call list expects {need} liburir kernels, ncu saw {len(ours)}"
     json.dump(out, open(sys.argv[3], "w"), indent=1)
