@@ -335,6 +335,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 for (int c = 0; c < PH_COLS / 32; ++c) tmem_ld32(lane_addr + ph * PH_COLS + c * 32, r + c * 32);
                 tmem_ld_wait();
                 if (tre && ph == 0) p.trace[it * 8 + 6] = clock64();
+                if (ph == BLOCK_N / PH_COLS - 1 && p.debug != 8) {
+                    // the tile's last columns are in registers: hand the accumulator stage back to the MMA issuer NOW,
+                    // not after the arithmetic and the global stores below (they were ~half of the time the stage was held)
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar + acc);
+                }
 #pragma unroll
                 for (int bb = 0; bb < PH_COLS / 16; ++bb) {
                     const int b = ph * (PH_COLS / 16) + bb;
@@ -391,9 +398,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 }
             }
             if (tre) p.trace[it * 8 + 7] = clock64();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar + acc);
+            if (p.debug == 2 || p.debug == 8) {        // (no TMEM loads issued in debug 2; debug 8 = round 1's late release)
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + acc);
+            }
             if (tre) p.trace[it * 8 + 5] = clock64();
         }
         if (want_stats) {
