@@ -803,7 +803,12 @@ class UNetEngine:
         self.refresh_operands()
 
     def set_lr(self, lr):
-        self.lr_dev.fill_(float(lr))
+        # the captured step reads the rate from device memory; rewritten only when it changes (Trainer.step calls this
+        # every step: one tiny launch less on the host path between two graph replays)
+        lr = float(lr)
+        if lr != getattr(self, "_lr_host", None):
+            self.lr_dev.fill_(lr)
+            self._lr_host = lr
 
     # ------------------------------------------------------------------ debugging / parity
     def forward_state(self):
