@@ -116,6 +116,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Drops what was sampled so far: called right before the timed region (the sampler itself is started earlier so
+        that NVML initialisation and the thread's start-up stay outside it)."""
+        self.sm.clear()
+        self.reasons.clear()
+
     def stop(self):
         self._stop.set()
         if self.proc is not None:
@@ -377,13 +383,14 @@ def run_gpu(args, rank, world, local):
         resident_step = graph.replay
     else:
         resident_step = lambda: dt._run(B)
-    for _ in range(2):
-        resident_step()
     clocks = ClockSampler(local)
-    n0 = L.launch_count(0)
-    barrier()
     if rank == 0:
         clocks.start()
+    for _ in range(5):                 # untimed replays of exactly what is timed next (at N = 2 one 20-step window once
+        resident_step()                # absorbed a ~35 ms one-off right after capture: 5.6 instead of 3.8 - 3.9 ms / step)
+    n0 = L.launch_count(0)
+    barrier()
+    clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(K):
