@@ -145,7 +145,7 @@ class UNetEngine:
         self.drop_ctr_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.losses_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
-        self.reg_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.reg_dev = torch.zeros(2, dtype=torch.float32, device=self.device)    # [whole / decoder part, encoder part]
         self.side = torch.cuda.Stream(device=self.device)
         self.prefetcher = InputPrefetcher(self)
         self.eval_cuda_graph = os.environ.get("URIR_NO_EVAL_GRAPH", "0") != "1"
@@ -757,20 +757,39 @@ class UNetEngine:
                self.losses_dev.data_ptr(), b["g_out"].data_ptr() if need_grad else None, None, 0)
         return self.losses_dev
 
-    def l2_loss_and_grad(self, scale):
+    def l2_loss_and_grad(self, scale, part=None):
         """DP loss regulariser (main_training.py:232-233): reg = scale * 0.001 * sum ||W||^2 over the
-        strided convs and ConvTs; its gradient 2*scale*0.001*W is added to the flat gradient. One launch."""
-        if getattr(self, "_l2_table", None) is None:
-            rows = [[self.param[n].data_ptr(), self.grad[n].data_ptr(), self.param[n].numel()]
-                    for n in self.offsets if PL.l2_regularised(n)]
-            self._l2_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
-        L.call("l2_reg_batched", self._l2_table.data_ptr(), self._l2_table.shape[0], float(scale * PL.L2_COEF),
-               self.reg_dev.data_ptr())
+        strided convs and ConvTs; its gradient 2*scale*0.001*W is added to the flat gradient. One launch.
+        part = "dec" / "enc": only the Conv2DTranspose kernels / only the encoder's strided kernels (the bucket-wise
+        optimiser of the data-parallel step); their sums land in reg_dev[0] / reg_dev[1], the whole sum in reg_dev[0]."""
+        if getattr(self, "_l2_tables", None) is None:
+            names = [n for n in self.offsets if PL.l2_regularised(n)]
+            def table(sel):
+                rows = [[self.param[n].data_ptr(), self.grad[n].data_ptr(), self.param[n].numel()] for n in sel]
+                return torch.tensor(rows, dtype=torch.int64, device=self.device)
+            self._l2_tables = {None: table(names), "dec": table([n for n in names if n.startswith("dec")]),
+                               "enc": table([n for n in names if not n.startswith("dec")])}
+        t = self._l2_tables[part]
+        slot = 1 if part == "enc" else 0
+        if part is None:
+            self.reg_dev[1:].zero_()
+        L.call("l2_reg_batched", t.data_ptr(), t.shape[0], float(scale * PL.L2_COEF), self.reg_dev[slot:].data_ptr())
         return self.reg_dev
 
     def adam_step(self, beta1=0.9, beta2=0.999, eps=1e-7):
         L.call("adam", self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.n_flat,
                self.lr_dev.data_ptr(), self.step_dev.data_ptr(), beta1, beta2, eps)
+        L.call("step_increment", self.step_dev.data_ptr())
+        self.refresh_operands()
+
+    def adam_range(self, lo, hi, beta1=0.9, beta2=0.999, eps=1e-7):
+        """Adam on flat elements [lo, hi) only (lo a multiple of 4: 16-byte accesses); the step counter is NOT advanced --
+        adam_finish() does that once every range of the step has been updated."""
+        if hi > lo:
+            L.call("adam", self.P.data_ptr() + 4 * lo, self.G.data_ptr() + 4 * lo, self.M.data_ptr() + 4 * lo,
+                   self.V.data_ptr() + 4 * lo, hi - lo, self.lr_dev.data_ptr(), self.step_dev.data_ptr(), beta1, beta2, eps)
+
+    def adam_finish(self):
         L.call("step_increment", self.step_dev.data_ptr())
         self.refresh_operands()
 
