@@ -271,6 +271,7 @@ thin_expand_mma_kernel(const __grid_constant__ ThinParams p) {
     static_assert(NP <= 512, "two patch pixels per thread");
     __shared__ float2 patch[TE_NBUF][NP];                   // (channel 0, channel 1) of a halo-patch pixel, fp32 as in HBM
     __shared__ uint32_t patch16[2][NP];                     // the current tile's patch as bf16 pairs = MMA A-fragment registers
+    pdl_sync();      // lets the successor's prologue start; the weights read next may come from the immediately preceding launch (operand refresh, BN fold)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int n0 = blockIdx.y * 32;
 
@@ -511,6 +512,7 @@ thin_wgrad_mma_kernel(const __grid_constant__ ThinParams p) {
     __shared__ __align__(128) uint8_t wide_s[TWM_NBUF][128 * 64];    // [tile pixel][32 ch], 16-byte chunks XOR-swizzled with (pixel / 2) % 4
     __shared__ float2 patch[TWM_NBUF][NP];
     __shared__ uint32_t planes[2][4 * PLANE];                        // [buffer][(thin channel, alignment)][row][pair]
+    pdl_sync();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int n0 = blockIdx.y * 32;
 
@@ -681,7 +683,7 @@ int thin_gemm(const urir_conv_desc* d, const void* thin, const void* w_ck, const
           int per_sm = ksz == 3 ? 3 : 2;      // 78 / 128 registers
           { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_MMA_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0) per_sm = ov; }
           const int gx = p.total_tiles < sm_count() * per_sm ? p.total_tiles : sm_count() * per_sm;
-          k2<<<dim3(gx, p.CW_total / 32), 256, 0, st>>>(p);
+          URIR_CUDA_OK(launch_pdl(k2, dim3(gx, p.CW_total / 32), dim3(256), 0, st, p));
           URIR_LAUNCH_OK(0);
           return URIR_OK;
       } }
@@ -726,7 +728,7 @@ int thin_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw
           int per_sm = 2;
           { static int ov = -1; if (ov < 0) { const char* e = getenv("URIR_THIN_WGRAD_PER_SM"); ov = e ? atoi(e) : 0; } if (ov > 0) per_sm = ov; }
           const int gx = p.total_tiles < sm_count() * per_sm ? p.total_tiles : sm_count() * per_sm;
-          k2<<<dim3(gx, p.CW_total / 32), 256, 0, st>>>(p);
+          URIR_CUDA_OK(launch_pdl(k2, dim3(gx, p.CW_total / 32), dim3(256), 0, st, p));
           URIR_LAUNCH_OK(0);
           return URIR_OK;
       } }
