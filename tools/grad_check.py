@@ -1,4 +1,5 @@
-"""Per-tensor gradient comparison engine vs oracle (debug aid)."""
+"""Per-tensor PARAMETER gradients, engine vs oracle with the device forward state substituted (debug aid;
+tools/grad_check_activations.py compares the gradients w.r.t. the raw conv outputs layer by layer)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))

@@ -1,3 +1,5 @@
+"""Clock stamps of the first tiles of a weight-gradient kernel (URIR_WGRAD_TRACE): producer / issuer barrier waits per iteration.
+usage: python tools/trace_wgrad.py [prof_conv case, default wgrad_full]"""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
