@@ -74,12 +74,13 @@ template <int HS>
 __device__ __forceinline__ void hl_halve_head(float (&v)[16], int lane) {
     if (HS >= 1) URIR_HALVE(v, 16, 8, 16)
     if (HS >= 2) URIR_HALVE(v, 8, 4, 8)
+    if (HS >= 3) URIR_HALVE(v, 4, 2, 4)
 }
 template <int HS>
 __device__ __forceinline__ float hl_halve_tail(float* v, int lane) {     // v holds 16 >> HS partial sums
     if (HS < 1) URIR_HALVE(v, 16, 8, 16)
     if (HS < 2) URIR_HALVE(v, 8, 4, 8)
-    URIR_HALVE(v, 4, 2, 4)
+    if (HS < 3) URIR_HALVE(v, 4, 2, 4)
     URIR_HALVE(v, 2, 1, 2)
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
@@ -277,7 +278,10 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         // each of them two tile times to finish it
         const int eg = warp >= 8 ? ((warp - 8) >> 2) + 1 : 0;      // group eg drains the tiles with it % NG == eg
         const int quarter = warp & 3;
-        constexpr int HS = BLOCK_N >= 128 ? 2 : BLOCK_N >= 64 ? 1 : 0;   // halving steps per tile (see hl_halve_head)
+        // halving steps per tile (see hl_halve_head): the partial sums kept across tiles cost 2 * (BLOCK_N / 16) * (16 >> HS)
+        // registers; at 64 of them the 64- and 128-column variants hit the 168-register cap and spilled 130 - 150 bytes per
+        // thread inside the tile loop (ptxas -v), so they halve once more per tile (32 registers) at 8 more shuffles per block
+        constexpr int HS = BLOCK_N >= 128 ? 3 : (BLOCK_N >= 64 || NG == 4) ? 2 : 0;     // (four groups: 96-register cap)
         constexpr int PART = 16 >> HS;                       // partial sums kept per 16-column block
         constexpr int NB = BLOCK_N / 16;
         float acc1[NB * PART], acc2[NB * PART];
