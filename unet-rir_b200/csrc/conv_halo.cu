@@ -252,8 +252,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
                 if (trm && kc == p.nchunks - 1) p.trace[it * 8 + 2] = clock64();
                 fence_after_sync();
                 uint32_t b_lo = w_lo + ((kc * B_BYTES) >> 4);
-                // (a fully unrolled 9-tap variant with register-resident offsets was measured: faster in isolation
-                // for the 64-channel dgrad, no gain at step level, more spills -- kept simple)
+                // (a fully unrolled 9-tap variant with register-resident offsets was measured twice -- round 1 and again
+                // after the epilogue's spills were gone: per kernel within +-8 % either way, no gain at step level (3.67 vs
+                // 3.65 ms). URIR_HALO_TRACE shows why: ~84 cycles per MMA on an issuer against 44 on the tensor pipe, but the
+                // two issuers together already match the pipe; what stretches a tile from 913 to 1174 cycles is the epilogue
+                // warps sharing the issuers' schedulers -- kept simple)
                 for (int t = 0; t < (p.debug == 3 ? 0 : p.ntaps); ++t) {
                     const uint32_t a_t = a_lo + (((uint32_t)__shfl_sync(0xffffffffu, (int)p.tap_row[t], 0) * ROW_BYTES) >> 4);
 #pragma unroll
