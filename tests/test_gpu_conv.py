@@ -253,9 +253,10 @@ THIN_CASES = [(2, 16, 32, 3), (3, 24, 48, 6), (1, 8, 16, 6), (2, 144, 160, 6), (
 
 @pytest.mark.parametrize("case", THIN_CASES, ids=[str(c) for c in THIN_CASES])
 def test_thin_channel_tensor_core_kernels(case):
-    """conv_thin.cu: the 2-channel stem (fprop, wgrad) and head (dgrad, wgrad) as one small tcgen05 GEMM per
-    128-pixel tile over an im2col tile built in shared memory from the fp32 thin tensor. The thin operand
-    is rounded to bf16 on chip, so the oracle gets the bf16-rounded tensor."""
+    """conv_thin.cu: the 2-channel stem (fprop, wgrad) and head (dgrad, wgrad). 3x3 and 6x6 kernels run on the warp-MMA
+    kernels (A fragments straight from the bf16 halo patch / ldmatrix.trans of the wide tile), other tap counts (the 5x5
+    case) on the tcgen05 kernels that build an im2col tile in shared memory. The thin operand is rounded to bf16 on chip,
+    so the oracle gets the bf16-rounded tensor."""
     N, H, W, k = case
     g = torch.Generator().manual_seed(21 + k)
     # ---- stem: x fp32 [.,2] -> 32 channels

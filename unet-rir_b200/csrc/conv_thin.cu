@@ -1,4 +1,4 @@
-// Thin-channel convolutions on tcgen05 (sm_100a): the layers where ONE side has 2 channels --
+// Thin-channel convolutions (sm_100a): the layers where ONE side has 2 channels --
 //   * the stem  enc1.down : Conv2D(2 -> F0, k)            (dl_models/u_net.py:269-276 on the spectrogram)
 //   * the head            : Conv2D(F0 -> 2, 6x6) + sigmoid (dl_models/u_net.py:247-249)
 // A (tap, 2-channel) im2col row of the thin tensor is only 18 / 72 values, so instead of running taps as
@@ -10,6 +10,10 @@
 // Both read / write the wide bf16 tensor exactly once (HBM-bound, ~94 MB per launch at B = 64) and share the
 // same shared-memory image of the im2col tile: 128 rows (pixels) of 128 B, 16-byte chunks XOR-swizzled with
 // (row % 8) -- consumed K-major by thin_gemm and MN-major by thin_wgrad.
+// Two implementations of each product live here. The tcgen05 kernels described above (thin_gemm_kernel, thin_wgrad_kernel) take
+// any tap count up to 36; the square 3x3 / 6x6 kernels of the model go to the warp-level MMA kernels further down
+// (thin_expand_mma_kernel, thin_wgrad_mma_kernel), which never stage im2col rows and are 1.5 - 2.6x faster on these
+// HBM-bound launches (URIR_THIN_UMMA=1 selects the tcgen05 ones for everything).
 // The head's forward (wide -> thin) lives in conv_head.cu.
 #include <stdlib.h>
 #include <atomic>
