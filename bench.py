@@ -72,6 +72,7 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
         self._stop, self._thread, self.proc, self.source = threading.Event(), None, None, None
+        self.period = float(os.environ.get("URIR_CLOCK_PERIOD_MS", "10")) * 1e-3
 
     def _nvml_loop(self, nv, h):
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
@@ -83,7 +84,7 @@ class ClockSampler:
                 self.reasons.update(k for k, b in bits.items() if r & b)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.period)
 
     def _smi_loop(self):
         for line in self.proc.stdout:
