@@ -129,6 +129,11 @@ int urir_conv2d_fprop(const urir_conv_desc* d, const void* x, const void* w_ck, 
  * sum is the bias gradient of the layer that produced x. */
 int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck, const void* w_kc,
                       const float* bias, void* dx, float* stats, void* stream);
+/* The same call when only the bias gradient is wanted from `stats`: stats[0..C) receives the channel sums of dx, stats[C..2C)
+ * is left unspecified (the halo-tile kernels then skip the sums of squares: their epilogue is the bound on the 64-channel
+ * input gradients of the net; other kernels still write both halves). Same buffer size, same zeroing rule. */
+int urir_conv2d_dgrad_sums(const urir_conv_desc* d, const void* dy, const void* w_ck, const void* w_kc,
+                           const float* bias, void* dx, float* stats, void* stream);
 /* Conv2D / Conv2DTranspose weight gradient: dw[R,S,C,K] fp32 (HWIO) = sum x * dy; overwritten.
  * For a Conv2DTranspose layer pass x = gradient of its output, dy = its input. */
 int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw,

@@ -347,6 +347,13 @@ def test_halo_tile_fprop_dgrad(case):
     U.run_dgrad(d, dyg, w_ck, w_kc, None, dx, dstats)
     assert U.rel_l2(dx.float(), gx) < BF16_TOL
     assert U.max_abs(dstats[:Cc], gx.sum(dim=(0, 1, 2))) < 2e-3 * float(gx.abs().sum(dim=(0, 1, 2)).max())
+    # the sums-only entry point (bias gradients): same dx, same channel sums, second half of the buffer untouched
+    dx2 = torch.empty_like(dx)
+    sums = torch.zeros(2 * Cc, device="cuda")
+    U.run_dgrad_sums(d, dyg, w_ck, w_kc, None, dx2, sums)
+    assert torch.equal(dx2, dx)
+    assert U.max_abs(sums[:Cc], gx.sum(dim=(0, 1, 2))) < 2e-3 * float(gx.abs().sum(dim=(0, 1, 2)).max())
+    assert float(sums[Cc:].abs().max()) == 0.0
 
 
 WGRAD_HALO_CASES = [

@@ -48,5 +48,10 @@ def run_dgrad(d, dy, w_ck, w_kc, bias, dx, stats=None):
            L.ptr(stats))
 
 
+def run_dgrad_sums(d, dy, w_ck, w_kc, bias, dx, stats):
+    L.call("conv2d_dgrad_sums", C.byref(d), dy.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), L.ptr(bias), dx.data_ptr(),
+           L.ptr(stats))
+
+
 def run_wgrad(d, x, dy, dw):
     L.call("conv2d_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr())

@@ -87,7 +87,8 @@ def run(which, reps=int(os.environ.get("PROF_REPS", "3"))):
         elif op == "fprop":
             L.call("conv2d_fprop", C.byref(d), x.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, dy.data_ptr(), sp)
         else:
-            L.call("conv2d_dgrad", C.byref(d), dy.data_ptr(), w_ck.data_ptr(), w_kc.data_ptr(), None, x.data_ptr(), sp)
+            L.call("conv2d_dgrad_sums" if (sp is not None and os.environ.get("PROF_SUMS")) else "conv2d_dgrad", C.byref(d), dy.data_ptr(),
+                   w_ck.data_ptr(), w_kc.data_ptr(), None, x.data_ptr(), sp)
     inner = 10 if reps > 1 else 1      # back-to-back launches per timing: host launch latency must not count
     if reps > 1 and not os.environ.get("PROF_NO_GRAPH"):
         # the C-ABI call costs ~20-25 us of host time (ctypes + two tensor-map encodes + launch): kernels shorter than that

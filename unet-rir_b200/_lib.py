@@ -44,6 +44,7 @@ _PROTOS = {
     "urir_family_name": (C.c_char_p, [_i]),
     "urir_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_conv2d_dgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "urir_conv2d_dgrad_sums": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "urir_conv2d_wgrad": (_i, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "urir_conv_path": (_i, [C.POINTER(ConvDesc), _i]),
     "urir_set_pdl": (_i, [_i]),
@@ -164,7 +165,7 @@ def _conv_info(name, args):
     d = args[0]._obj if hasattr(args[0], "_obj") else None
     if not isinstance(d, ConvDesc):
         return {}
-    op = {"conv2d_fprop": 0, "conv2d_dgrad": 1, "conv2d_wgrad": 2, "conv2d_dgrad_up2": 3}[name]
+    op = {"conv2d_fprop": 0, "conv2d_dgrad": 1, "conv2d_dgrad_sums": 1, "conv2d_wgrad": 2, "conv2d_dgrad_up2": 3}[name]
     tc = int(load().urir_conv_path(C.byref(d), op))
     xs, ys = (4 if d.x_dtype == F32 else 2), (4 if d.y_dtype == F32 else 2)
     xb, yb = d.N * d.H * d.W * d.C * xs, d.N * d.P * d.Q * d.K * ys

@@ -18,6 +18,9 @@ int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
+// urir_conv2d_dgrad_sums: the statistics epilogue of the call in flight on this host thread needs channel sums only
+static thread_local bool g_sums_only = false;
+bool stats_sums_only() { return g_sums_only; }
 static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
     int v = g_pdl.load();
@@ -213,6 +216,14 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
     const bool use_tc = d->impl == URIR_IMPL_TC || (d->impl == URIR_IMPL_AUTO && tc_ok && !env_force_simt());
     return use_tc ? fam(URIR_FAM_IGEMM, conv_dgrad_igemm(d, dy, w_ck, bias, dx, stats, st))
                   : fam(URIR_FAM_SIMT, conv_dgrad_simt_dispatch(d, dy, w_kc, bias, dx, stats, st, w_ck));
+}
+
+int urir_conv2d_dgrad_sums(const urir_conv_desc* d, const void* dy, const void* w_ck, const void* w_kc, const float* bias,
+                           void* dx, float* stats, void* stream) {
+    urir::g_sums_only = true;
+    const int rc = urir_conv2d_dgrad(d, dy, w_ck, w_kc, bias, dx, stats, stream);
+    urir::g_sums_only = false;
+    return rc;
 }
 
 int urir_conv2d_wgrad(const urir_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {

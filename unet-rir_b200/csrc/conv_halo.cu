@@ -28,6 +28,7 @@ using namespace tc;
 
 int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, int swizzle_bytes);
+bool stats_sums_only();          // set around a urir_conv2d_dgrad_sums call (capi.cu)
 
 constexpr int HL_TH = 8, HL_TW = 16;          // output tile: 8 rows x 16 columns = 128 GEMM rows
 constexpr int HL_MAX_STAGES = 8;
@@ -52,6 +53,7 @@ struct HaloParams {
     int n_total;
     int bias_mod;               // bias index = GEMM-N column % bias_mod (the 4 parity classes of an up-2 layer share it)
     int accumulate;             // out += result (fp32 add before the bf16 rounding)
+    int sums_only;              // statistics: channel sums only, no sums of squares (urir_conv2d_dgrad_sums: bias gradients)
     int grp_off[16];            // output element offset of every 32-column group of GEMM-N (channel / parity placement)
     unsigned int* gate;         // deterministic mode: CTAs commit their statistics in blockIdx order (urir_common.cuh)
     int debug;                  // URIR_HALO_DEBUG: 1 no global stores, 2 no epilogue math/stores, 3 no MMAs, 4 no TMA loads (timing experiments)
@@ -292,7 +294,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         for (int i = 0; i < NB * PART; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
         const int row = quarter * 32 + lane;
         const int ih = row & 7, iw = row >> 3;
-        const bool want_stats = p.stats != nullptr;
+        const bool want_stats = p.stats != nullptr, want_sq = want_stats && !p.sums_only;
         int it = eg;
         for (int tile = blockIdx.x + eg * gridDim.x; tile < p.total_tiles; tile += NG * gridDim.x, it += NG) {
             const int acc = it & 3;
@@ -398,9 +400,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) { if (!valid) v[j] = 0.f; q[j] = v[j] * v[j]; }
                         hl_halve_head<HS>(v, lane);
-                        hl_halve_head<HS>(q, lane);
 #pragma unroll
-                        for (int j = 0; j < PART; ++j) { acc1[b * PART + j] += v[j]; acc2[b * PART + j] += q[j]; }
+                        for (int j = 0; j < PART; ++j) acc1[b * PART + j] += v[j];
+                        if (want_sq) {
+                            hl_halve_head<HS>(q, lane);
+#pragma unroll
+                            for (int j = 0; j < PART; ++j) acc2[b * PART + j] += q[j];
+                        }
                     }
                 }
             }
@@ -439,7 +445,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     __syncthreads();
     if (p.stats) {
         gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
-        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (p.sums_only ? 1 : 2) * BLOCK_N; i += blockDim.x) {
             const int which = i / BLOCK_N, col = i % BLOCK_N;
             if (n_tile * BLOCK_N + col < p.n_total)
                 atomicAdd(p.stats + which * p.n_total + n_tile * BLOCK_N + col, sstats[i]);
@@ -532,7 +538,7 @@ int conv_halo(const urir_conv_desc* d, int op, const void* a, const void* w, con
     if (p.stages < 2) return fail(URIR_ERR_UNSUP, "halo conv: weights of %d bytes leave no room for the activation ring", p.w_bytes);
     p.o_sn = (long long)d->H * d->W * o_ld; p.o_sh = (long long)d->W * o_ld; p.o_sw = o_ld; p.o_off = o_coff;
     p.bias = bias; p.stats = stats; p.out = (__nv_bfloat16*)out; p.n_total = ng; p.gate = stats ? next_gate() : nullptr;
-    p.bias_mod = ng; p.accumulate = 0;
+    p.bias_mod = ng; p.accumulate = 0; p.sums_only = stats_sums_only() ? 1 : 0;
     for (int g = 0; g < 16; ++g) p.grp_off[g] = 32 * g;
     { const char* e = getenv("URIR_HALO_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr; }
     { const char* e = getenv("URIR_HALO_DEBUG"); p.debug = e ? atoi(e) : 0; }

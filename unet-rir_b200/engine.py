@@ -339,7 +339,8 @@ class UNetEngine:
                    self.param[name + ".b"].data_ptr() if bias else None, dx.ptr())
             return
         w_ck, w_kc = self._w(name)
-        L.call("conv2d_dgrad", C.byref(d), dy.ptr(), w_ck, w_kc,
+        # every caller reads only the channel SUMS of the statistics (bias gradients): the sums-only entry point
+        L.call("conv2d_dgrad" if stats is None else "conv2d_dgrad_sums", C.byref(d), dy.ptr(), w_ck, w_kc,
                self.param[name + ".b"].data_ptr() if bias else None, dx.ptr(),
                None if stats is None else stats.data_ptr())
 
