@@ -131,7 +131,7 @@ int urir_conv2d_dgrad(const urir_conv_desc* d, const void* dy, const void* w_ck,
                       const float* bias, void* dx, float* stats, void* stream);
 /* The same call when only the bias gradient is wanted from `stats`: stats[0..C) receives the channel sums of dx, stats[C..2C)
  * is left unspecified (the halo-tile kernels then skip the sums of squares: their epilogue is the bound on the 64-channel
- * input gradients of the net; other kernels still write both halves). Same buffer size, same zeroing rule. */
+ * input gradients of the net; the deep-layer kernel likewise; the remaining kernels still write both halves). Same buffer size, same zeroing rule. */
 int urir_conv2d_dgrad_sums(const urir_conv_desc* d, const void* dy, const void* w_ck, const void* w_kc,
                            const float* bias, void* dx, float* stats, void* stream);
 /* Conv2D / Conv2DTranspose weight gradient: dw[R,S,C,K] fp32 (HWIO) = sum x * dy; overwritten.

@@ -530,6 +530,11 @@ def test_deep_kernel_fprop_dgrad(case):
     assert U.rel_l2(dx.float(), gx) < BF16_TOL, U.rel_l2(dx.float(), gx)
     assert U.max_abs(dstats[:Cc], gx.sum(dim=(0, 1, 2))) < 2e-3 * float(gx.abs().sum(dim=(0, 1, 2)).max())
     assert L.family_calls()["deep"] - fam0 == 2
+    # sums-only statistics (bias gradients): same dx, same sums, no sums of squares
+    dx2, sums = torch.empty_like(dx), torch.zeros(2 * Cc, device="cuda")
+    U.run_dgrad_sums(d, dyg, w_ck, w_kc, None, dx2, sums)
+    assert torch.equal(dx2, dx) and float(sums[Cc:].abs().max()) == 0.0
+    assert U.max_abs(sums[:Cc], gx.sum(dim=(0, 1, 2))) < 2e-3 * float(gx.abs().sum(dim=(0, 1, 2)).max())
 
 
 def test_deep_kernel_concat_slices_and_relu():

@@ -35,6 +35,7 @@ using namespace tc;
 
 int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, int swizzle_bytes);
+bool stats_sums_only();          // set around a urir_conv2d_dgrad_sums call (capi.cu)
 
 constexpr int DP_BN = 128;               // GEMM-N tile (one tcgen05.mma N)
 constexpr int DP_BK = 64;                // GEMM-K chunk: 64 bf16 = one 128-byte swizzled row
@@ -59,6 +60,7 @@ struct DeepParams {
     short tb[4][4], te[4][4];   // [class][plane]: range of the tap list that plane contributes to that class
     long long o_cls[4];         // output element offset of class c (its parity position)
     int accumulate;             // out += result
+    int sums_only;              // statistics: channel sums only (urir_conv2d_dgrad_sums)
     int a_slots, a_stage_bytes, w_stages;
     int tmax;                   // M tiles per round (<= DP_TMAX, < a_slots: the other slots run ahead)
     int tmem_cols;
@@ -323,7 +325,7 @@ conv_deep_kernel(const __grid_constant__ DeepMaps maps, const __grid_constant__ 
 #pragma unroll
                             for (int q = 0; q < 16; ++q) q2[q] = v[q] * v[q];
                             const float s1 = dp_colsum16(v, lane);
-                            const float s2 = dp_colsum16(q2, lane);
+                            const float s2 = p.sums_only ? 0.f : dp_colsum16(q2, lane);
                             if ((lane & 1) == 0) {          // this lane owns (warp, column): plain accumulation, fixed order
                                 const int col = c0 + half * 16 + dp_col_of_lane(lane);
                                 my_stats[col] += s1;
@@ -341,7 +343,7 @@ conv_deep_kernel(const __grid_constant__ DeepMaps maps, const __grid_constant__ 
     __syncthreads();
     if (p.stats) {
         gate_enter(p.gate, cta_linear(), threadIdx.x == 0, 0, blockDim.x);
-        for (int i = threadIdx.x; i < 2 * DP_BN; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (p.sums_only ? 1 : 2) * DP_BN; i += blockDim.x) {
             const int which = i / DP_BN, col = i % DP_BN;
             float v = 0.f;
 #pragma unroll
@@ -459,7 +461,7 @@ int conv_deep(const urir_conv_desc* d, int op, const void* a, const void* w, con
     p.nplanes = (s2 && op == 0) ? 4 : 1;
     p.nclasses = (s2 && op == 1) ? 4 : 1;
     p.nchunks = kg / DP_BK; p.ntaps = 9;
-    p.accumulate = d->accumulate;
+    p.accumulate = d->accumulate; p.sums_only = stats_sums_only() ? 1 : 0;
     // tap list, grouped by (class, plane)
     int job_taps[16];
     {
