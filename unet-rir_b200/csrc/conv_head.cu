@@ -108,6 +108,23 @@ head_fprop_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             mbar_wait(full_bar + stage, phase);
             fence_after_sync();
             const uint32_t a_st = a0 + ((stage * p.stage_bytes) >> 4);
+            if (p.R == 6) {
+                // the model's 6x6 head: 48 MMAs per region issued as straight-line code with immediate offsets. This warp is
+                // the only issuer, and the rolled loops below cost ~84 cycles per MMA against 44 on the tensor pipe
+                // (measured on the halo kernel's identical issue sequence, profiles/r02_halo_trace.txt)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t ad = ((uint64_t)d_hi << 32) | (a_st + (uint32_t)((((4 * q + r) * HF_ROWB) >> 4) + 2 * kk));
+                            const uint64_t bd = ((uint64_t)d_hi << 32) | (b0 + (uint32_t)(((r * 1024) >> 4) + 2 * kk));
+                            umma_bf16_elect(tm0 + acc * 64 + q * 16, ad, bd, IDESC, (r | kk) != 0);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
 #pragma unroll 1
@@ -121,6 +138,7 @@ head_fprop_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                         umma_bf16_elect(tm0 + acc * 64 + q * 16, ad, bd, IDESC, (r | kk) != 0);
                     }
                 }
+            }
             }
             umma_commit_elect(empty_bar + stage);
             umma_commit_elect(tfull_bar + acc);
